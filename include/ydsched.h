@@ -1,0 +1,230 @@
+/*
+ * ydsched.h -- C ABI of the B200-native yadcc scheduler hot path.
+ *
+ * This is the drop-in boundary: every entry point below
+ * replaces one public method of the reference's `TaskDispatcher`
+ * (yadcc/scheduler/task_dispatcher.h:120-181), which in production is called
+ * only from `SchedulerServiceImpl` (yadcc/scheduler/scheduler_service_impl.cc:
+ * 171,180,235,255,292,308,315).  No C++ or torch types cross this boundary:
+ * plain pointers, sizes and fixed-width integers only.
+ *
+ * Three shared libraries export exactly this ABI:
+ *   - yadcc_b200/libydsched.so        host C++ + sm_100a CUDA kernels (the product)
+ *   - oracle/libydoracle.so           CPU restatement of the algorithm (test infra)
+ *   - oracle/_ref/libydref.so         the reference's own .cc files compiled
+ *                                     verbatim against oracle/shim (test infra)
+ *
+ * Conventions (mirroring the reference, task_dispatcher.h / .cc):
+ *   - Time never comes from a wall clock inside the library.  Every call that
+ *     reads `flare::ReadCoarseSteadyClock()` in the reference takes `now_ns`
+ *     (steady-clock nanoseconds) here, so event streams replay bit-exactly.
+ *   - The 1 Hz `OnExpirationTimer` (task_dispatcher.cc:81-82,498-536) is driven
+ *     by the caller through `yd_on_expiration_timer`.
+ *   - Calls on one handle must be externally serialised, which is what the
+ *     reference's single `allocation_lock_` (task_dispatcher.h:289) does.
+ *   - Errors are values (status codes / counts / flags).  Programmer errors
+ *     (NULL handle, invariant violations the reference FLARE_CHECKs) abort.
+ *   - All strings are borrowed for the duration of the call only.
+ *   - Integer field widths are the wire widths of yadcc/api/scheduler.proto
+ *     (HeartbeatRequest :64-120, all uint32 except memory which is uint64).
+ */
+#ifndef YDSCHED_H_
+#define YDSCHED_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define YD_ABI_VERSION 1u
+
+/* WaitStatus numeric values are the reference's (task_dispatcher.h:41-44);
+ * 2 is the success arm of flare::Expected<TaskAllocation, WaitStatus>. */
+#define YD_STATUS_ENVIRONMENT_NOT_FOUND 0u
+#define YD_STATUS_TIMEOUT 1u
+#define YD_STATUS_GRANTED 2u
+
+/* ServantPriority, yadcc/api/scheduler.proto:38-48. */
+#define YD_PRIORITY_UNKNOWN 0
+#define YD_PRIORITY_DEDICATED 1
+#define YD_PRIORITY_USER 2
+
+#define YD_REQ_FLAG_PREFETCH 1u /* `prefetching` arg, task_dispatcher.cc:96 */
+
+#define YD_NO_SERVANT 0xffffffffu
+#define YD_IP_NONE 0u /* requestor IP that was never seen as a servant IP */
+
+typedef struct yd_sched yd_sched; /* opaque; one per scheduler process */
+
+typedef struct yd_config {
+  uint32_t abi_version; /* must be YD_ABI_VERSION */
+  int32_t device;       /* CUDA device ordinal; ignored by the CPU oracles */
+  /* gflag --servant_min_memory_for_accepting_new_task (task_dispatcher.cc:35-38),
+   * parsed with yd_parse_size; NULL means the reference default "10G". */
+  const char* servant_min_memory_for_accepting_new_task;
+  /* Solver selection for the CUDA backend: 0 = auto, 1 = row-scan solver,
+   * 2 = slot-stream solver.  Ignored by the oracles. */
+  uint32_t solver;
+  uint32_t reserved;
+} yd_config;
+
+/* ServantPersonality, task_dispatcher.h:80-116, as filled in by
+ * SchedulerServiceImpl::Heartbeat (scheduler_service_impl.cc:124-170). */
+typedef struct yd_servant {
+  int32_t version;                   /* int in the reference (h:84) */
+  int32_t priority;                  /* YD_PRIORITY_* (h:112) */
+  int32_t not_accepting_task_reason; /* NotAcceptingTaskReason (h:115) */
+  uint32_t num_envs;
+  const char* observed_location; /* "ip:port" as seen by the scheduler (h:87) */
+  const char* reported_location; /* "ip:port" as reported (h:91) */
+  const char* const* env_digests; /* num_envs compiler digests (h:94) */
+  uint32_t num_processors;        /* h:97 */
+  uint32_t current_load;          /* h:100 */
+  uint32_t max_tasks;             /* h:109 ("capacity" on the wire) */
+  uint32_t reserved;
+  uint64_t total_memory_in_bytes;     /* h:103 */
+  uint64_t memory_available_in_bytes; /* h:106 */
+} yd_servant;
+
+/* One WaitForStartingNewTask call (task_dispatcher.cc:93-96): the
+ * TaskPersonality (h:48-66) with its two strings replaced by interned ids,
+ * plus `expires_in` and `prefetching`.  24 bytes. */
+typedef struct yd_task_req {
+  uint32_t env_id;       /* yd_intern_env(env_desc.compiler_digest) */
+  uint32_t min_version;  /* TaskPersonality::min_version */
+  uint32_t requestor_ip; /* yd_intern_ip(TaskPersonality::requestor_ip) */
+  uint32_t flags;        /* YD_REQ_FLAG_* */
+  int64_t expires_in_ns; /* lease length, counted from the grant */
+} yd_task_req;
+
+/* Outcome of one decision: flare::Expected<TaskAllocation, WaitStatus>
+ * (task_dispatcher.h:69-77).  16 bytes. */
+typedef struct yd_grant {
+  uint64_t task_id;       /* valid iff status == YD_STATUS_GRANTED */
+  uint32_t servant_index; /* registry position at grant time, else YD_NO_SERVANT */
+  uint32_t status;        /* YD_STATUS_* */
+} yd_grant;
+
+/* RunningTask, yadcc/api/scheduler.proto:233-238. */
+typedef struct yd_running_task {
+  uint64_t servant_task_id;
+  uint64_t task_grant_id;
+  const char* servant_location;
+  const char* task_digest;
+} yd_running_task;
+
+/* Per-servant bookkeeping exposed for parity checks; the same numbers the
+ * reference publishes through DumpInternals (task_dispatcher.cc:548-584). */
+typedef struct yd_servant_state {
+  uint64_t running_tasks;       /* ServantDesc::running_tasks (h:189) */
+  uint64_t ever_assigned_tasks; /* ServantDesc::ever_assigned_tasks (h:190) */
+  uint64_t capacity_available;  /* GetCapacityAvailable (cc:283-313) */
+  int64_t expires_at_ns;        /* ServantDesc::expires_at (h:187) */
+} yd_servant_state;
+
+/* Device-side timing of the most recent yd_wait_for_starting_new_tasks call
+ * (CUDA backend; the oracles fill host wall-clock into solve_ms only). */
+typedef struct yd_solve_stats {
+  double total_ms;   /* H2D + all kernels + D2H, CUDA events on the solve stream */
+  double solve_ms;   /* the assignment kernel alone */
+  double prep_ms;    /* slot-table / classification kernels */
+  double final_ms;   /* task-id scan + grant/lease write-out */
+  uint64_t decisions;
+  uint64_t granted;
+  uint32_t kernel_launches; /* kernels launched by the call */
+  uint32_t solver;          /* which solver ran (1 row-scan, 2 slot-stream) */
+  uint64_t h2d_bytes;
+  uint64_t d2h_bytes;
+} yd_solve_stats;
+
+/* ---- lifecycle --------------------------------------------------------- */
+
+/* TaskDispatcher::TaskDispatcher (cc:78-88).  Returns NULL if the config is
+ * malformed or (CUDA backend) no usable sm_100 device is present -- the CUDA
+ * backend never falls back to a CPU path. */
+yd_sched* yd_create(const yd_config* cfg);
+/* TaskDispatcher::~TaskDispatcher (cc:90-92). */
+void yd_destroy(yd_sched* s);
+/* "cuda-sm100a", "oracle-port" or "reference". */
+const char* yd_backend_name(void);
+/* yadcc::TryParseSize (yadcc/common/parse_size.cc:25-45).  Returns 1 and
+ * stores the byte count on success, 0 when the reference returns nullopt. */
+int yd_parse_size(const char* text, uint64_t* out_bytes);
+
+/* ---- string interning (host only) --------------------------------------- */
+
+/* Map a compiler digest / requestor IP string to a small id that yd_task_req
+ * carries.  Ids are stable for the life of the handle.  yd_intern_ip returns
+ * ids >= 1 (YD_IP_NONE is never returned, it is for callers that know the
+ * requestor cannot be a servant). */
+uint32_t yd_intern_env(yd_sched* s, const char* digest, size_t len);
+uint32_t yd_intern_ip(yd_sched* s, const char* ip, size_t len);
+
+/* ---- servant maintenance ------------------------------------------------ */
+
+/* TaskDispatcher::KeepServantAlive (cc:190-220). */
+void yd_keep_servant_alive(yd_sched* s, int64_t now_ns, const yd_servant* servant,
+                           int64_t expires_in_ns);
+/* TaskDispatcher::NotifyServantRunningTasks (cc:222-277).  Writes the unknown
+ * task-grant ids (request order preserved) to unknown_out (capacity n) and
+ * returns how many there are. */
+size_t yd_notify_servant_running_tasks(yd_sched* s, const char* servant_location,
+                                       const yd_running_task* tasks, size_t n,
+                                       uint64_t* unknown_out);
+/* TaskDispatcher::GetRunningTasks (cc:279-281).  Returns the total count; at
+ * most `cap` entries are written.  Returned strings are owned by the library
+ * and valid until the next call that mutates the handle. */
+size_t yd_get_running_tasks(yd_sched* s, yd_running_task* out, size_t cap);
+/* TaskDispatcher::OnExpirationTimer (cc:498-536), fired by the caller at 1 Hz. */
+void yd_on_expiration_timer(yd_sched* s, int64_t now_ns);
+
+/* ---- task-grant allocation (THE HOT PATH) ------------------------------- */
+
+/* n sequential TaskDispatcher::WaitForStartingNewTask calls (cc:93-140), in
+ * array order, each with timeout == now (the zero-wait discipline
+ * SchedulerServiceImpl itself uses for every request after the first,
+ * scheduler_service_impl.cc:236-240).  out[i] is what call i would have
+ * returned had the calls been issued one after another. */
+void yd_wait_for_starting_new_tasks(yd_sched* s, int64_t now_ns, const yd_task_req* reqs,
+                                    size_t n, yd_grant* out);
+/* n TaskDispatcher::KeepTaskAlive calls (cc:142-165); ok_out[i] is the bool. */
+void yd_keep_task_alive(yd_sched* s, int64_t now_ns, const uint64_t* task_ids, size_t n,
+                        int64_t new_expires_in_ns, uint8_t* ok_out);
+/* n TaskDispatcher::FreeTask calls (cc:167-188), one per id (so an unknown id
+ * only skips itself, as in SchedulerServiceImpl::FreeTask, :307-309). */
+void yd_free_tasks(yd_sched* s, const uint64_t* task_ids, size_t n);
+
+/* ---- introspection ------------------------------------------------------ */
+
+size_t yd_num_servants(yd_sched* s);
+/* observed_location of registry position `servant_index`; NULL if out of
+ * range.  Valid until the next mutating call. */
+const char* yd_servant_location(yd_sched* s, uint32_t servant_index);
+/* Fills up to `cap` entries in registry order; returns the servant count. */
+size_t yd_get_servant_state(yd_sched* s, yd_servant_state* out, size_t cap);
+/* Next task id that would be handed out (TaskRegistry::next_task_id, h:218). */
+uint64_t yd_next_task_id(yd_sched* s);
+/* Number of live (granted, not freed/swept) task leases, zombies included. */
+uint64_t yd_num_tasks(yd_sched* s);
+/* DumpInternals summary (cc:538-614) as JSON: servants_up, running_tasks,
+ * capacity, capacity_available, capacity_unavailable.  Returns the length
+ * needed (excluding NUL); writes at most cap bytes. */
+size_t yd_dump_internals_json(yd_sched* s, char* buf, size_t cap);
+/* Returns 1 and fills *out if a solve has run on this handle. */
+int yd_last_solve_stats(yd_sched* s, yd_solve_stats* out);
+
+/* ---- host staging buffers ----------------------------------------------- */
+
+/* Page-locked host memory for request / grant arrays, so that the copies in
+ * yd_wait_for_starting_new_tasks are single DMA transfers.  The CPU oracles
+ * implement these with malloc/free. */
+void* yd_alloc_host(size_t bytes);
+void yd_free_host(void* p);
+
+#ifdef __cplusplus
+} /* extern "C" */
+#endif
+
+#endif /* YDSCHED_H_ */

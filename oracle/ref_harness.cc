@@ -1,0 +1,283 @@
+// ref_harness.cc -- TEST INFRASTRUCTURE.  Puts the reference's own
+// `yadcc::scheduler::TaskDispatcher` (compiled verbatim from /root/reference
+// by oracle/Makefile against oracle/shim) behind the C ABI of
+// include/ydsched.h, so parity tests and the bench's reference arm can drive
+// it with exactly the event streams the CUDA backend sees.
+//
+// Nothing in yadcc_b200/ may link or load this; only tests/, bench.py's
+// reference/cpu_baseline legs and __graft_entry__.smoke() do.
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "flare/base/chrono.h"
+#include "flare/fiber/timer.h"
+#include "gflags/gflags.h"
+#include "yadcc/common/parse_size.h"
+#include "yadcc/scheduler/task_dispatcher.h"
+
+#include "ydsched.h"
+
+DECLARE_string(servant_min_memory_for_accepting_new_task);
+
+using yadcc::scheduler::RunningTask;
+using yadcc::scheduler::ServantPersonality;
+using yadcc::scheduler::TaskDispatcher;
+using yadcc::scheduler::TaskPersonality;
+using yadcc::scheduler::WaitStatus;
+
+// Granted friendship by the FRIEND_TEST shim (oracle/shim/gtest/gtest_prod.h).
+struct yd_oracle_access {
+  static auto& Servants(TaskDispatcher& d) { return d.servants_.servants; }
+  static auto& Tasks(TaskDispatcher& d) { return d.tasks_.tasks; }
+  static std::uint64_t NextTaskId(TaskDispatcher& d) { return d.tasks_.next_task_id.load(); }
+  static std::size_t Capacity(TaskDispatcher& d, std::size_t i) {
+    return d.GetCapacityAvailable(*d.servants_.servants[i]);
+  }
+  static Json::Value Dump(TaskDispatcher& d) { return d.DumpInternals(); }
+  static std::uint64_t TimerId(TaskDispatcher& d) { return d.expiration_timer_; }
+};
+
+namespace {
+
+inline void SetNow(std::int64_t now_ns) {
+  yd_shim::g_now = std::chrono::steady_clock::time_point(std::chrono::nanoseconds(now_ns));
+}
+
+}  // namespace
+
+struct yd_sched {
+  std::unique_ptr<TaskDispatcher> d;
+  std::vector<std::string> envs;  // env_id -> digest
+  std::unordered_map<std::string, std::uint32_t> env_ids;
+  std::vector<std::string> ips;  // ip id -> text (id 0 = "")
+  std::unordered_map<std::string, std::uint32_t> ip_ids;
+  std::vector<RunningTask> running_cache;  // backing store for yd_get_running_tasks
+  std::string location_cache;
+  yd_solve_stats stats{};
+  bool have_stats = false;
+};
+
+extern "C" {
+
+const char* yd_backend_name(void) { return "reference"; }
+
+int yd_parse_size(const char* text, uint64_t* out_bytes) {
+  if (!text || !*text) return 0;  // reference calls .back() on the string: UB on empty
+  auto v = yadcc::TryParseSize(text);
+  if (!v) return 0;
+  *out_bytes = *v;
+  return 1;
+}
+
+yd_sched* yd_create(const yd_config* cfg) {
+  if (!cfg || cfg->abi_version != YD_ABI_VERSION) return nullptr;
+  const char* mm = cfg->servant_min_memory_for_accepting_new_task;
+  uint64_t parsed;
+  if (mm && !yd_parse_size(mm, &parsed)) return nullptr;  // reference would FLARE_CHECK
+  FLAGS_servant_min_memory_for_accepting_new_task = mm ? mm : "10G";
+  auto* s = new yd_sched;
+  s->d = std::make_unique<TaskDispatcher>();
+  s->ips.emplace_back();  // id 0 == YD_IP_NONE == ""
+  s->ip_ids.emplace("", 0);
+  return s;
+}
+
+void yd_destroy(yd_sched* s) { delete s; }
+
+uint32_t yd_intern_env(yd_sched* s, const char* digest, size_t len) {
+  std::string k(digest, len);
+  auto it = s->env_ids.find(k);
+  if (it != s->env_ids.end()) return it->second;
+  auto id = static_cast<std::uint32_t>(s->envs.size());
+  s->envs.push_back(k);
+  s->env_ids.emplace(std::move(k), id);
+  return id;
+}
+
+uint32_t yd_intern_ip(yd_sched* s, const char* ip, size_t len) {
+  std::string k(ip, len);
+  auto it = s->ip_ids.find(k);
+  if (it != s->ip_ids.end()) return it->second;
+  auto id = static_cast<std::uint32_t>(s->ips.size());
+  s->ips.push_back(k);
+  s->ip_ids.emplace(std::move(k), id);
+  return id;
+}
+
+void yd_keep_servant_alive(yd_sched* s, int64_t now_ns, const yd_servant* sv,
+                           int64_t expires_in_ns) {
+  SetNow(now_ns);
+  ServantPersonality p;
+  p.version = sv->version;
+  p.observed_location = sv->observed_location;
+  p.reported_location = sv->reported_location;
+  for (std::uint32_t i = 0; i != sv->num_envs; ++i) {
+    p.environments.emplace_back().set_compiler_digest(sv->env_digests[i]);
+  }
+  p.num_processors = sv->num_processors;
+  p.current_load = sv->current_load;
+  p.total_memory_in_bytes = sv->total_memory_in_bytes;
+  p.memory_available_in_bytes = sv->memory_available_in_bytes;
+  p.max_tasks = sv->max_tasks;
+  p.priority = static_cast<yadcc::scheduler::ServantPriority>(sv->priority);
+  p.not_accepting_task_reason =
+      static_cast<yadcc::scheduler::NotAcceptingTaskReason>(sv->not_accepting_task_reason);
+  s->d->KeepServantAlive(p, std::chrono::nanoseconds(expires_in_ns));
+}
+
+size_t yd_notify_servant_running_tasks(yd_sched* s, const char* servant_location,
+                                       const yd_running_task* tasks, size_t n,
+                                       uint64_t* unknown_out) {
+  std::vector<RunningTask> v(n);
+  for (size_t i = 0; i != n; ++i) {
+    v[i].set_servant_task_id(tasks[i].servant_task_id);
+    v[i].set_task_grant_id(tasks[i].task_grant_id);
+    v[i].set_servant_location(tasks[i].servant_location ? tasks[i].servant_location : "");
+    v[i].set_task_digest(tasks[i].task_digest ? tasks[i].task_digest : "");
+  }
+  auto unknown = s->d->NotifyServantRunningTasks(servant_location, std::move(v));
+  for (size_t i = 0; i != unknown.size(); ++i) unknown_out[i] = unknown[i];
+  return unknown.size();
+}
+
+size_t yd_get_running_tasks(yd_sched* s, yd_running_task* out, size_t cap) {
+  s->running_cache = s->d->GetRunningTasks();
+  for (size_t i = 0; i < s->running_cache.size() && i < cap; ++i) {
+    auto&& t = s->running_cache[i];
+    out[i] = yd_running_task{t.servant_task_id(), t.task_grant_id(), t.servant_location().c_str(),
+                             t.task_digest().c_str()};
+  }
+  return s->running_cache.size();
+}
+
+void yd_on_expiration_timer(yd_sched* s, int64_t now_ns) {
+  SetNow(now_ns);
+  // Fire the callback this dispatcher registered with fiber::SetTimer.
+  auto it = yd_shim::g_timers.find(yd_oracle_access::TimerId(*s->d));
+  if (it == yd_shim::g_timers.end()) std::abort();
+  it->second();
+}
+
+void yd_wait_for_starting_new_tasks(yd_sched* s, int64_t now_ns, const yd_task_req* reqs, size_t n,
+                                    yd_grant* out) {
+  SetNow(now_ns);
+  auto timeout = yd_shim::g_now;  // zero-wait
+  // Personalities are materialised before the clock starts: in production they
+  // arrive as strings from the RPC layer, so building them is not the
+  // dispatcher's cost.
+  std::vector<TaskPersonality> tp(n);
+  for (size_t i = 0; i != n; ++i) {
+    tp[i].requestor_ip = reqs[i].requestor_ip < s->ips.size() ? s->ips[reqs[i].requestor_ip] : "";
+    tp[i].min_version = reqs[i].min_version;
+    if (reqs[i].env_id < s->envs.size()) {
+      tp[i].env_desc.set_compiler_digest(s->envs[reqs[i].env_id]);
+    } else {
+      tp[i].env_desc.set_compiler_digest("<unknown env id>");
+    }
+  }
+  std::vector<std::string> locations(n);
+  std::uint64_t granted = 0;
+  auto t0 = std::chrono::steady_clock::now();
+  for (size_t i = 0; i != n; ++i) {
+    auto r = s->d->WaitForStartingNewTask(tp[i], std::chrono::nanoseconds(reqs[i].expires_in_ns),
+                                          timeout, (reqs[i].flags & YD_REQ_FLAG_PREFETCH) != 0);
+    if (r) {
+      out[i].task_id = r->task_id;
+      out[i].status = YD_STATUS_GRANTED;
+      locations[i] = std::move(r->servant_location);
+      ++granted;
+    } else {
+      out[i].task_id = 0;
+      out[i].servant_index = YD_NO_SERVANT;
+      out[i].status = static_cast<std::uint32_t>(r.error());
+    }
+  }
+  auto t1 = std::chrono::steady_clock::now();
+  // Resolve locations to registry positions outside the timed loop.  The
+  // registry cannot change during the batch (no heartbeat / timer in between).
+  std::unordered_map<std::string, std::uint32_t> pos;
+  auto& sv = yd_oracle_access::Servants(*s->d);
+  for (std::uint32_t i = 0; i != sv.size(); ++i) {
+    pos.emplace(sv[i]->personality.observed_location, i);  // first wins, like find_if
+  }
+  for (size_t i = 0; i != n; ++i) {
+    if (out[i].status == YD_STATUS_GRANTED) out[i].servant_index = pos.at(locations[i]);
+  }
+  s->stats = yd_solve_stats{};
+  s->stats.solve_ms = s->stats.total_ms = std::chrono::duration<double, std::milli>(t1 - t0).count();
+  s->stats.decisions = n;
+  s->stats.granted = granted;
+  s->have_stats = true;
+}
+
+void yd_keep_task_alive(yd_sched* s, int64_t now_ns, const uint64_t* ids, size_t n,
+                        int64_t new_expires_in_ns, uint8_t* ok_out) {
+  SetNow(now_ns);
+  for (size_t i = 0; i != n; ++i) {
+    ok_out[i] = s->d->KeepTaskAlive(ids[i], std::chrono::nanoseconds(new_expires_in_ns));
+  }
+}
+
+void yd_free_tasks(yd_sched* s, const uint64_t* ids, size_t n) {
+  for (size_t i = 0; i != n; ++i) s->d->FreeTask(ids[i]);
+}
+
+size_t yd_num_servants(yd_sched* s) { return yd_oracle_access::Servants(*s->d).size(); }
+
+const char* yd_servant_location(yd_sched* s, uint32_t idx) {
+  auto& sv = yd_oracle_access::Servants(*s->d);
+  if (idx >= sv.size()) return nullptr;
+  s->location_cache = sv[idx]->personality.observed_location;
+  return s->location_cache.c_str();
+}
+
+size_t yd_get_servant_state(yd_sched* s, yd_servant_state* out, size_t cap) {
+  auto& sv = yd_oracle_access::Servants(*s->d);
+  for (size_t i = 0; i < sv.size() && i < cap; ++i) {
+    out[i].running_tasks = sv[i]->running_tasks;
+    out[i].ever_assigned_tasks = sv[i]->ever_assigned_tasks;
+    out[i].capacity_available = yd_oracle_access::Capacity(*s->d, i);
+    out[i].expires_at_ns =
+        std::chrono::duration_cast<std::chrono::nanoseconds>(sv[i]->expires_at.time_since_epoch())
+            .count();
+  }
+  return sv.size();
+}
+
+uint64_t yd_next_task_id(yd_sched* s) { return yd_oracle_access::NextTaskId(*s->d); }
+uint64_t yd_num_tasks(yd_sched* s) { return yd_oracle_access::Tasks(*s->d).size(); }
+
+size_t yd_dump_internals_json(yd_sched* s, char* buf, size_t cap) {
+  auto j = yd_oracle_access::Dump(*s->d);
+  char tmp[512];
+  int len = std::snprintf(
+      tmp, sizeof(tmp),
+      "{\"servants_up\":%llu,\"running_tasks\":%llu,\"capacity\":%llu,"
+      "\"capacity_available\":%llu,\"capacity_unavailable\":%llu}",
+      (unsigned long long)j["servants_up"].asUInt64(),
+      (unsigned long long)j["running_tasks"].asUInt64(),
+      (unsigned long long)j["capacity"].asUInt64(),
+      (unsigned long long)j["capacity_available"].asUInt64(),
+      (unsigned long long)j["capacity_unavailable"].asUInt64());
+  if (buf && cap) {
+    std::snprintf(buf, cap, "%s", tmp);
+  }
+  return static_cast<size_t>(len);
+}
+
+int yd_last_solve_stats(yd_sched* s, yd_solve_stats* out) {
+  if (!s->have_stats) return 0;
+  *out = s->stats;
+  return 1;
+}
+
+void* yd_alloc_host(size_t bytes) { return std::malloc(bytes ? bytes : 1); }
+void yd_free_host(void* p) { std::free(p); }
+
+}  // extern "C"

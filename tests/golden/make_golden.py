@@ -1,0 +1,38 @@
+"""Regenerates tests/golden/* from the REFERENCE ITSELF (oracle/_ref/libydref.so,
+i.e. /root/reference's task_dispatcher.cc compiled verbatim).  Run in the dev
+container:  python tests/golden/make_golden.py
+"""
+import json
+import sys
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parents[2]
+sys.path.insert(0, str(ROOT))
+from yadcc_b200 import TaskDispatcher  # noqa: E402
+from yadcc_b200 import streams as S  # noqa: E402
+
+REF = ROOT / "oracle" / "_ref" / "libydref.so"
+NAMES = ["cfg1", "cfg2-mod-small", "cfg2-random-small", "cfg3-small", "cfg3-mod-small"] + [f"fuzz-{i}" for i in range(40)]
+BIG = ["cfg2-mod", "cfg2-random"]  # full BASELINE sizes; ~2-4 s each on the reference
+
+
+def main():
+    out = {"generator": "oracle/_ref/libydref.so (reference compiled verbatim)", "streams": {}}
+    for name in NAMES + BIG:
+        d = TaskDispatcher(str(REF))
+        r = S.Replayer(d)
+        tr = r.run(S.named_stream(name, d))
+        out["streams"][name] = {"sha256": S.trace_digest(tr), "decisions": r.decisions, "granted": r.granted}
+        if name == "cfg1":
+            g = tr[0]
+            np.savez_compressed(Path(__file__).parent / "cfg1_reference.npz", status=g["status"],
+                                task_id=g["task_id"], servant_index=g["servant_index"])
+        d.close()
+        print(name, out["streams"][name])
+    (Path(__file__).parent / "digests.json").write_text(json.dumps(out, indent=1) + "\n")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,154 @@
+"""ctypes declarations for include/ydsched.h (one-to-one, same order)."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+import numpy as np
+
+ABI_VERSION = 1
+
+STATUS_ENVIRONMENT_NOT_FOUND = 0  # WaitStatus::EnvironmentNotFound, task_dispatcher.h:42
+STATUS_TIMEOUT = 1  # WaitStatus::Timeout, task_dispatcher.h:43
+STATUS_GRANTED = 2
+
+PRIORITY_UNKNOWN = 0  # scheduler.proto:38-48
+PRIORITY_DEDICATED = 1
+PRIORITY_USER = 2
+
+REQ_FLAG_PREFETCH = 1
+NO_SERVANT = 0xFFFFFFFF
+
+# struct yd_task_req (24 B) / yd_grant (16 B) / yd_servant_state (32 B)
+REQ_DTYPE = np.dtype(
+    [
+        ("env_id", "<u4"),
+        ("min_version", "<u4"),
+        ("requestor_ip", "<u4"),
+        ("flags", "<u4"),
+        ("expires_in_ns", "<i8"),
+    ]
+)
+GRANT_DTYPE = np.dtype([("task_id", "<u8"), ("servant_index", "<u4"), ("status", "<u4")])
+SERVANT_STATE_DTYPE = np.dtype(
+    [
+        ("running_tasks", "<u8"),
+        ("ever_assigned_tasks", "<u8"),
+        ("capacity_available", "<u8"),
+        ("expires_at_ns", "<i8"),
+    ]
+)
+assert REQ_DTYPE.itemsize == 24 and GRANT_DTYPE.itemsize == 16
+
+
+class yd_config(C.Structure):
+    _fields_ = [
+        ("abi_version", C.c_uint32),
+        ("device", C.c_int32),
+        ("servant_min_memory_for_accepting_new_task", C.c_char_p),
+        ("solver", C.c_uint32),
+        ("reserved", C.c_uint32),
+    ]
+
+
+class yd_servant(C.Structure):
+    _fields_ = [
+        ("version", C.c_int32),
+        ("priority", C.c_int32),
+        ("not_accepting_task_reason", C.c_int32),
+        ("num_envs", C.c_uint32),
+        ("observed_location", C.c_char_p),
+        ("reported_location", C.c_char_p),
+        ("env_digests", C.POINTER(C.c_char_p)),
+        ("num_processors", C.c_uint32),
+        ("current_load", C.c_uint32),
+        ("max_tasks", C.c_uint32),
+        ("reserved", C.c_uint32),
+        ("total_memory_in_bytes", C.c_uint64),
+        ("memory_available_in_bytes", C.c_uint64),
+    ]
+
+
+class yd_running_task(C.Structure):
+    _fields_ = [
+        ("servant_task_id", C.c_uint64),
+        ("task_grant_id", C.c_uint64),
+        ("servant_location", C.c_char_p),
+        ("task_digest", C.c_char_p),
+    ]
+
+
+class yd_solve_stats(C.Structure):
+    _fields_ = [
+        ("total_ms", C.c_double),
+        ("solve_ms", C.c_double),
+        ("prep_ms", C.c_double),
+        ("final_ms", C.c_double),
+        ("decisions", C.c_uint64),
+        ("granted", C.c_uint64),
+        ("kernel_launches", C.c_uint32),
+        ("solver", C.c_uint32),
+        ("h2d_bytes", C.c_uint64),
+        ("d2h_bytes", C.c_uint64),
+    ]
+
+
+# Every symbol include/ydsched.h declares: (name, restype, argtypes).
+_P = C.c_void_p
+PROTOTYPES = [
+    ("yd_create", _P, [C.POINTER(yd_config)]),
+    ("yd_destroy", None, [_P]),
+    ("yd_backend_name", C.c_char_p, []),
+    ("yd_parse_size", C.c_int, [C.c_char_p, C.POINTER(C.c_uint64)]),
+    ("yd_intern_env", C.c_uint32, [_P, C.c_char_p, C.c_size_t]),
+    ("yd_intern_ip", C.c_uint32, [_P, C.c_char_p, C.c_size_t]),
+    ("yd_keep_servant_alive", None, [_P, C.c_int64, C.POINTER(yd_servant), C.c_int64]),
+    (
+        "yd_notify_servant_running_tasks",
+        C.c_size_t,
+        [_P, C.c_char_p, C.POINTER(yd_running_task), C.c_size_t, C.POINTER(C.c_uint64)],
+    ),
+    ("yd_get_running_tasks", C.c_size_t, [_P, C.POINTER(yd_running_task), C.c_size_t]),
+    ("yd_on_expiration_timer", None, [_P, C.c_int64]),
+    ("yd_wait_for_starting_new_tasks", None, [_P, C.c_int64, _P, C.c_size_t, _P]),
+    ("yd_keep_task_alive", None, [_P, C.c_int64, _P, C.c_size_t, C.c_int64, _P]),
+    ("yd_free_tasks", None, [_P, _P, C.c_size_t]),
+    ("yd_num_servants", C.c_size_t, [_P]),
+    ("yd_servant_location", C.c_char_p, [_P, C.c_uint32]),
+    ("yd_get_servant_state", C.c_size_t, [_P, _P, C.c_size_t]),
+    ("yd_next_task_id", C.c_uint64, [_P]),
+    ("yd_num_tasks", C.c_uint64, [_P]),
+    ("yd_dump_internals_json", C.c_size_t, [_P, C.c_char_p, C.c_size_t]),
+    ("yd_last_solve_stats", C.c_int, [_P, C.POINTER(yd_solve_stats)]),
+    ("yd_alloc_host", _P, [C.c_size_t]),
+    ("yd_free_host", None, [_P]),
+]
+
+
+def cuda_library_path() -> Path:
+    """In-tree location of the product library (built by `make` / build())."""
+    env = os.environ.get("YDSCHED_LIBRARY")
+    return Path(env) if env else Path(__file__).resolve().parent / "libydsched.so"
+
+
+def load_library(path: os.PathLike | str | None = None) -> C.CDLL:
+    """dlopen a library exporting the ydsched C ABI and attach prototypes.
+
+    With no argument this loads the CUDA product library and fails loudly if it
+    has not been built -- there is no CPU fallback on the product path.
+    """
+    p = Path(path) if path is not None else cuda_library_path()
+    if not p.exists():
+        raise FileNotFoundError(
+            f"{p} not found: build it first (`make -C {Path(__file__).resolve().parent.parent}` "
+            "or `python -c 'import __graft_entry__ as g; g.build()'`). "
+            "yadcc_b200 has no CPU fallback."
+        )
+    lib = C.CDLL(str(p), mode=C.RTLD_LOCAL)
+    for name, restype, argtypes in PROTOTYPES:
+        fn = getattr(lib, name)  # AttributeError if the symbol is missing
+        fn.restype = restype
+        fn.argtypes = argtypes
+    lib._yd_path = str(p)
+    return lib

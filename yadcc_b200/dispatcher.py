@@ -1,0 +1,329 @@
+"""Host-side mirror of the reference's `TaskDispatcher` public interface.
+
+Same method names, argument meaning and error behaviour as
+yadcc/scheduler/task_dispatcher.h:120-181, so that tests read like the
+reference's own (yadcc/scheduler/task_dispatcher_test.cc).  Differences, all
+forced by deterministic replay:
+
+* time is an explicit ``now`` argument (seconds, float or int nanoseconds via
+  ``now_ns=``) instead of ``flare::ReadCoarseSteadyClock()``;
+* the 1 Hz expiration timer is fired by the caller (``on_expiration_timer``);
+* ``wait_for_starting_new_task`` never blocks: ``timeout`` is accepted for
+  signature parity but a request that finds no free servant fails with
+  ``WaitStatus.Timeout`` at once (zero-wait discipline);
+* the batched ``wait_for_starting_new_tasks`` is the hot path: *n* sequential
+  calls in one C-ABI crossing.
+
+All computation happens behind the C ABI (include/ydsched.h); this file only
+marshals arguments.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import enum
+import json
+from dataclasses import dataclass, field
+from typing import Iterable, Sequence
+
+import numpy as np
+
+from . import _abi
+from ._abi import GRANT_DTYPE, REQ_DTYPE, SERVANT_STATE_DTYPE
+
+
+class WaitStatus(enum.IntEnum):
+    """task_dispatcher.h:41-44."""
+
+    EnvironmentNotFound = 0
+    Timeout = 1
+
+
+@dataclass
+class TaskAllocation:
+    """task_dispatcher.h:69-77."""
+
+    task_id: int
+    servant_location: str
+
+
+@dataclass
+class Servant:
+    """ServantPersonality, task_dispatcher.h:80-116."""
+
+    observed_location: str
+    reported_location: str | None = None
+    environments: Sequence[str] = ()
+    version: int = 0
+    num_processors: int = 0
+    current_load: int = 0
+    total_memory_in_bytes: int = 0
+    memory_available_in_bytes: int = 0
+    max_tasks: int = 0
+    priority: int = _abi.PRIORITY_USER
+    not_accepting_task_reason: int = 0
+
+
+@dataclass
+class RunningTask:
+    """yadcc/api/scheduler.proto:233-238."""
+
+    servant_task_id: int = 0
+    task_grant_id: int = 0
+    servant_location: str = ""
+    task_digest: str = ""
+
+
+def _ns(seconds: float | int) -> int:
+    return int(round(seconds * 1_000_000_000))
+
+
+class TaskDispatcher:
+    def __init__(
+        self,
+        library=None,
+        *,
+        device: int = 0,
+        servant_min_memory_for_accepting_new_task: str | None = None,
+        solver: int = 0,
+    ):
+        self._lib = library if isinstance(library, C.CDLL) else _abi.load_library(library)
+        cfg = _abi.yd_config(
+            abi_version=_abi.ABI_VERSION,
+            device=device,
+            servant_min_memory_for_accepting_new_task=(
+                servant_min_memory_for_accepting_new_task.encode()
+                if servant_min_memory_for_accepting_new_task is not None
+                else None
+            ),
+            solver=solver,
+        )
+        self._h = self._lib.yd_create(C.byref(cfg))
+        if not self._h:
+            raise RuntimeError(
+                f"yd_create failed for backend {self.backend!r} ({self._lib._yd_path}); "
+                "the CUDA backend needs an sm_100 GPU and never falls back to the CPU"
+            )
+        self._env_ids: dict[str, int] = {}
+        self._ip_ids: dict[str, int] = {}
+
+    # -- lifecycle ---------------------------------------------------------
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            self._lib.yd_destroy(self._h)
+            self._h = None
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    @property
+    def backend(self) -> str:
+        return self._lib.yd_backend_name().decode()
+
+    # -- interning ---------------------------------------------------------
+    def intern_env(self, compiler_digest: str) -> int:
+        v = self._env_ids.get(compiler_digest)
+        if v is None:
+            b = compiler_digest.encode()
+            v = self._env_ids[compiler_digest] = self._lib.yd_intern_env(self._h, b, len(b))
+        return v
+
+    def intern_ip(self, requestor_ip: str) -> int:
+        v = self._ip_ids.get(requestor_ip)
+        if v is None:
+            b = requestor_ip.encode()
+            v = self._ip_ids[requestor_ip] = self._lib.yd_intern_ip(self._h, b, len(b))
+        return v
+
+    # -- task servant allocation (task_dispatcher.h:126-155) ----------------
+    def wait_for_starting_new_tasks(
+        self, reqs: np.ndarray, now: float = 0.0, *, now_ns: int | None = None, out: np.ndarray | None = None
+    ) -> np.ndarray:
+        """n sequential WaitForStartingNewTask calls (cc:93-140); THE hot path.
+
+        `reqs` is a REQ_DTYPE array (ideally in memory from `alloc_requests`);
+        returns a GRANT_DTYPE array.
+        """
+        assert reqs.dtype == REQ_DTYPE and reqs.flags.c_contiguous
+        n = reqs.shape[0]
+        if out is None:
+            out = np.empty(n, dtype=GRANT_DTYPE)
+        assert out.dtype == GRANT_DTYPE and out.shape[0] >= n and out.flags.c_contiguous
+        self._lib.yd_wait_for_starting_new_tasks(
+            self._h, now_ns if now_ns is not None else _ns(now), reqs.ctypes.data, n, out.ctypes.data
+        )
+        return out[:n]
+
+    def make_requests(
+        self,
+        n: int,
+        compiler_digest: str | Sequence[str],
+        requestor_ip: str | Sequence[str],
+        min_version: int | Sequence[int] = 0,
+        expires_in: float = 15.0,
+        prefetching: bool = False,
+        pinned: bool = False,
+    ) -> np.ndarray:
+        r = self.alloc_requests(n) if pinned else np.zeros(n, dtype=REQ_DTYPE)
+        if isinstance(compiler_digest, str):
+            r["env_id"] = self.intern_env(compiler_digest)
+        else:
+            r["env_id"] = [self.intern_env(d) for d in compiler_digest]
+        if isinstance(requestor_ip, str):
+            r["requestor_ip"] = self.intern_ip(requestor_ip)
+        else:
+            r["requestor_ip"] = [self.intern_ip(d) for d in requestor_ip]
+        r["min_version"] = min_version
+        r["flags"] = _abi.REQ_FLAG_PREFETCH if prefetching else 0
+        r["expires_in_ns"] = _ns(expires_in)
+        return r
+
+    def wait_for_starting_new_task(
+        self,
+        requestor_ip: str,
+        min_version: int,
+        compiler_digest: str,
+        expires_in: float,
+        timeout: float | None = None,
+        prefetching: bool = False,
+        *,
+        now: float = 0.0,
+    ) -> TaskAllocation | WaitStatus:
+        """One decision; returns a TaskAllocation or the WaitStatus error."""
+        del timeout  # zero-wait discipline
+        r = self.make_requests(1, compiler_digest, requestor_ip, min_version, expires_in, prefetching)
+        g = self.wait_for_starting_new_tasks(r, now)[0]
+        if g["status"] == _abi.STATUS_GRANTED:
+            return TaskAllocation(int(g["task_id"]), self.servant_location(int(g["servant_index"])))
+        return WaitStatus(int(g["status"]))
+
+    def keep_task_alive(self, task_id: int, new_expires_in: float, *, now: float = 0.0) -> bool:
+        return bool(self.keep_tasks_alive([task_id], new_expires_in, now=now)[0])
+
+    def keep_tasks_alive(self, task_ids: Iterable[int], new_expires_in: float, *, now: float = 0.0) -> np.ndarray:
+        ids = np.ascontiguousarray(np.asarray(list(task_ids) if not isinstance(task_ids, np.ndarray) else task_ids, dtype=np.uint64))
+        ok = np.zeros(ids.shape[0], dtype=np.uint8)
+        self._lib.yd_keep_task_alive(self._h, _ns(now), ids.ctypes.data, ids.shape[0], _ns(new_expires_in), ok.ctypes.data)
+        return ok.astype(bool)
+
+    def free_task(self, task_id: int) -> None:
+        self.free_tasks([task_id])
+
+    def free_tasks(self, task_ids: Iterable[int]) -> None:
+        ids = np.ascontiguousarray(np.asarray(list(task_ids) if not isinstance(task_ids, np.ndarray) else task_ids, dtype=np.uint64))
+        self._lib.yd_free_tasks(self._h, ids.ctypes.data, ids.shape[0])
+
+    # -- servant maintenance (task_dispatcher.h:157-181) -------------------
+    def keep_servant_alive(self, servant: Servant, expires_in: float, *, now: float = 0.0) -> None:
+        envs = [e.encode() for e in servant.environments]
+        arr = (C.c_char_p * max(len(envs), 1))(*envs)
+        rep = servant.reported_location if servant.reported_location is not None else servant.observed_location
+        sv = _abi.yd_servant(
+            version=servant.version,
+            priority=servant.priority,
+            not_accepting_task_reason=servant.not_accepting_task_reason,
+            num_envs=len(envs),
+            observed_location=servant.observed_location.encode(),
+            reported_location=rep.encode(),
+            env_digests=arr,
+            num_processors=servant.num_processors,
+            current_load=servant.current_load,
+            max_tasks=servant.max_tasks,
+            total_memory_in_bytes=servant.total_memory_in_bytes,
+            memory_available_in_bytes=servant.memory_available_in_bytes,
+        )
+        self._lib.yd_keep_servant_alive(self._h, _ns(now), C.byref(sv), _ns(expires_in))
+
+    def notify_servant_running_tasks(self, servant_location: str, tasks: Sequence[RunningTask]) -> list[int]:
+        n = len(tasks)
+        arr = (_abi.yd_running_task * max(n, 1))()
+        keep = []
+        for i, t in enumerate(tasks):
+            loc, dig = t.servant_location.encode(), t.task_digest.encode()
+            keep.append((loc, dig))
+            arr[i] = _abi.yd_running_task(t.servant_task_id, t.task_grant_id, loc, dig)
+        out = (C.c_uint64 * max(n, 1))()
+        k = self._lib.yd_notify_servant_running_tasks(self._h, servant_location.encode(), arr, n, out)
+        return [int(out[i]) for i in range(k)]
+
+    def get_running_tasks(self) -> list[RunningTask]:
+        n = self._lib.yd_get_running_tasks(self._h, None, 0)
+        arr = (_abi.yd_running_task * max(n, 1))()
+        n = min(n, self._lib.yd_get_running_tasks(self._h, arr, n))
+        return [
+            RunningTask(
+                int(arr[i].servant_task_id),
+                int(arr[i].task_grant_id),
+                (arr[i].servant_location or b"").decode(),
+                (arr[i].task_digest or b"").decode(),
+            )
+            for i in range(n)
+        ]
+
+    def on_expiration_timer(self, *, now: float) -> None:
+        self._lib.yd_on_expiration_timer(self._h, _ns(now))
+
+    # -- introspection -----------------------------------------------------
+    def num_servants(self) -> int:
+        return int(self._lib.yd_num_servants(self._h))
+
+    def servant_location(self, index: int) -> str | None:
+        v = self._lib.yd_servant_location(self._h, index)
+        return v.decode() if v is not None else None
+
+    def servant_state(self) -> np.ndarray:
+        n = self.num_servants()
+        out = np.zeros(n, dtype=SERVANT_STATE_DTYPE)
+        self._lib.yd_get_servant_state(self._h, out.ctypes.data, n)
+        return out
+
+    def next_task_id(self) -> int:
+        return int(self._lib.yd_next_task_id(self._h))
+
+    def num_tasks(self) -> int:
+        return int(self._lib.yd_num_tasks(self._h))
+
+    def dump_internals(self) -> dict:
+        buf = C.create_string_buffer(4096)
+        self._lib.yd_dump_internals_json(self._h, buf, len(buf))
+        return json.loads(buf.value.decode())
+
+    def last_solve_stats(self) -> dict | None:
+        st = _abi.yd_solve_stats()
+        if not self._lib.yd_last_solve_stats(self._h, C.byref(st)):
+            return None
+        return {k: getattr(st, k) for k, _ in st._fields_}
+
+    def parse_size(self, text: str) -> int | None:
+        v = C.c_uint64()
+        return int(v.value) if self._lib.yd_parse_size(text.encode(), C.byref(v)) else None
+
+    # -- pinned staging ----------------------------------------------------
+    def _alloc(self, n: int, dtype: np.dtype) -> np.ndarray:
+        nbytes = max(n, 1) * dtype.itemsize
+        p = self._lib.yd_alloc_host(nbytes)
+        if not p:
+            raise MemoryError("yd_alloc_host failed")
+        buf = (C.c_char * nbytes).from_address(p)
+        arr = np.frombuffer(buf, dtype=dtype, count=n)
+        lib = self._lib
+        # keep the allocation alive as long as the array; free it afterwards
+        import weakref
+
+        weakref.finalize(buf, lib.yd_free_host, p)
+        arr[...] = np.zeros((), dtype=dtype)
+        return arr
+
+    def alloc_requests(self, n: int) -> np.ndarray:
+        return self._alloc(n, REQ_DTYPE)
+
+    def alloc_grants(self, n: int) -> np.ndarray:
+        return self._alloc(n, GRANT_DTYPE)
