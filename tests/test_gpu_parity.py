@@ -1,0 +1,134 @@
+"""Parity of the CUDA backend (through the C ABI) against the CPU checkers and
+the committed golden vectors generated from the reference.  Bit-exact: statuses,
+task ids, servant indices, per-servant bookkeeping, unknown-id lists."""
+import json
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from conftest import REF_LIB
+from golden_cases import ALL_CASES
+from yadcc_b200 import streams as S
+from yadcc_b200 import STATUS_GRANTED
+
+pytestmark = pytest.mark.gpu
+GOLDEN = Path(__file__).parent / "golden"
+
+
+@pytest.mark.parametrize("case", ALL_CASES, ids=lambda f: f.__name__)
+def test_reference_golden_cases_on_cuda(make_dispatcher, case):
+    case(make_dispatcher("cuda"))
+
+
+def _parity(make_dispatcher, name_or_builder, kinds=("port",)):
+    traces = {}
+    for kind in ("cuda",) + tuple(kinds):
+        d = make_dispatcher(kind)
+        st = name_or_builder(d) if callable(name_or_builder) else S.named_stream(name_or_builder, d)
+        traces[kind] = S.Replayer(d, pinned=(kind == "cuda")).run(st)
+        d.close()
+    for kind in kinds:
+        assert S.traces_equal(traces["cuda"], traces[kind]), f"cuda vs {kind}: " + S.first_mismatch(
+            traces["cuda"], traces[kind]
+        )
+    return traces["cuda"]
+
+
+@pytest.mark.parametrize("seed", range(150))
+def test_fuzz_cuda_equals_oracle(make_dispatcher, seed):
+    kinds = ("port", "ref") if REF_LIB.exists() and seed % 3 == 0 else ("port",)
+    _parity(make_dispatcher, lambda d: S.fuzz_stream(d, seed, n_servants=8 + seed % 30, wide=(seed % 5 == 0)), kinds)
+
+
+@pytest.mark.parametrize("seed", range(1000, 1012))
+def test_fuzz_large_components(make_dispatcher, seed):
+    """Components above 256 servants use the multi-warp path of the solver."""
+    _parity(make_dispatcher, lambda d: S.fuzz_stream(d, seed, n_servants=300 + 150 * (seed % 4), n_events=40, max_batch=600))
+
+
+@pytest.mark.parametrize("name", ["cfg1", "cfg2-mod-small", "cfg2-random-small", "cfg3-small", "cfg3-mod-small"])
+def test_small_configs(make_dispatcher, name):
+    tr = _parity(make_dispatcher, name)
+    golden = json.loads((GOLDEN / "digests.json").read_text())["streams"]
+    assert S.trace_digest(tr) == golden[name]["sha256"]
+
+
+@pytest.mark.parametrize("name", ["cfg2-mod", "cfg2-random"])
+def test_full_size_configs_match_reference_digest(make_dispatcher, name):
+    """BASELINE.json configs[1] at full size against the digest produced by the
+    reference itself (tests/golden/make_golden.py)."""
+    d = make_dispatcher("cuda")
+    tr = S.Replayer(d, pinned=True).run(S.named_stream(name, d))
+    golden = json.loads((GOLDEN / "digests.json").read_text())["streams"][name]
+    g = tr[0]
+    assert int((g["status"] == STATUS_GRANTED).sum()) == golden["granted"]
+    assert S.trace_digest(tr) == golden["sha256"]
+
+
+def test_cfg1_vectors(make_dispatcher):
+    z = np.load(GOLDEN / "cfg1_reference.npz")
+    d = make_dispatcher("cuda")
+    g = S.Replayer(d).run(S.named_stream("cfg1", d))[0]
+    for k in ("status", "task_id", "servant_index"):
+        assert (g[k] == z[k]).all(), k
+
+
+def test_cfg3_million_properties(make_dispatcher):
+    """1 M x 4 k (BASELINE configs[2]) through size-independent properties: ids are
+    the grant ordinals, per-servant running counts equal the grants they received
+    and never exceed capacity, a second offer of the same queue grants nothing,
+    and the oracle agrees on a 50 k-request prefix."""
+    w = S.config3(1_000_000, 4000, 8)
+    d = make_dispatcher("cuda")
+    w.register(d)
+    reqs = w.build_requests(d)
+    g = d.wait_for_starting_new_tasks(reqs, 0.001)
+    ok = g["status"] == STATUS_GRANTED
+    n_ok = int(ok.sum())
+    assert (g["task_id"][ok] == np.arange(n_ok, dtype=np.uint64)).all()
+    st = d.servant_state()
+    counts = np.bincount(g["servant_index"][ok], minlength=len(st))
+    assert (st["running_tasks"] == counts).all()
+    assert (st["ever_assigned_tasks"] == counts).all()
+    assert d.num_tasks() == n_ok and d.next_task_id() == n_ok
+    # every servant that got work stayed within its capacity model
+    assert (st["running_tasks"][counts > 0] <= st["capacity_available"][counts > 0]).all()
+    # idempotence: the queue that timed out times out again (nothing was freed)
+    pend = reqs[g["status"] == 1]
+    g2 = d.wait_for_starting_new_tasks(pend[:200_000], 0.002)
+    assert not (g2["status"] == STATUS_GRANTED).any()
+    # prefix against the oracle
+    d2, o = make_dispatcher("cuda"), make_dispatcher("port")
+    for x in (d2, o):
+        w.register(x)
+    r2, ro = w.build_requests(d2)[:50_000], w.build_requests(o)[:50_000]
+    a, b = d2.wait_for_starting_new_tasks(r2, 0.001), o.wait_for_starting_new_tasks(ro, 0.001)
+    assert (a == b).all()
+
+
+def test_lease_ring_growth_and_window(make_dispatcher):
+    """More leases than the initial ring (65536) and a sliding window."""
+    traces = []
+    for kind in ("cuda", "port"):
+        d = make_dispatcher(kind)
+        w = S.config2(150_000, 2500, 4, variant="mod", max_tasks=64, nproc=128)
+        ev = [("hb", 0.0, sv, 30.0) for sv in w.servants]
+        ev += [("enqueue", w.build_requests(d)), ("solve", 0.001), ("free_frac", 7, 0.9), ("tick", 1.0),
+               ("enqueue", w.build_requests(d)), ("solve", 1.5), ("keepalive", 2.0, None, 1.0), ("tick", 20.0),
+               ("state",), ("free_frac", 8, 0.5), ("tick", 21.0), ("state",)]
+        traces.append(S.Replayer(d).run(S.Stream("ring", ev)))
+        d.close()
+    assert S.traces_equal(*traces), S.first_mismatch(*traces)
+
+
+def test_native_library_is_what_ran(make_dispatcher):
+    d = make_dispatcher("cuda")
+    assert d.backend == "cuda-sm100a"
+    w = S.config1()
+    w.register(d)
+    d.wait_for_starting_new_tasks(w.build_requests(d), 0.0)
+    st = d.last_solve_stats()
+    assert st["kernel_launches"] >= 4 and st["solver"] == 1 and st["decisions"] == 1000
+    maps = Path("/proc/self/maps").read_text()
+    assert "libydsched.so" in maps

@@ -1,0 +1,104 @@
+// common.cuh -- shared definitions for the sm_100a scheduler kernels.
+//
+// HBM layout (all arrays are structure-of-arrays, indexed by REGISTRY POSITION,
+// i.e. the reference's `servants_.servants` vector index, whose order is the
+// pick tie-break; task_dispatcher.h:195-197, .cc:444):
+//
+//   servant facts   nproc[S] load[S] max_tasks[S] flags[S] version[S]   (u32/i32, rewritten on heartbeat)
+//   servant state   run[S] (u32 running_tasks)  ever[S] (u64 ever_assigned_tasks)
+//   lease ring      t_exp[C] (i64 ns) t_srv[C] (u32 position) t_flags[C] (u32)
+//                   slot of task id = id & (C-1); window [lo, next) of ids is live-or-dead,
+//                   everything below lo is dead (TaskRegistry, task_dispatcher.h:217-220)
+//   per solve       reqs[n] (24 B AoS, as received)  res[n] (u32)  grants[n] (16 B AoS)
+//                   slot codes: one u32 per (servant, running_tasks value) -- the
+//                   (task x servant) cost-matrix column for that servant, see slots.cuh
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "ydsched.h"
+
+namespace yd {
+
+constexpr uint32_t kNone = 0xFFFFFFFFu;
+constexpr uint32_t kFull = 0xFFFFFFFFu;            // slot code of a servant that is not free
+constexpr uint32_t kResEnvNotFound = 0xFFFFFFFFu;  // res[] encodings (anything below is a position)
+constexpr uint32_t kResTimeout = 0xFFFFFFFEu;
+constexpr uint32_t kSelfBit = 0x80000000u;  // "tier 2": the requestor's own servant, last resort
+constexpr uint32_t kTierBit = 0x40000000u;  // tier 1: not (dedicated and below 50% of its cores)
+constexpr int kFracBits = 30;
+
+// Largest capacity for which floor(r * 2^30 / cap) orders r/cap exactly like the
+// reference's double division (distinct fractions with denominators <= 2^15
+// differ by >= 2^-30).  Above it the wide (64-bit key) path must be used.
+constexpr uint32_t kNarrowCapLimit = 32768;
+
+constexpr uint32_t kFlagDedicated = 1u;  // ServantPriority == DEDICATED
+constexpr uint32_t kFlagLowMem = 2u;     // total_memory != 0 && available < min_memory (cc:286-292)
+
+constexpr uint32_t kTaskAlive = 1u;
+constexpr uint32_t kTaskZombie = 2u;
+constexpr uint32_t kTaskPrefetch = 4u;
+
+struct Counters {
+  unsigned long long granted;   // grants of the last solve
+  unsigned long long alive;     // live leases (zombies included)
+  unsigned long long zombies;   // live leases marked zombie
+  unsigned long long min_live;  // smallest live id seen by the last tick (or ~0)
+  unsigned long long slots;     // slot-table entries of the last solve
+  unsigned long long pad[3];
+};
+
+struct ServantArrays {
+  uint32_t* nproc;
+  uint32_t* load;
+  uint32_t* max_tasks;
+  uint32_t* flags;
+  int32_t* version;
+  uint32_t* run;
+  unsigned long long* ever;
+};
+
+struct TaskRing {
+  long long* exp;
+  uint32_t* srv;
+  uint32_t* flags;
+  uint64_t mask;  // capacity - 1
+  uint64_t lo;    // ids below lo are dead
+  uint64_t next;  // next id to hand out
+};
+
+// GetCapacityAvailable (task_dispatcher.cc:283-313) for the not-low-memory case,
+// as a function of running_tasks r.  All operands are zero-extended u32, so the
+// reference's size_t/int64 juggling is plain signed arithmetic here.
+__host__ __device__ inline int64_t capacity_at(uint32_t max_tasks, uint32_t nproc, uint32_t load,
+                                               uint64_t r) {
+  int64_t foreign = (int64_t)load - (int64_t)r;
+  if (foreign < 0) foreign = 0;
+  int64_t avail = (int64_t)nproc - foreign;
+  if (avail < 0) avail = 0;
+  return avail < (int64_t)max_tasks ? avail : (int64_t)max_tasks;
+}
+
+// First running_tasks value at which the servant is no longer free
+// (`running_tasks >= GetCapacityAvailable`, cc:353).  Derivation in DESIGN.md:
+// with P = nproc, L = load, M = max_tasks the servant is free at r iff
+// !lowmem && P > L && r < min(M, P).
+__host__ __device__ inline uint32_t free_end(uint32_t max_tasks, uint32_t nproc, uint32_t load,
+                                             uint32_t flags) {
+  if ((flags & kFlagLowMem) || nproc <= load) return 0;
+  return max_tasks < nproc ? max_tasks : nproc;
+}
+
+}  // namespace yd
+
+#define YD_CUDA_CHECK(expr)                                                                   \
+  do {                                                                                        \
+    cudaError_t e__ = (expr);                                                                 \
+    if (e__ != cudaSuccess) {                                                                 \
+      fprintf(stderr, "ydsched: CUDA error %s at %s:%d: %s\n", cudaGetErrorName(e__), __FILE__, \
+              __LINE__, cudaGetErrorString(e__));                                             \
+      abort();                                                                                \
+    }                                                                                         \
+  } while (0)

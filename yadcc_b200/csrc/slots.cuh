@@ -1,0 +1,115 @@
+// slots.cuh -- the per-solve slot-code table: the cost column of every servant.
+//
+// For fixed heartbeat facts a servant's pick key depends only on its
+// running_tasks value r (UnsafeTryPickServantFor, task_dispatcher.cc:417-451;
+// dedicated predicate :405-409; GetCapacityAvailable :283-313):
+//
+//   key(s, r) = ( tier(s,r), double(r)/cap(s,r), registry position )
+//
+// and the servant is free on a prefix [run[s], free_end(s)) of r values.  One
+// u32 per (servant, r) encodes (tier, r/cap) order-exactly:
+//
+//   code = tier << 30 | floor(r * 2^30 / cap)        (cap <= 32768)
+//
+// Row s of the table holds the codes for r = run[s] .. run[s]+len-1 followed by
+// a kFull sentinel, so the solver advances a servant by bumping one index.
+// Algorithmic bytes: 4 B written per slot; facts read once (20 B per servant).
+#pragma once
+#include "common.cuh"
+
+namespace yd {
+
+// Single CTA: row lengths + exclusive scan -> row offsets.  S is a few thousand,
+// so one 1024-thread block with a running carry is launch-latency bound anyway.
+__global__ void __launch_bounds__(1024) k_slot_rows(uint32_t S, uint32_t n_requests,
+                                                    ServantArrays sv, uint32_t* __restrict__ row_off,
+                                                    uint32_t* __restrict__ row_len,
+                                                    Counters* __restrict__ counters) {
+  __shared__ uint32_t warp_sums[32];
+  __shared__ uint32_t carry_s;
+  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) carry_s = 0;
+  __syncthreads();
+  for (uint32_t base = 0; base < S; base += 1024) {
+    uint32_t s = base + tid;
+    uint32_t len = 0;
+    if (s < S) {
+      uint32_t end = free_end(sv.max_tasks[s], sv.nproc[s], sv.load[s], sv.flags[s]);
+      uint32_t r0 = sv.run[s];
+      len = end > r0 ? end - r0 : 0;
+      if (len > n_requests) len = n_requests;  // a servant cannot win more than n times
+      row_len[s] = len;
+    }
+    uint32_t v = len + 1;  // + sentinel
+    if (s >= S) v = 0;
+    // inclusive warp scan
+    uint32_t x = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      uint32_t y = __shfl_up_sync(0xffffffffu, x, d);
+      if (lane >= d) x += y;
+    }
+    if (lane == 31) warp_sums[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+      uint32_t w = warp_sums[lane];
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        uint32_t y = __shfl_up_sync(0xffffffffu, w, d);
+        if (lane >= d) w += y;
+      }
+      warp_sums[lane] = w;  // inclusive over warps
+    }
+    __syncthreads();
+    uint32_t carry = carry_s;
+    uint32_t excl = carry + (warp ? warp_sums[warp - 1] : 0) + x - v;
+    if (s < S) row_off[s] = excl;
+    __syncthreads();
+    if (tid == 1023) carry_s = carry + warp_sums[31];
+    __syncthreads();
+  }
+  if (tid == 0) {
+    row_off[S] = carry_s;
+    counters->slots = carry_s;
+  }
+}
+
+// One warp per servant row; lanes stride over r.  The u64 division is the only
+// expensive instruction and it is fully parallel here, off the solver's
+// dependency chain.
+template <bool kWide>
+__global__ void __launch_bounds__(256) k_slot_fill(uint32_t S, ServantArrays sv,
+                                                   const uint32_t* __restrict__ row_off,
+                                                   const uint32_t* __restrict__ row_len,
+                                                   uint32_t* __restrict__ codes,
+                                                   unsigned long long* __restrict__ codes_wide) {
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t s = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (s >= S) return;
+  const uint32_t len = row_len[s], off = row_off[s];
+  const uint32_t M = sv.max_tasks[s], P = sv.nproc[s], L = sv.load[s], fl = sv.flags[s];
+  const uint32_t r0 = sv.run[s];
+  for (uint32_t i = lane; i <= len; i += 32) {
+    if (i == len) {
+      if (kWide) codes_wide[off + i] = ~0ull; else codes[off + i] = kFull;
+      break;
+    }
+    uint64_t r = (uint64_t)r0 + i;
+    uint64_t cap = (uint64_t)capacity_at(M, P, L, r);  // > r by construction
+    bool tier0 = (fl & kFlagDedicated) && (r * 2 < (uint64_t)P);
+    if (kWide) {
+      // Any capacity: keep the reference's own key, the IEEE double r/cap
+      // (cc:440-441).  Non-negative doubles order like their bit patterns and
+      // bits 63 (sign) and 62 (u < 2) are free for self/tier.  (For cap > 2^26 distinct fractions
+      // can round to the same double; the reference then falls back to "first
+      // index wins", and so do we.)
+      double u = (double)r / (double)cap;
+      codes_wide[off + i] = (tier0 ? 0ull : (1ull << 62)) | (unsigned long long)__double_as_longlong(u);
+    } else {
+      uint32_t frac = (uint32_t)((r << kFracBits) / cap);
+      codes[off + i] = (tier0 ? 0u : kTierBit) | frac;
+    }
+  }
+}
+
+}  // namespace yd

@@ -1,0 +1,263 @@
+// tasks.cuh -- task-id assignment and the device-resident lease registry.
+//
+// TaskRegistry (task_dispatcher.h:199-220) is an unordered_map<id, TaskDesc> in
+// the reference; every sweep (UnsafeSweepZombiesOf cc:453-476, UnsafeSweepOrphans
+// cc:478-496, the zombie marking cc:522-535) walks the whole map under the lock.
+// Here ids are dense (next_task_id++ per grant, cc:127), so the registry is a
+// power-of-two ring of 16-byte entries in HBM indexed by id & mask; the sweeps
+// are coalesced streaming passes over the live window [lo, next).
+#pragma once
+#include "common.cuh"
+
+namespace yd {
+
+// ---- grants: task ids in FIFO order = exclusive scan over "granted" flags -----
+
+__global__ void __launch_bounds__(1024) k_final_count(const uint32_t* __restrict__ res, uint32_t n,
+                                                      uint32_t* __restrict__ block_counts) {
+  uint32_t q = blockIdx.x * 1024 + threadIdx.x;
+  int granted = (q < n) && (res[q] < kResTimeout);
+  int c = __syncthreads_count(granted);
+  if (threadIdx.x == 0) block_counts[blockIdx.x] = (uint32_t)c;
+}
+
+__global__ void __launch_bounds__(1024) k_final_scan(uint32_t* __restrict__ block_counts, uint32_t nb,
+                                                     Counters* __restrict__ counters) {
+  __shared__ uint32_t warp_sums[32];
+  __shared__ uint32_t carry_s;
+  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) carry_s = 0;
+  __syncthreads();
+  for (uint32_t base = 0; base < nb; base += 1024) {
+    uint32_t i = base + tid;
+    uint32_t v = i < nb ? block_counts[i] : 0;
+    uint32_t x = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      uint32_t y = __shfl_up_sync(0xffffffffu, x, d);
+      if (lane >= d) x += y;
+    }
+    if (lane == 31) warp_sums[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+      uint32_t w = warp_sums[lane];
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        uint32_t y = __shfl_up_sync(0xffffffffu, w, d);
+        if (lane >= d) w += y;
+      }
+      warp_sums[lane] = w;
+    }
+    __syncthreads();
+    uint32_t carry = carry_s;
+    if (i < nb) block_counts[i] = carry + (warp ? warp_sums[warp - 1] : 0) + x - v;  // exclusive
+    __syncthreads();
+    if (tid == 1023) carry_s = carry + warp_sums[31];
+    __syncthreads();
+  }
+  if (tid == 0) {
+    counters->granted = carry_s;
+    counters->alive += carry_s;
+  }
+}
+
+// Writes yd_grant records and creates the TaskDesc of every grant (cc:126-135).
+__global__ void __launch_bounds__(1024) k_final_write(const uint32_t* __restrict__ res,
+                                                      const yd_task_req* __restrict__ reqs, uint32_t n,
+                                                      const uint32_t* __restrict__ block_off,
+                                                      long long now_ns, TaskRing ring,
+                                                      yd_grant* __restrict__ out) {
+  __shared__ uint32_t warp_cnt[32];
+  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t q = blockIdx.x * 1024 + tid;
+  uint32_t r = q < n ? res[q] : kResEnvNotFound;
+  bool granted = r < kResTimeout;
+  uint32_t bal = __ballot_sync(0xffffffffu, granted);
+  if (lane == 0) warp_cnt[warp] = __popc(bal);
+  __syncthreads();
+  uint32_t before = 0;
+  for (uint32_t w = 0; w < warp; ++w) before += warp_cnt[w];
+  before += __popc(bal & ((1u << lane) - 1));
+  if (q >= n) return;
+  uint4 g;  // {task_id lo, task_id hi, servant_index, status} == yd_grant
+  if (granted) {
+    uint64_t id = ring.next + block_off[blockIdx.x] + before;
+    g = make_uint4((uint32_t)id, (uint32_t)(id >> 32), r, YD_STATUS_GRANTED);
+    uint64_t slot = id & ring.mask;
+    const yd_task_req rq = reqs[q];
+    ring.exp[slot] = now_ns + rq.expires_in_ns;
+    ring.srv[slot] = r;
+    ring.flags[slot] = kTaskAlive | ((rq.flags & YD_REQ_FLAG_PREFETCH) ? kTaskPrefetch : 0u);
+  } else {
+    g = make_uint4(0u, 0u, YD_NO_SERVANT,
+                   (r == kResTimeout) ? YD_STATUS_TIMEOUT : YD_STATUS_ENVIRONMENT_NOT_FOUND);
+  }
+  *reinterpret_cast<uint4*>(out + q) = g;  // one 16-byte store
+}
+
+// ---- FreeTask (cc:167-188), one thread per id --------------------------------
+__global__ void k_free(const unsigned long long* __restrict__ ids, uint32_t n, TaskRing ring,
+                       uint32_t* __restrict__ run, Counters* __restrict__ counters) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  unsigned long long id = ids[i];
+  if (id < ring.lo || id >= ring.next) return;  // unknown id: FreeTask just returns (cc:175-179)
+  uint64_t slot = id & ring.mask;
+  uint32_t old = atomicExch(&ring.flags[slot], 0u);  // duplicates in one call: first one wins
+  if (old & kTaskAlive) {
+    atomicSub(&run[ring.srv[slot]], 1u);
+    atomicAdd(&counters->alive, ~0ull);
+    if (old & kTaskZombie) atomicAdd(&counters->zombies, ~0ull);
+  }
+}
+
+// ---- KeepTaskAlive (cc:142-165) ----------------------------------------------
+__global__ void k_keep_alive(const unsigned long long* __restrict__ ids, uint32_t n, long long now_ns,
+                             long long new_expires_in_ns, TaskRing ring, uint8_t* __restrict__ ok) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  unsigned long long id = ids[i];
+  uint8_t r = 0;
+  if (id >= ring.lo && id < ring.next) {
+    uint64_t slot = id & ring.mask;
+    uint32_t f = ring.flags[slot];
+    if ((f & kTaskAlive) && !(f & kTaskZombie)) {
+      ring.exp[slot] = now_ns + new_expires_in_ns;
+      r = 1;
+    }
+  }
+  ok[i] = r;
+}
+
+// ---- OnExpirationTimer (cc:498-536) over the live window ---------------------
+// remap: old registry position -> new position, or kNone if the servant expired
+// (then the task is an orphan and is forgotten without becoming a zombie,
+// cc:478-496).  remap == nullptr when no servant expired.
+__global__ void k_tick(TaskRing ring, long long now_ns, const uint32_t* __restrict__ remap,
+                       Counters* __restrict__ counters) {
+  unsigned long long id = ring.lo + (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned long long my_min = ~0ull;
+  long long d_alive = 0, d_zombie = 0;
+  if (id < ring.next) {
+    uint64_t slot = id & ring.mask;
+    uint32_t f = ring.flags[slot];
+    if (f & kTaskAlive) {
+      bool gone = false;
+      if (remap) {
+        uint32_t np = remap[ring.srv[slot]];
+        if (np == kNone) {
+          ring.flags[slot] = 0;
+          gone = true;
+          d_alive = -1;
+          if (f & kTaskZombie) d_zombie = -1;
+        } else {
+          ring.srv[slot] = np;
+        }
+      }
+      if (!gone) {
+        my_min = id;
+        if (!(f & kTaskZombie) && ring.exp[slot] < now_ns) {
+          ring.flags[slot] = f | kTaskZombie;
+          d_zombie = 1;
+        }
+      }
+    }
+  }
+  // block reduction, then one atomic per block per counter
+  __shared__ unsigned long long s_min[32];
+  __shared__ int s_a[32], s_z[32];
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int a = (int)d_alive, z = (int)d_zombie;
+#pragma unroll
+  for (int d = 16; d; d >>= 1) {
+    unsigned long long o = __shfl_xor_sync(0xffffffffu, my_min, d);
+    my_min = o < my_min ? o : my_min;
+    a += __shfl_xor_sync(0xffffffffu, a, d);
+    z += __shfl_xor_sync(0xffffffffu, z, d);
+  }
+  if (lane == 0) { s_min[warp] = my_min; s_a[warp] = a; s_z[warp] = z; }
+  __syncthreads();
+  if (warp == 0) {
+    uint32_t nw = blockDim.x >> 5;
+    my_min = lane < nw ? s_min[lane] : ~0ull;
+    a = lane < nw ? s_a[lane] : 0;
+    z = lane < nw ? s_z[lane] : 0;
+#pragma unroll
+    for (int d = 16; d; d >>= 1) {
+      unsigned long long o = __shfl_xor_sync(0xffffffffu, my_min, d);
+      my_min = o < my_min ? o : my_min;
+      a += __shfl_xor_sync(0xffffffffu, a, d);
+      z += __shfl_xor_sync(0xffffffffu, z, d);
+    }
+    if (lane == 0) {
+      if (my_min != ~0ull) atomicMin(&counters->min_live, my_min);
+      if (a) atomicAdd(&counters->alive, (unsigned long long)(long long)a);
+      if (z) atomicAdd(&counters->zombies, (unsigned long long)(long long)z);
+    }
+  }
+}
+
+// Order-preserving erase of expired servants from the state arrays (cc:503-516).
+__global__ void k_compact_servants(uint32_t S_old, const uint32_t* __restrict__ remap,
+                                   const uint32_t* __restrict__ run_old,
+                                   const unsigned long long* __restrict__ ever_old,
+                                   uint32_t* __restrict__ run_new,
+                                   unsigned long long* __restrict__ ever_new) {
+  uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= S_old) return;
+  uint32_t np = remap[s];
+  if (np != kNone) {
+    run_new[np] = run_old[s];
+    ever_new[np] = ever_old[s];
+  }
+}
+
+// ---- NotifyServantRunningTasks (cc:222-277) ----------------------------------
+// Sweep: zombies of servant `pos` that the servant no longer reports are freed
+// (UnsafeSweepZombiesOf, cc:453-476).  Reported ids are staged in shared memory.
+__global__ void k_notify_sweep(TaskRing ring, uint32_t pos, const unsigned long long* __restrict__ reported,
+                               uint32_t n, uint32_t* __restrict__ run, Counters* __restrict__ counters) {
+  extern __shared__ unsigned long long s_rep[];
+  for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) s_rep[i] = reported[i];
+  __syncthreads();
+  unsigned long long id = ring.lo + (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (id >= ring.next) return;
+  uint64_t slot = id & ring.mask;
+  uint32_t f = ring.flags[slot];
+  if ((f & (kTaskAlive | kTaskZombie)) != (kTaskAlive | kTaskZombie) || ring.srv[slot] != pos) return;
+  for (uint32_t i = 0; i < n; ++i) {
+    if (s_rep[i] == id) return;  // still reported: stays a zombie
+  }
+  ring.flags[slot] = 0;
+  atomicSub(&run[pos], 1u);
+  atomicAdd(&counters->alive, ~0ull);
+  atomicAdd(&counters->zombies, ~0ull);
+}
+
+// Check: a reported id is "permitted" iff it is a live, non-zombie grant on this
+// servant (cc:257-262); everything else goes back to the daemon as unknown.
+__global__ void k_notify_check(TaskRing ring, uint32_t pos, const unsigned long long* __restrict__ reported,
+                               uint32_t n, uint8_t* __restrict__ permitted) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  unsigned long long id = reported[i];
+  uint8_t ok = 0;
+  if (id >= ring.lo && id < ring.next) {
+    uint64_t slot = id & ring.mask;
+    uint32_t f = ring.flags[slot];
+    ok = (f & kTaskAlive) && !(f & kTaskZombie) && ring.srv[slot] == pos;
+  }
+  permitted[i] = ok;
+}
+
+// Ring growth: re-place the live window into a ring twice (or more) the size.
+__global__ void k_ring_grow(TaskRing old_ring, TaskRing new_ring) {
+  unsigned long long id = old_ring.lo + (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (id >= old_ring.next) return;
+  uint64_t so = id & old_ring.mask, sn = id & new_ring.mask;
+  new_ring.exp[sn] = old_ring.exp[so];
+  new_ring.srv[sn] = old_ring.srv[so];
+  new_ring.flags[sn] = old_ring.flags[so];
+}
+
+}  // namespace yd

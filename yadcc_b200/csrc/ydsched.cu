@@ -1,0 +1,836 @@
+// ydsched.cu -- host side of the B200-native scheduler hot path and its C ABI
+// (include/ydsched.h).  This translation unit owns:
+//
+//   * the servant registry mirror (strings, digests, leases) -- the part of
+//     TaskDispatcher that is string handling, not arithmetic
+//     (KeepServantAlive cc:190-220, the expiry decision of OnExpirationTimer
+//     cc:503-516, RunningTaskBookkeeper);
+//   * the topology builder: digest<->servant components, per-component digest
+//     membership bit tables, requestor-ip -> servant CSR;
+//   * the launch sequences for the kernels in slots.cuh / solve_rowscan.cuh /
+//     tasks.cuh.  All arithmetic of the hot path (eligibility, capacity,
+//     utilisation, pick, task ids, leases, sweeps) runs on the GPU.
+//
+// There is no CPU fallback: yd_create fails without an sm_100 device.
+#include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <numeric>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "common.cuh"
+#include "slots.cuh"
+#include "solve_rowscan.cuh"
+#include "tasks.cuh"
+
+namespace {
+
+using yd::Counters;
+using yd::kNone;
+
+// ---- small helpers ---------------------------------------------------------
+
+struct DevBuf {  // grow-only device allocation
+  void* p = nullptr;
+  size_t cap = 0;
+  template <class T> T* as() const { return static_cast<T*>(p); }
+  void ensure(size_t bytes, bool keep = false, cudaStream_t st = nullptr) {
+    if (bytes <= cap) return;
+    size_t ncap = std::max(bytes, cap * 2);
+    ncap = (ncap + 255) & ~size_t(255);
+    void* np = nullptr;
+    YD_CUDA_CHECK(cudaMalloc(&np, ncap));
+    if (keep && p && cap) YD_CUDA_CHECK(cudaMemcpyAsync(np, p, cap, cudaMemcpyDeviceToDevice, st));
+    if (p) {
+      YD_CUDA_CHECK(cudaStreamSynchronize(st));
+      YD_CUDA_CHECK(cudaFree(p));
+    }
+    p = np;
+    cap = ncap;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+struct PinBuf {  // grow-only pinned host staging
+  void* p = nullptr;
+  size_t cap = 0;
+  template <class T> T* as() const { return static_cast<T*>(p); }
+  void ensure(size_t bytes) {
+    if (bytes <= cap) return;
+    size_t ncap = std::max(bytes, cap * 2);
+    if (p) YD_CUDA_CHECK(cudaFreeHost(p));
+    YD_CUDA_CHECK(cudaHostAlloc(&p, ncap, cudaHostAllocDefault));
+    cap = ncap;
+  }
+  void release() {
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+// yadcc::TryParseSize, yadcc/common/parse_size.cc:25-45.
+bool ParseSize(const char* text, uint64_t* out) {
+  if (!text) return false;
+  size_t len = strlen(text);
+  if (len == 0) return false;
+  uint64_t scale = 1;
+  switch (text[len - 1]) {
+    case 'G': scale = 1ull << 30; --len; break;
+    case 'M': scale = 1ull << 20; --len; break;
+    case 'K': scale = 1ull << 10; --len; break;
+    case 'B': --len; break;
+    default: break;
+  }
+  if (len == 0) return false;
+  uint64_t v = 0;
+  for (size_t i = 0; i != len; ++i) {
+    if (text[i] < '0' || text[i] > '9') return false;
+    uint64_t nv = v * 10 + uint64_t(text[i] - '0');
+    if (nv / 10 != v) return false;
+    v = nv;
+  }
+  *out = v * scale;
+  return true;
+}
+
+struct ServantHost {  // ServantPersonality + ServantDesc lease fields (h:80-116,184-193)
+  int32_t version = 0;
+  std::string observed, reported;
+  std::vector<uint32_t> envs;  // interned digest ids, heartbeat order (duplicates kept)
+  uint32_t nproc = 0, load = 0, max_tasks = 0;
+  uint64_t total_mem = 0, avail_mem = 0;
+  int32_t priority = 0, reason = 0;
+  int64_t discovered_at = 0, expires_at = 0;
+};
+
+struct RunningRec {
+  uint64_t servant_task_id, task_grant_id;
+  std::string servant_location, task_digest;
+};
+
+}  // namespace
+
+struct yd_sched {
+  int device = 0;
+  cudaStream_t st = nullptr;
+  uint64_t min_mem = 0;
+  uint32_t solver_pref = 0;
+
+  // interning
+  std::vector<std::string> envs, ips;
+  std::unordered_map<std::string, uint32_t> env_ids, ip_ids;
+
+  // registry mirror
+  std::vector<ServantHost> sv;
+  std::unordered_map<std::string, uint32_t> loc2pos;
+  bool topo_dirty = true, facts_dirty = true;
+
+  // device servant arrays; state (run/ever) is valid for positions < S_dev
+  DevBuf d_nproc, d_load, d_maxt, d_flags, d_ver, d_run, d_ever;
+  DevBuf d_run_tmp, d_ever_tmp, d_remap;
+  uint32_t S_dev = 0;
+  PinBuf h_facts;
+
+  // topology on device
+  DevBuf d_env_comp, d_env_local, d_comp_sv_off, d_comp_sv, d_comp_mask_off, d_comp_nwarps, d_envmask,
+      d_sv_comp, d_sv_local, d_ip_off, d_ip_sv;
+  uint32_t n_comps = 0, n_envs_dev = 0, n_ips_dev = 0, max_warps = 1;
+  bool wide = false;
+  PinBuf h_topo;
+
+  // lease ring
+  DevBuf d_t_exp, d_t_srv, d_t_flags;
+  uint64_t ring_cap = 0;
+  uint64_t lo = 0, next_id = 0;
+  uint64_t zombies_ub = 0;
+
+  // per-solve buffers
+  DevBuf d_reqs, d_res, d_out, d_blk, d_row_off, d_row_len, d_codes, d_ids, d_ok;
+  DevBuf d_counters;
+  PinBuf h_counters, h_small;
+
+  // RunningTaskBookkeeper (running_task_bookkeeper.h:41-42): same container, same
+  // operation sequence as the reference, hence the same iteration order.
+  std::unordered_map<std::string, std::vector<RunningRec>> running;
+  std::vector<RunningRec> running_cache;
+
+  cudaEvent_t ev[6] = {};
+  yd_solve_stats stats{};
+  bool have_stats = false;
+
+  yd::ServantArrays arrays() const {
+    return yd::ServantArrays{d_nproc.as<uint32_t>(), d_load.as<uint32_t>(), d_maxt.as<uint32_t>(),
+                             d_flags.as<uint32_t>(), d_ver.as<int32_t>(), d_run.as<uint32_t>(),
+                             d_ever.as<unsigned long long>()};
+  }
+  yd::TaskRing ring() const {
+    return yd::TaskRing{d_t_exp.as<long long>(), d_t_srv.as<uint32_t>(), d_t_flags.as<uint32_t>(),
+                        ring_cap - 1, lo, next_id};
+  }
+
+  uint32_t InternEnv(const std::string& k) {
+    auto it = env_ids.find(k);
+    if (it != env_ids.end()) return it->second;
+    uint32_t id = (uint32_t)envs.size();
+    envs.push_back(k);
+    env_ids.emplace(k, id);
+    return id;
+  }
+  uint32_t InternIp(const std::string& k) {
+    auto it = ip_ids.find(k);
+    if (it != ip_ids.end()) return it->second;
+    uint32_t id = (uint32_t)ips.size();
+    ips.push_back(k);
+    ip_ids.emplace(k, id);
+    return id;
+  }
+
+  uint32_t FactFlags(const ServantHost& s) const {
+    uint32_t f = 0;
+    if (s.priority == YD_PRIORITY_DEDICATED) f |= yd::kFlagDedicated;
+    if (s.total_mem != 0 && s.avail_mem < min_mem) f |= yd::kFlagLowMem;  // cc:286-292
+    return f;
+  }
+
+  void EnsureRing(uint64_t need_ids);
+  void SyncServantState();
+  void SyncFacts();
+  void SyncTopology();
+  void FetchCounters();
+};
+
+// ---- device state maintenance ------------------------------------------------
+
+// Extend run[] / ever[] with zeros for servants appended since the last sync
+// (a new ServantDesc starts with running_tasks = 0, cc:208).
+void yd_sched::SyncServantState() {
+  uint32_t S = (uint32_t)sv.size();
+  if (S <= S_dev) return;
+  d_run.ensure(size_t(S) * 4, true, st);
+  d_ever.ensure(size_t(S) * 8, true, st);
+  YD_CUDA_CHECK(cudaMemsetAsync(d_run.as<uint32_t>() + S_dev, 0, size_t(S - S_dev) * 4, st));
+  YD_CUDA_CHECK(cudaMemsetAsync(d_ever.as<unsigned long long>() + S_dev, 0, size_t(S - S_dev) * 8, st));
+  S_dev = S;
+}
+
+void yd_sched::SyncFacts() {
+  if (!facts_dirty) return;
+  uint32_t S = (uint32_t)sv.size();
+  if (S) {
+    h_facts.ensure(size_t(S) * 20);
+    uint32_t* h = h_facts.as<uint32_t>();
+    uint32_t maxcap = 0;
+    for (uint32_t i = 0; i != S; ++i) {
+      const ServantHost& s = sv[i];
+      h[i] = s.nproc;
+      h[S + i] = s.load;
+      h[2 * S + i] = s.max_tasks;
+      h[3 * S + i] = FactFlags(s);
+      h[4 * S + i] = (uint32_t)s.version;
+      maxcap = std::max(maxcap, std::min(s.nproc, s.max_tasks));
+    }
+    wide = maxcap > yd::kNarrowCapLimit;
+    d_nproc.ensure(size_t(S) * 4); d_load.ensure(size_t(S) * 4); d_maxt.ensure(size_t(S) * 4);
+    d_flags.ensure(size_t(S) * 4); d_ver.ensure(size_t(S) * 4);
+    YD_CUDA_CHECK(cudaMemcpyAsync(d_nproc.p, h, size_t(S) * 4, cudaMemcpyHostToDevice, st));
+    YD_CUDA_CHECK(cudaMemcpyAsync(d_load.p, h + S, size_t(S) * 4, cudaMemcpyHostToDevice, st));
+    YD_CUDA_CHECK(cudaMemcpyAsync(d_maxt.p, h + 2 * S, size_t(S) * 4, cudaMemcpyHostToDevice, st));
+    YD_CUDA_CHECK(cudaMemcpyAsync(d_flags.p, h + 3 * S, size_t(S) * 4, cudaMemcpyHostToDevice, st));
+    YD_CUDA_CHECK(cudaMemcpyAsync(d_ver.p, h + 4 * S, size_t(S) * 4, cudaMemcpyHostToDevice, st));
+    // h_facts is reused by the next SyncFacts: make sure the DMA has read it.
+    YD_CUDA_CHECK(cudaStreamSynchronize(st));
+  }
+  facts_dirty = false;
+}
+
+// Components of the digest<->servant graph, digest membership bit tables and the
+// requestor-ip CSR.  Runs only when the servant set or a digest list changed.
+void yd_sched::SyncTopology() {
+  if (!topo_dirty) return;
+  const uint32_t S = (uint32_t)sv.size();
+  const uint32_t E = (uint32_t)envs.size();
+  // union-find over servants, joined through shared digests
+  std::vector<uint32_t> parent(S);
+  std::iota(parent.begin(), parent.end(), 0u);
+  auto find = [&](uint32_t x) {
+    while (parent[x] != x) { parent[x] = parent[parent[x]]; x = parent[x]; }
+    return x;
+  };
+  std::vector<uint32_t> env_first(E, kNone);
+  for (uint32_t i = 0; i != S; ++i) {
+    for (uint32_t e : sv[i].envs) {
+      if (env_first[e] == kNone) { env_first[e] = i; continue; }
+      uint32_t a = find(env_first[e]), b = find(i);
+      if (a != b) parent[std::max(a, b)] = std::min(a, b);
+    }
+  }
+  std::vector<uint32_t> comp_of_root(S, kNone), sv_comp(S, kNone), sv_local(S, kNone);
+  std::vector<std::vector<uint32_t>> comp_sv, comp_envs;
+  for (uint32_t i = 0; i != S; ++i) {
+    if (sv[i].envs.empty()) continue;  // can never be eligible
+    uint32_t r = find(i);
+    if (comp_of_root[r] == kNone) {
+      comp_of_root[r] = (uint32_t)comp_sv.size();
+      comp_sv.emplace_back();
+      comp_envs.emplace_back();
+    }
+    uint32_t c = comp_of_root[r];
+    sv_comp[i] = c;
+    sv_local[i] = (uint32_t)comp_sv[c].size();
+    comp_sv[c].push_back(i);
+  }
+  std::vector<uint32_t> env_comp(E, kNone), env_local(E, kNone);
+  for (uint32_t i = 0; i != S; ++i) {
+    for (uint32_t e : sv[i].envs) {
+      if (env_comp[e] != kNone) continue;
+      uint32_t c = sv_comp[i];
+      env_comp[e] = c;
+      env_local[e] = (uint32_t)comp_envs[c].size();
+      comp_envs[c].push_back(e);
+    }
+  }
+  const uint32_t C = (uint32_t)comp_sv.size();
+  std::vector<uint32_t> sv_off(C + 1, 0), mask_off(C, 0), nwarps(C, 1), flat_sv;
+  size_t mask_bytes = 0;
+  max_warps = 1;
+  for (uint32_t c = 0; c != C; ++c) {
+    sv_off[c] = (uint32_t)flat_sv.size();
+    flat_sv.insert(flat_sv.end(), comp_sv[c].begin(), comp_sv[c].end());
+    uint32_t w = (uint32_t)((comp_sv[c].size() + 32 * yd::kK - 1) / (32 * yd::kK));
+    if (w > 32) {
+      fprintf(stderr,
+              "ydsched: a digest component has %zu servants; the row-scan solver handles at most %d per "
+              "component\n", comp_sv[c].size(), 32 * 32 * yd::kK);
+      abort();
+    }
+    nwarps[c] = std::max(1u, w);
+    max_warps = std::max(max_warps, nwarps[c]);
+    mask_off[c] = (uint32_t)mask_bytes;
+    mask_bytes += size_t(comp_envs[c].size()) * nwarps[c] * 32;
+  }
+  sv_off[C] = (uint32_t)flat_sv.size();
+  std::vector<uint8_t> envmask(std::max<size_t>(mask_bytes, 1), 0);
+  for (uint32_t i = 0; i != S; ++i) {
+    uint32_t c = sv_comp[i];
+    if (c == kNone) continue;
+    uint32_t l = sv_local[i], T = nwarps[c] * 32;
+    for (uint32_t e : sv[i].envs) {
+      envmask[mask_off[c] + size_t(env_local[e]) * T + l / yd::kK] |= uint8_t(1u << (l % yd::kK));
+    }
+  }
+  // requestor-ip CSR: IsNetworkAddressEqual(ip_port, ip) (cc:66-69) holds iff `ip`
+  // is a prefix of the observed location that ends right before a ':'.
+  std::vector<std::vector<uint32_t>> by_ip(ips.size());
+  for (uint32_t i = 0; i != S; ++i) {
+    const std::string& loc = sv[i].observed;
+    for (size_t k = 0; k < loc.size(); ++k) {
+      if (loc[k] != ':') continue;
+      uint32_t id = InternIp(loc.substr(0, k));
+      if (id >= by_ip.size()) by_ip.resize(id + 1);
+      by_ip[id].push_back(i);
+    }
+  }
+  const uint32_t NI = (uint32_t)by_ip.size();
+  std::vector<uint32_t> ip_off(NI + 1, 0), ip_sv;
+  for (uint32_t k = 0; k != NI; ++k) {
+    ip_off[k] = (uint32_t)ip_sv.size();
+    ip_sv.insert(ip_sv.end(), by_ip[k].begin(), by_ip[k].end());
+  }
+  ip_off[NI] = (uint32_t)ip_sv.size();
+
+  auto up = [&](DevBuf& b, const void* src, size_t bytes) {
+    b.ensure(std::max<size_t>(bytes, 4));
+    if (bytes) YD_CUDA_CHECK(cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, st));
+  };
+  up(d_env_comp, env_comp.data(), size_t(E) * 4);
+  up(d_env_local, env_local.data(), size_t(E) * 4);
+  up(d_comp_sv_off, sv_off.data(), size_t(C + 1) * 4);
+  up(d_comp_sv, flat_sv.data(), flat_sv.size() * 4);
+  up(d_comp_mask_off, mask_off.data(), size_t(C) * 4);
+  up(d_comp_nwarps, nwarps.data(), size_t(C) * 4);
+  up(d_envmask, envmask.data(), envmask.size());
+  up(d_sv_comp, sv_comp.data(), size_t(S) * 4);
+  up(d_sv_local, sv_local.data(), size_t(S) * 4);
+  up(d_ip_off, ip_off.data(), size_t(NI + 1) * 4);
+  up(d_ip_sv, ip_sv.data(), ip_sv.size() * 4);
+  YD_CUDA_CHECK(cudaStreamSynchronize(st));  // sources are pageable temporaries
+  n_comps = C;
+  n_envs_dev = E;
+  n_ips_dev = NI;
+  topo_dirty = false;
+}
+
+void yd_sched::EnsureRing(uint64_t need_ids) {
+  uint64_t need = (next_id - lo) + need_ids;
+  if (ring_cap && need <= ring_cap) return;
+  uint64_t ncap = ring_cap ? ring_cap : (1ull << 16);
+  while (ncap < need * 2) ncap <<= 1;
+  DevBuf ne, ns, nf;
+  ne.ensure(ncap * 8); ns.ensure(ncap * 4); nf.ensure(ncap * 4);
+  YD_CUDA_CHECK(cudaMemsetAsync(nf.p, 0, ncap * 4, st));
+  if (ring_cap && next_id > lo) {
+    yd::TaskRing nr{ne.as<long long>(), ns.as<uint32_t>(), nf.as<uint32_t>(), ncap - 1, lo, next_id};
+    uint64_t cnt = next_id - lo;
+    yd::k_ring_grow<<<(unsigned)((cnt + 255) / 256), 256, 0, st>>>(ring(), nr);
+    YD_CUDA_CHECK(cudaGetLastError());
+  }
+  YD_CUDA_CHECK(cudaStreamSynchronize(st));
+  d_t_exp.release(); d_t_srv.release(); d_t_flags.release();
+  d_t_exp = ne; d_t_srv = ns; d_t_flags = nf;
+  ring_cap = ncap;
+}
+
+void yd_sched::FetchCounters() {
+  YD_CUDA_CHECK(cudaMemcpyAsync(h_counters.p, d_counters.p, sizeof(Counters), cudaMemcpyDeviceToHost, st));
+  YD_CUDA_CHECK(cudaStreamSynchronize(st));
+}
+
+// ---- C ABI -------------------------------------------------------------------
+
+extern "C" {
+
+const char* yd_backend_name(void) { return "cuda-sm100a"; }
+
+int yd_parse_size(const char* text, uint64_t* out_bytes) { return ParseSize(text, out_bytes) ? 1 : 0; }
+
+yd_sched* yd_create(const yd_config* cfg) {
+  if (!cfg || cfg->abi_version != YD_ABI_VERSION) return nullptr;
+  uint64_t min_mem = 0;
+  const char* mm = cfg->servant_min_memory_for_accepting_new_task;
+  if (!ParseSize(mm ? mm : "10G", &min_mem)) return nullptr;  // cc:83-87
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || cfg->device < 0 || cfg->device >= ndev) {
+    fprintf(stderr, "ydsched: no CUDA device %d (found %d); this backend has no CPU fallback\n",
+            cfg->device, ndev);
+    return nullptr;
+  }
+  cudaDeviceProp prop{};
+  YD_CUDA_CHECK(cudaGetDeviceProperties(&prop, cfg->device));
+  if (prop.major < 10) {
+    fprintf(stderr, "ydsched: device %d is sm_%d%d; kernels are built for sm_100a only\n", cfg->device,
+            prop.major, prop.minor);
+    return nullptr;
+  }
+  YD_CUDA_CHECK(cudaSetDevice(cfg->device));
+  auto* s = new yd_sched;
+  s->device = cfg->device;
+  s->min_mem = min_mem;
+  s->solver_pref = cfg->solver;
+  YD_CUDA_CHECK(cudaStreamCreateWithFlags(&s->st, cudaStreamNonBlocking));
+  for (auto& e : s->ev) YD_CUDA_CHECK(cudaEventCreate(&e));
+  s->ips.emplace_back();  // id 0 == YD_IP_NONE == the empty requestor string
+  s->ip_ids.emplace("", 0);
+  s->d_counters.ensure(sizeof(Counters));
+  YD_CUDA_CHECK(cudaMemsetAsync(s->d_counters.p, 0, sizeof(Counters), s->st));
+  s->h_counters.ensure(sizeof(Counters));
+  s->h_small.ensure(1 << 16);
+  s->EnsureRing(0);
+  return s;
+}
+
+void yd_destroy(yd_sched* s) {
+  if (!s) return;
+  cudaSetDevice(s->device);
+  cudaStreamSynchronize(s->st);
+  for (DevBuf* b : {&s->d_nproc, &s->d_load, &s->d_maxt, &s->d_flags, &s->d_ver, &s->d_run, &s->d_ever,
+                    &s->d_run_tmp, &s->d_ever_tmp, &s->d_remap, &s->d_env_comp, &s->d_env_local,
+                    &s->d_comp_sv_off, &s->d_comp_sv, &s->d_comp_mask_off, &s->d_comp_nwarps, &s->d_envmask,
+                    &s->d_sv_comp, &s->d_sv_local, &s->d_ip_off, &s->d_ip_sv, &s->d_t_exp, &s->d_t_srv,
+                    &s->d_t_flags, &s->d_reqs, &s->d_res, &s->d_out, &s->d_blk, &s->d_row_off, &s->d_row_len,
+                    &s->d_codes, &s->d_ids, &s->d_ok, &s->d_counters}) {
+    b->release();
+  }
+  for (PinBuf* b : {&s->h_facts, &s->h_topo, &s->h_counters, &s->h_small}) b->release();
+  for (auto& e : s->ev) cudaEventDestroy(e);
+  cudaStreamDestroy(s->st);
+  delete s;
+}
+
+uint32_t yd_intern_env(yd_sched* s, const char* digest, size_t len) {
+  return s->InternEnv(std::string(digest, len));
+}
+uint32_t yd_intern_ip(yd_sched* s, const char* ip, size_t len) { return s->InternIp(std::string(ip, len)); }
+
+// KeepServantAlive, cc:190-220.  Pure registry work; the device copy of the facts
+// is refreshed lazily before the next solve.
+void yd_keep_servant_alive(yd_sched* s, int64_t now_ns, const yd_servant* v, int64_t expires_in_ns) {
+  std::string loc = v->observed_location;
+  auto it = s->loc2pos.find(loc);
+  ServantHost* rec;
+  std::vector<uint32_t> envs(v->num_envs);
+  for (uint32_t i = 0; i != v->num_envs; ++i) envs[i] = s->InternEnv(v->env_digests[i]);
+  if (it == s->loc2pos.end()) {
+    s->loc2pos.emplace(loc, (uint32_t)s->sv.size());
+    rec = &s->sv.emplace_back();
+    rec->observed = loc;
+    rec->discovered_at = now_ns;
+    s->topo_dirty = true;
+  } else {
+    rec = &s->sv[it->second];
+    if (rec->envs != envs) s->topo_dirty = true;
+  }
+  rec->version = v->version;
+  rec->reported = v->reported_location ? v->reported_location : "";
+  rec->envs = std::move(envs);
+  rec->nproc = v->num_processors;
+  rec->load = v->current_load;
+  rec->max_tasks = v->max_tasks;
+  rec->total_mem = v->total_memory_in_bytes;
+  rec->avail_mem = v->memory_available_in_bytes;
+  rec->priority = v->priority;
+  rec->reason = v->not_accepting_task_reason;
+  rec->expires_at = now_ns + expires_in_ns;
+  s->facts_dirty = true;
+}
+
+// THE HOT PATH: n sequential WaitForStartingNewTask decisions (cc:93-140).
+void yd_wait_for_starting_new_tasks(yd_sched* s, int64_t now_ns, const yd_task_req* reqs, size_t n,
+                                    yd_grant* out) {
+  if (n == 0) return;
+  if (n > 0x7fffffffull) { fprintf(stderr, "ydsched: batch too large\n"); abort(); }
+  YD_CUDA_CHECK(cudaSetDevice(s->device));
+  cudaStream_t st = s->st;
+  const uint32_t N = (uint32_t)n;
+  const uint32_t S = (uint32_t)s->sv.size();
+  s->SyncServantState();
+  s->SyncFacts();
+  s->SyncTopology();
+  s->EnsureRing(N);
+
+  const uint32_t nb = (N + 1023) / 1024;
+  s->d_reqs.ensure(size_t(N) * sizeof(yd_task_req));
+  s->d_res.ensure(size_t(N) * 4);
+  s->d_out.ensure(size_t(N) * sizeof(yd_grant));
+  s->d_blk.ensure(size_t(nb) * 4);
+  s->d_row_off.ensure(size_t(S + 1) * 4);
+  s->d_row_len.ensure(size_t(S + 1) * 4);
+  size_t slot_bound = 0;
+  for (auto&& v : s->sv) slot_bound += size_t(std::min(std::min(v.nproc, v.max_tasks), N)) + 1;
+  s->d_codes.ensure(std::max<size_t>(slot_bound, 1) * (s->wide ? 8 : 4));
+
+  uint32_t launches = 0;
+  YD_CUDA_CHECK(cudaEventRecord(s->ev[0], st));
+  YD_CUDA_CHECK(cudaMemcpyAsync(s->d_reqs.p, reqs, size_t(N) * sizeof(yd_task_req), cudaMemcpyHostToDevice, st));
+  YD_CUDA_CHECK(cudaMemsetAsync(s->d_res.p, 0xFF, size_t(N) * 4, st));  // == kResEnvNotFound
+  YD_CUDA_CHECK(cudaEventRecord(s->ev[1], st));
+  yd::ServantArrays arr = s->arrays();
+  if (S && s->n_comps) {
+    yd::k_slot_rows<<<1, 1024, 0, st>>>(S, N, arr, s->d_row_off.as<uint32_t>(), s->d_row_len.as<uint32_t>(),
+                                        s->d_counters.as<Counters>());
+    if (s->wide) {
+      yd::k_slot_fill<true><<<(S + 7) / 8, 256, 0, st>>>(S, arr, s->d_row_off.as<uint32_t>(),
+                                                         s->d_row_len.as<uint32_t>(), nullptr,
+                                                         s->d_codes.as<unsigned long long>());
+    } else {
+      yd::k_slot_fill<false><<<(S + 7) / 8, 256, 0, st>>>(S, arr, s->d_row_off.as<uint32_t>(),
+                                                          s->d_row_len.as<uint32_t>(),
+                                                          s->d_codes.as<uint32_t>(), nullptr);
+    }
+    launches += 2;
+  }
+  YD_CUDA_CHECK(cudaEventRecord(s->ev[2], st));
+  if (S && s->n_comps) {
+    yd::SolveArgs a{};
+    a.reqs = s->d_reqs.as<yd_task_req>();
+    a.n = N;
+    a.res = s->d_res.as<uint32_t>();
+    a.env_comp = s->d_env_comp.as<uint32_t>();
+    a.env_local = s->d_env_local.as<uint32_t>();
+    a.n_envs = s->n_envs_dev;
+    a.comp_sv_off = s->d_comp_sv_off.as<uint32_t>();
+    a.comp_sv = s->d_comp_sv.as<uint32_t>();
+    a.comp_mask_off = s->d_comp_mask_off.as<uint32_t>();
+    a.comp_nwarps = s->d_comp_nwarps.as<uint32_t>();
+    a.envmask = s->d_envmask.as<uint8_t>();
+    a.sv_comp = s->d_sv_comp.as<uint32_t>();
+    a.sv_local = s->d_sv_local.as<uint32_t>();
+    a.ip_off = s->d_ip_off.as<uint32_t>();
+    a.ip_sv = s->d_ip_sv.as<uint32_t>();
+    a.n_ips = s->n_ips_dev;
+    a.sv = arr;
+    a.row_off = s->d_row_off.as<uint32_t>();
+    a.codes = s->d_codes.p;
+    // Two register budgets: components of <= 8 warps (2048 servants) get the full
+    // register file per thread; larger ones are capped at 64 registers.
+    const unsigned threads = s->max_warps * 32;
+    if (threads <= 256) {
+      if (s->wide) yd::k_solve_rowscan<unsigned long long, 256><<<s->n_comps, threads, 0, st>>>(a);
+      else yd::k_solve_rowscan<uint32_t, 256><<<s->n_comps, threads, 0, st>>>(a);
+    } else {
+      if (s->wide) yd::k_solve_rowscan<unsigned long long, 1024><<<s->n_comps, threads, 0, st>>>(a);
+      else yd::k_solve_rowscan<uint32_t, 1024><<<s->n_comps, threads, 0, st>>>(a);
+    }
+    launches += 1;
+  }
+  YD_CUDA_CHECK(cudaEventRecord(s->ev[3], st));
+  yd::k_final_count<<<nb, 1024, 0, st>>>(s->d_res.as<uint32_t>(), N, s->d_blk.as<uint32_t>());
+  yd::k_final_scan<<<1, 1024, 0, st>>>(s->d_blk.as<uint32_t>(), nb, s->d_counters.as<Counters>());
+  yd::k_final_write<<<nb, 1024, 0, st>>>(s->d_res.as<uint32_t>(), s->d_reqs.as<yd_task_req>(), N,
+                                         s->d_blk.as<uint32_t>(), (long long)now_ns, s->ring(),
+                                         s->d_out.as<yd_grant>());
+  launches += 3;
+  YD_CUDA_CHECK(cudaGetLastError());
+  YD_CUDA_CHECK(cudaEventRecord(s->ev[4], st));
+  YD_CUDA_CHECK(cudaMemcpyAsync(out, s->d_out.p, size_t(N) * sizeof(yd_grant), cudaMemcpyDeviceToHost, st));
+  YD_CUDA_CHECK(cudaMemcpyAsync(s->h_counters.p, s->d_counters.p, sizeof(Counters), cudaMemcpyDeviceToHost, st));
+  YD_CUDA_CHECK(cudaEventRecord(s->ev[5], st));
+  YD_CUDA_CHECK(cudaStreamSynchronize(st));
+  const Counters* c = s->h_counters.as<Counters>();
+  s->next_id += c->granted;
+
+  float ms = 0;
+  yd_solve_stats& stt = s->stats;
+  stt = yd_solve_stats{};
+  cudaEventElapsedTime(&ms, s->ev[0], s->ev[5]); stt.total_ms = ms;
+  cudaEventElapsedTime(&ms, s->ev[1], s->ev[2]); stt.prep_ms = ms;
+  cudaEventElapsedTime(&ms, s->ev[2], s->ev[3]); stt.solve_ms = ms;
+  cudaEventElapsedTime(&ms, s->ev[3], s->ev[4]); stt.final_ms = ms;
+  stt.decisions = N;
+  stt.granted = c->granted;
+  stt.kernel_launches = launches;
+  stt.solver = 1;
+  stt.h2d_bytes = size_t(N) * sizeof(yd_task_req);
+  stt.d2h_bytes = size_t(N) * sizeof(yd_grant) + sizeof(Counters);
+  s->have_stats = true;
+}
+
+// KeepTaskAlive x n, cc:142-165.
+void yd_keep_task_alive(yd_sched* s, int64_t now_ns, const uint64_t* ids, size_t n, int64_t new_expires_in_ns,
+                        uint8_t* ok_out) {
+  if (n == 0) return;
+  YD_CUDA_CHECK(cudaSetDevice(s->device));
+  s->d_ids.ensure(n * 8);
+  s->d_ok.ensure(n);
+  YD_CUDA_CHECK(cudaMemcpyAsync(s->d_ids.p, ids, n * 8, cudaMemcpyHostToDevice, s->st));
+  yd::k_keep_alive<<<(unsigned)((n + 255) / 256), 256, 0, s->st>>>(
+      s->d_ids.as<unsigned long long>(), (uint32_t)n, (long long)now_ns, (long long)new_expires_in_ns, s->ring(),
+      s->d_ok.as<uint8_t>());
+  YD_CUDA_CHECK(cudaGetLastError());
+  YD_CUDA_CHECK(cudaMemcpyAsync(ok_out, s->d_ok.p, n, cudaMemcpyDeviceToHost, s->st));
+  YD_CUDA_CHECK(cudaStreamSynchronize(s->st));
+}
+
+// FreeTask x n, cc:167-188.  Fire and forget: ordered on the solve stream.
+void yd_free_tasks(yd_sched* s, const uint64_t* ids, size_t n) {
+  if (n == 0) return;
+  YD_CUDA_CHECK(cudaSetDevice(s->device));
+  s->SyncServantState();
+  s->d_ids.ensure(n * 8);
+  YD_CUDA_CHECK(cudaMemcpyAsync(s->d_ids.p, ids, n * 8, cudaMemcpyHostToDevice, s->st));
+  yd::k_free<<<(unsigned)((n + 255) / 256), 256, 0, s->st>>>(s->d_ids.as<unsigned long long>(), (uint32_t)n,
+                                                              s->ring(), s->d_run.as<uint32_t>(),
+                                                              s->d_counters.as<Counters>());
+  YD_CUDA_CHECK(cudaGetLastError());
+  // `ids` may be pageable and reused by the caller: the copy above has already
+  // staged it (pageable H2D returns after staging) or the memory is pinned and we
+  // must wait for the DMA.
+  YD_CUDA_CHECK(cudaStreamSynchronize(s->st));
+}
+
+// OnExpirationTimer, cc:498-536.
+void yd_on_expiration_timer(yd_sched* s, int64_t now_ns) {
+  YD_CUDA_CHECK(cudaSetDevice(s->device));
+  cudaStream_t st = s->st;
+  s->SyncServantState();
+  const uint32_t S_old = (uint32_t)s->sv.size();
+  std::vector<uint32_t> remap;
+  uint32_t kept = 0;
+  bool any_expired = false;
+  for (auto&& v : s->sv) any_expired |= v.expires_at < now_ns;
+  if (any_expired) {
+    remap.resize(S_old);
+    std::vector<ServantHost> alive;
+    alive.reserve(S_old);
+    for (uint32_t i = 0; i != S_old; ++i) {
+      if (s->sv[i].expires_at < now_ns) {
+        remap[i] = kNone;
+        s->running.erase(s->sv[i].observed);  // RunningTaskBookkeeper::DropServant, cc:510-511
+      } else {
+        remap[i] = kept++;
+        alive.push_back(std::move(s->sv[i]));
+      }
+    }
+    s->sv.swap(alive);
+    s->loc2pos.clear();
+    for (uint32_t i = 0; i != s->sv.size(); ++i) s->loc2pos.emplace(s->sv[i].observed, i);
+    s->topo_dirty = s->facts_dirty = true;
+    s->d_remap.ensure(size_t(S_old) * 4);
+    YD_CUDA_CHECK(cudaMemcpyAsync(s->d_remap.p, remap.data(), size_t(S_old) * 4, cudaMemcpyHostToDevice, st));
+  }
+  // min_live = ~0 before the pass
+  YD_CUDA_CHECK(cudaMemsetAsync(&s->d_counters.as<Counters>()->min_live, 0xFF, 8, st));
+  if (s->next_id > s->lo) {
+    uint64_t cnt = s->next_id - s->lo;
+    yd::k_tick<<<(unsigned)((cnt + 255) / 256), 256, 0, st>>>(
+        s->ring(), (long long)now_ns, any_expired ? s->d_remap.as<uint32_t>() : nullptr,
+        s->d_counters.as<Counters>());
+    YD_CUDA_CHECK(cudaGetLastError());
+  }
+  if (any_expired) {
+    s->d_run_tmp.ensure(std::max<size_t>(size_t(S_old) * 4, 4));
+    s->d_ever_tmp.ensure(std::max<size_t>(size_t(S_old) * 8, 8));
+    yd::k_compact_servants<<<(S_old + 255) / 256, 256, 0, st>>>(
+        S_old, s->d_remap.as<uint32_t>(), s->d_run.as<uint32_t>(), s->d_ever.as<unsigned long long>(),
+        s->d_run_tmp.as<uint32_t>(), s->d_ever_tmp.as<unsigned long long>());
+    YD_CUDA_CHECK(cudaGetLastError());
+    std::swap(s->d_run, s->d_run_tmp);
+    std::swap(s->d_ever, s->d_ever_tmp);
+    s->S_dev = kept;
+  }
+  s->FetchCounters();  // also makes `remap` (pageable) safe to drop
+  const Counters* c = s->h_counters.as<Counters>();
+  s->zombies_ub = c->zombies;
+  s->lo = (c->min_live == ~0ull) ? s->next_id : c->min_live;
+}
+
+// NotifyServantRunningTasks, cc:222-277.
+size_t yd_notify_servant_running_tasks(yd_sched* s, const char* servant_location, const yd_running_task* tasks,
+                                       size_t n, uint64_t* unknown_out) {
+  auto it = s->loc2pos.find(servant_location);
+  if (it == s->loc2pos.end()) {  // the servant itself expired: every id is unknown (cc:243-245)
+    for (size_t i = 0; i != n; ++i) unknown_out[i] = tasks[i].task_grant_id;
+    return n;
+  }
+  const uint32_t pos = it->second;
+  YD_CUDA_CHECK(cudaSetDevice(s->device));
+  cudaStream_t st = s->st;
+  s->SyncServantState();
+  std::vector<uint8_t> permitted(n, 0);
+  const bool window = s->next_id > s->lo;
+  if (window && (n || s->zombies_ub)) {
+    s->h_small.ensure(std::max<size_t>(n * 9, 64));
+    unsigned long long* hid = s->h_small.as<unsigned long long>();
+    for (size_t i = 0; i != n; ++i) hid[i] = tasks[i].task_grant_id;
+    s->d_ids.ensure(std::max<size_t>(n * 8, 8));
+    s->d_ok.ensure(std::max<size_t>(n, 1));
+    if (n) YD_CUDA_CHECK(cudaMemcpyAsync(s->d_ids.p, hid, n * 8, cudaMemcpyHostToDevice, st));
+    if (s->zombies_ub) {
+      if (n * 8 > 48 * 1024) { fprintf(stderr, "ydsched: heartbeat reports too many tasks\n"); abort(); }
+      uint64_t cnt = s->next_id - s->lo;
+      yd::k_notify_sweep<<<(unsigned)((cnt + 255) / 256), 256, n * 8, st>>>(
+          s->ring(), pos, s->d_ids.as<unsigned long long>(), (uint32_t)n, s->d_run.as<uint32_t>(),
+          s->d_counters.as<Counters>());
+      YD_CUDA_CHECK(cudaGetLastError());
+    }
+    if (n) {
+      yd::k_notify_check<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(
+          s->ring(), pos, s->d_ids.as<unsigned long long>(), (uint32_t)n, s->d_ok.as<uint8_t>());
+      YD_CUDA_CHECK(cudaGetLastError());
+      uint8_t* hp = reinterpret_cast<uint8_t*>(hid + n);
+      YD_CUDA_CHECK(cudaMemcpyAsync(hp, s->d_ok.p, n, cudaMemcpyDeviceToHost, st));
+      s->FetchCounters();
+      memcpy(permitted.data(), hp, n);
+    } else {
+      s->FetchCounters();
+    }
+    s->zombies_ub = s->h_counters.as<Counters>()->zombies;
+  }
+  size_t k = 0;
+  std::vector<RunningRec> kept;
+  for (size_t i = 0; i != n; ++i) {
+    if (!permitted[i]) {
+      unknown_out[k++] = tasks[i].task_grant_id;
+    } else {
+      kept.push_back(RunningRec{tasks[i].servant_task_id, tasks[i].task_grant_id,
+                                tasks[i].servant_location ? tasks[i].servant_location : "",
+                                tasks[i].task_digest ? tasks[i].task_digest : ""});
+    }
+  }
+  // RunningTaskBookkeeper::SetServantRunningTasks, running_task_bookkeeper.cc:24-29
+  s->running.erase(servant_location);
+  s->running.emplace(servant_location, std::move(kept));
+  return k;
+}
+
+// RunningTaskBookkeeper::GetRunningTasks, running_task_bookkeeper.cc:36-43.
+size_t yd_get_running_tasks(yd_sched* s, yd_running_task* out, size_t cap) {
+  s->running_cache.clear();
+  for (auto&& [k, v] : s->running) s->running_cache.insert(s->running_cache.begin(), v.begin(), v.end());
+  for (size_t i = 0; i < s->running_cache.size() && i < cap; ++i) {
+    auto&& t = s->running_cache[i];
+    out[i] = yd_running_task{t.servant_task_id, t.task_grant_id, t.servant_location.c_str(), t.task_digest.c_str()};
+  }
+  return s->running_cache.size();
+}
+
+size_t yd_num_servants(yd_sched* s) { return s->sv.size(); }
+
+const char* yd_servant_location(yd_sched* s, uint32_t idx) {
+  return idx < s->sv.size() ? s->sv[idx].observed.c_str() : nullptr;
+}
+
+size_t yd_get_servant_state(yd_sched* s, yd_servant_state* out, size_t cap) {
+  const size_t S = s->sv.size();
+  if (!S || !cap) return S;
+  YD_CUDA_CHECK(cudaSetDevice(s->device));
+  s->SyncServantState();
+  std::vector<uint32_t> run(S);
+  std::vector<unsigned long long> ever(S);
+  YD_CUDA_CHECK(cudaMemcpyAsync(run.data(), s->d_run.p, S * 4, cudaMemcpyDeviceToHost, s->st));
+  YD_CUDA_CHECK(cudaMemcpyAsync(ever.data(), s->d_ever.p, S * 8, cudaMemcpyDeviceToHost, s->st));
+  YD_CUDA_CHECK(cudaStreamSynchronize(s->st));
+  for (size_t i = 0; i < S && i < cap; ++i) {
+    const ServantHost& v = s->sv[i];
+    uint64_t capav = (s->FactFlags(v) & yd::kFlagLowMem)
+                         ? run[i]
+                         : (uint64_t)yd::capacity_at(v.max_tasks, v.nproc, v.load, run[i]);
+    out[i] = yd_servant_state{run[i], ever[i], capav, v.expires_at};
+  }
+  return S;
+}
+
+uint64_t yd_next_task_id(yd_sched* s) { return s->next_id; }
+
+uint64_t yd_num_tasks(yd_sched* s) {
+  YD_CUDA_CHECK(cudaSetDevice(s->device));
+  s->FetchCounters();
+  return s->h_counters.as<Counters>()->alive;
+}
+
+// DumpInternals summary, cc:540-547,581-584,603-612.
+size_t yd_dump_internals_json(yd_sched* s, char* buf, size_t cap) {
+  const size_t S = s->sv.size();
+  std::vector<yd_servant_state> st(S);
+  yd_get_servant_state(s, st.data(), S);
+  uint64_t capacity = 0, unavailable = 0, running = 0;
+  for (size_t i = 0; i != S; ++i) {
+    running += st[i].running_tasks;
+    capacity += s->sv[i].max_tasks;
+    unavailable += s->sv[i].max_tasks - st[i].capacity_available;
+  }
+  int64_t av = (int64_t)(capacity - running - unavailable);
+  char tmp[512];
+  int len = snprintf(tmp, sizeof(tmp),
+                     "{\"servants_up\":%llu,\"running_tasks\":%llu,\"capacity\":%llu,"
+                     "\"capacity_available\":%llu,\"capacity_unavailable\":%llu}",
+                     (unsigned long long)S, (unsigned long long)running, (unsigned long long)capacity,
+                     (unsigned long long)(av > 0 ? av : 0), (unsigned long long)unavailable);
+  if (buf && cap) snprintf(buf, cap, "%s", tmp);
+  return (size_t)len;
+}
+
+int yd_last_solve_stats(yd_sched* s, yd_solve_stats* out) {
+  if (!s->have_stats) return 0;
+  *out = s->stats;
+  return 1;
+}
+
+void* yd_alloc_host(size_t bytes) {
+  void* p = nullptr;
+  if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+  return p;
+}
+void yd_free_host(void* p) {
+  if (p) cudaFreeHost(p);
+}
+
+}  // extern "C"
