@@ -27,12 +27,13 @@ constexpr uint32_t kResEnvNotFound = 0xFFFFFFFFu;  // res[] encodings (anything 
 constexpr uint32_t kResTimeout = 0xFFFFFFFEu;
 constexpr uint32_t kSelfBit = 0x80000000u;  // "tier 2": the requestor's own servant, last resort
 constexpr uint32_t kTierBit = 0x40000000u;  // tier 1: not (dedicated and below 50% of its cores)
-constexpr int kFracBits = 30;
+constexpr int kFracBits = 27;
 
-// Largest capacity for which floor(r * 2^30 / cap) orders r/cap exactly like the
-// reference's double division (distinct fractions with denominators <= 2^15
-// differ by >= 2^-30).  Above it the wide (64-bit key) path must be used.
-constexpr uint32_t kNarrowCapLimit = 32768;
+// Largest capacity for which floor(r * 2^27 / cap) orders r/cap exactly like the
+// reference's double division (distinct fractions with denominators <= 2^13
+// differ by >= 2^-26 > 2^-27, and equal fractions give equal floors).  Above it
+// the wide (64-bit key) path is used.
+constexpr uint32_t kNarrowCapLimit = 8192;
 
 constexpr uint32_t kFlagDedicated = 1u;  // ServantPriority == DEDICATED
 constexpr uint32_t kFlagLowMem = 2u;     // total_memory != 0 && available < min_memory (cc:286-292)

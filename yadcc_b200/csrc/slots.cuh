@@ -9,7 +9,10 @@
 // and the servant is free on a prefix [run[s], free_end(s)) of r values.  One
 // u32 per (servant, r) encodes (tier, r/cap) order-exactly:
 //
-//   code = tier << 30 | floor(r * 2^30 / cap)        (cap <= 32768)
+//   code = tier << 30 | floor(r * 2^27 / cap) << 3   (cap <= 8192; low 3 bits are
+//                                                      stamped by the solver)
+// or, for larger capacities, a 64-bit word holding the reference's own double
+// r/cap (see the kWide branch below).
 //
 // Row s of the table holds the codes for r = run[s] .. run[s]+len-1 followed by
 // a kFull sentinel, so the solver advances a servant by bumping one index.
@@ -106,8 +109,10 @@ __global__ void __launch_bounds__(256) k_slot_fill(uint32_t S, ServantArrays sv,
       double u = (double)r / (double)cap;
       codes_wide[off + i] = (tier0 ? 0ull : (1ull << 62)) | (unsigned long long)__double_as_longlong(u);
     } else {
+      // packed key: bit 30 tier | bits 29..3 floor(r * 2^27 / cap) | bits 2..0 left for
+      // the solver thread's servant index
       uint32_t frac = (uint32_t)((r << kFracBits) / cap);
-      codes[off + i] = (tier0 ? 0u : kTierBit) | frac;
+      codes[off + i] = (tier0 ? 0u : kTierBit) | (frac << 3);
     }
   }
 }

@@ -65,6 +65,7 @@ __global__ void __launch_bounds__(1024) k_final_scan(uint32_t* __restrict__ bloc
 __global__ void __launch_bounds__(1024) k_final_write(const uint32_t* __restrict__ res,
                                                       const yd_task_req* __restrict__ reqs, uint32_t n,
                                                       const uint32_t* __restrict__ block_off,
+                                                      const uint32_t* __restrict__ comp_sv,
                                                       long long now_ns, TaskRing ring,
                                                       yd_grant* __restrict__ out) {
   __shared__ uint32_t warp_cnt[32];
@@ -72,6 +73,7 @@ __global__ void __launch_bounds__(1024) k_final_write(const uint32_t* __restrict
   const uint32_t q = blockIdx.x * 1024 + tid;
   uint32_t r = q < n ? res[q] : kResEnvNotFound;
   bool granted = r < kResTimeout;
+  if (granted) r = comp_sv[r];  // solver results index the component-ordered servant list
   uint32_t bal = __ballot_sync(0xffffffffu, granted);
   if (lane == 0) warp_cnt[warp] = __popc(bal);
   __syncthreads();

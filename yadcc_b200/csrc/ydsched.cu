@@ -559,12 +559,13 @@ void yd_wait_for_starting_new_tasks(yd_sched* s, int64_t now_ns, const yd_task_r
     a.sv = arr;
     a.row_off = s->d_row_off.as<uint32_t>();
     a.codes = s->d_codes.p;
-    // Two register budgets: components of <= 8 warps (2048 servants) get the full
-    // register file per thread; larger ones are capped at 64 registers.
-    const unsigned threads = s->max_warps * 32;
-    if (threads <= 256) {
-      if (s->wide) yd::k_solve_rowscan<unsigned long long, 256><<<s->n_comps, threads, 0, st>>>(a);
-      else yd::k_solve_rowscan<uint32_t, 256><<<s->n_comps, threads, 0, st>>>(a);
+    // Two register budgets: up to 8 solver warps (2048 servants per component) plus
+    // 8 producer warps run with <= 128 registers per thread; larger components are
+    // capped at 64 registers.
+    const unsigned threads = std::min(32u, s->max_warps + yd::kMaxProducers) * 32;
+    if (threads <= 512) {
+      if (s->wide) yd::k_solve_rowscan<unsigned long long, 512><<<s->n_comps, threads, 0, st>>>(a);
+      else yd::k_solve_rowscan<uint32_t, 512><<<s->n_comps, threads, 0, st>>>(a);
     } else {
       if (s->wide) yd::k_solve_rowscan<unsigned long long, 1024><<<s->n_comps, threads, 0, st>>>(a);
       else yd::k_solve_rowscan<uint32_t, 1024><<<s->n_comps, threads, 0, st>>>(a);
@@ -575,7 +576,8 @@ void yd_wait_for_starting_new_tasks(yd_sched* s, int64_t now_ns, const yd_task_r
   yd::k_final_count<<<nb, 1024, 0, st>>>(s->d_res.as<uint32_t>(), N, s->d_blk.as<uint32_t>());
   yd::k_final_scan<<<1, 1024, 0, st>>>(s->d_blk.as<uint32_t>(), nb, s->d_counters.as<Counters>());
   yd::k_final_write<<<nb, 1024, 0, st>>>(s->d_res.as<uint32_t>(), s->d_reqs.as<yd_task_req>(), N,
-                                         s->d_blk.as<uint32_t>(), (long long)now_ns, s->ring(),
+                                         s->d_blk.as<uint32_t>(), s->d_comp_sv.as<uint32_t>(), (long long)now_ns,
+                                         s->ring(),
                                          s->d_out.as<yd_grant>());
   launches += 3;
   YD_CUDA_CHECK(cudaGetLastError());
