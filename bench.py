@@ -177,7 +177,7 @@ def run_ours(args):
     dev = torch.device("cuda", local)
 
     w = build_workload(args.workload, rank)
-    d = TaskDispatcher(device=local)
+    d = TaskDispatcher(device=local, solver=args.solver)
     assert d.backend == "cuda-sm100a"
     w.register(d, now=0.0, expires_in=3600.0)
     src = w.build_requests(d)
@@ -255,7 +255,8 @@ def run_ours(args):
             "dtype": "u32", "data": "synthetic",
             "config": {"workload": f"{args.workload}: {w.meta} per GPU", "decisions_per_step_per_gpu": n,
                        "granted_per_step_per_gpu": granted, "parallelism": f"component-sharded x{world}",
-                       "l2": "flushed between steps (256 MiB write)", "solver": "row-scan"},
+                       "l2": "flushed between steps (256 MiB write)",
+                       "solver": {1: "row-scan", 2: "slot-stream"}.get(st["solver"], st["solver"])},
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": tot_e2e / K,
                     "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
             "gpu_launches": int(launches),
@@ -285,6 +286,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2-mod")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--solver", type=int, default=0, help="0 auto, 1 row-scan, 2 slot-stream")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -21,10 +21,13 @@ def test_reference_golden_cases_on_cuda(make_dispatcher, case):
     case(make_dispatcher("cuda"))
 
 
-def _parity(make_dispatcher, name_or_builder, kinds=("port",)):
+SOLVERS = {1: "rowscan", 2: "stream"}
+
+
+def _parity(make_dispatcher, name_or_builder, kinds=("port",), solver=0):
     traces = {}
     for kind in ("cuda",) + tuple(kinds):
-        d = make_dispatcher(kind)
+        d = make_dispatcher(kind, solver=solver) if kind == "cuda" else make_dispatcher(kind)
         st = name_or_builder(d) if callable(name_or_builder) else S.named_stream(name_or_builder, d)
         traces[kind] = S.Replayer(d, pinned=(kind == "cuda")).run(st)
         d.close()
@@ -35,30 +38,37 @@ def _parity(make_dispatcher, name_or_builder, kinds=("port",)):
     return traces["cuda"]
 
 
+@pytest.mark.parametrize("solver", [1, 2], ids=SOLVERS.get)
 @pytest.mark.parametrize("seed", range(150))
-def test_fuzz_cuda_equals_oracle(make_dispatcher, seed):
+def test_fuzz_cuda_equals_oracle(make_dispatcher, seed, solver):
     kinds = ("port", "ref") if REF_LIB.exists() and seed % 3 == 0 else ("port",)
-    _parity(make_dispatcher, lambda d: S.fuzz_stream(d, seed, n_servants=8 + seed % 30, wide=(seed % 5 == 0)), kinds)
+    _parity(make_dispatcher, lambda d: S.fuzz_stream(d, seed, n_servants=8 + seed % 30, wide=(seed % 5 == 0)), kinds,
+            solver)
 
 
+@pytest.mark.parametrize("solver", [1, 2], ids=SOLVERS.get)
 @pytest.mark.parametrize("seed", range(1000, 1012))
-def test_fuzz_large_components(make_dispatcher, seed):
-    """Components above 256 servants use the multi-warp path of the solver."""
-    _parity(make_dispatcher, lambda d: S.fuzz_stream(d, seed, n_servants=300 + 150 * (seed % 4), n_events=40, max_batch=600))
+def test_fuzz_large_components(make_dispatcher, seed, solver):
+    """Components above 256 servants use the multi-warp path of the row-scan solver."""
+    _parity(make_dispatcher,
+            lambda d: S.fuzz_stream(d, seed, n_servants=300 + 150 * (seed % 4), n_events=40, max_batch=600),
+            solver=solver)
 
 
+@pytest.mark.parametrize("solver", [1, 2], ids=SOLVERS.get)
 @pytest.mark.parametrize("name", ["cfg1", "cfg2-mod-small", "cfg2-random-small", "cfg3-small", "cfg3-mod-small"])
-def test_small_configs(make_dispatcher, name):
-    tr = _parity(make_dispatcher, name)
+def test_small_configs(make_dispatcher, name, solver):
+    tr = _parity(make_dispatcher, name, solver=solver)
     golden = json.loads((GOLDEN / "digests.json").read_text())["streams"]
     assert S.trace_digest(tr) == golden[name]["sha256"]
 
 
+@pytest.mark.parametrize("solver", [1, 2], ids=SOLVERS.get)
 @pytest.mark.parametrize("name", ["cfg2-mod", "cfg2-random"])
-def test_full_size_configs_match_reference_digest(make_dispatcher, name):
+def test_full_size_configs_match_reference_digest(make_dispatcher, name, solver):
     """BASELINE.json configs[1] at full size against the digest produced by the
     reference itself (tests/golden/make_golden.py)."""
-    d = make_dispatcher("cuda")
+    d = make_dispatcher("cuda", solver=solver)
     tr = S.Replayer(d, pinned=True).run(S.named_stream(name, d))
     golden = json.loads((GOLDEN / "digests.json").read_text())["streams"][name]
     g = tr[0]
@@ -129,6 +139,6 @@ def test_native_library_is_what_ran(make_dispatcher):
     w.register(d)
     d.wait_for_starting_new_tasks(w.build_requests(d), 0.0)
     st = d.last_solve_stats()
-    assert st["kernel_launches"] >= 4 and st["solver"] == 1 and st["decisions"] == 1000
+    assert st["kernel_launches"] >= 4 and st["solver"] in (1, 2) and st["decisions"] == 1000
     maps = Path("/proc/self/maps").read_text()
     assert "libydsched.so" in maps

@@ -1,0 +1,99 @@
+// parallel.cuh -- the data-parallel assignment path of the slot-stream solver.
+//
+// If every request that can reach a component belongs to ONE class (one digest,
+// one min_version) and none of them comes from a machine that is itself a servant
+// of that component, the sequential fold of task_dispatcher.cc:93-140 collapses:
+// all requests see the same sorted slot list, nobody skips anything, so the j-th
+// request of the class (FIFO order) takes the j-th slot of the list and requests
+// beyond the list's end time out.  That is a per-class exclusive prefix count
+// (the FIFO rank) followed by one gather -- no dependency between decisions.
+//
+//   k_comp_mode    marks such components (comp_mode = 1); the sequential solver
+//                  (solve_stream.cuh) skips them
+//   k_rank_count   per 1024-request tile: class of each request, its rank among the
+//                  tile's requests of the same class (warp __match_any_sync + a
+//                  32 x 256 shared-memory count table), per-(class, tile) totals
+//   k_rank_assign  rank = scanned (class, tile) base + in-tile rank;
+//                  grant list[rank] or Timeout / EnvironmentNotFound
+#pragma once
+#include "classes.cuh"
+
+namespace yd {
+
+__global__ void k_comp_mode(uint32_t n_comps, ClassTable ct, uint32_t* __restrict__ comp_mode) {
+  uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n_comps) return;
+  comp_mode[c] = (ct.meta[1] == 0 && ct.comp_ncls[c] == 1 && !(ct.comp_flags[c] & 1u)) ? 1u : 0u;
+}
+
+constexpr int kRankTile = 1024;
+
+__global__ void __launch_bounds__(kRankTile) k_rank_count(const yd_task_req* __restrict__ reqs, uint32_t n,
+                                                          TopoView t, ClassTable ct,
+                                                          const uint32_t* __restrict__ comp_mode, uint32_t n_tiles,
+                                                          uint32_t* __restrict__ rcls,   // [n] class or kNone
+                                                          uint32_t* __restrict__ rrank,  // [n] rank inside the tile
+                                                          uint32_t* __restrict__ tile_cnt /* [kMaxClasses][n_tiles] */) {
+  __shared__ uint16_t wc[32][kMaxClasses];
+  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (uint32_t i = tid; i < 32 * kMaxClasses / 2; i += kRankTile) reinterpret_cast<uint32_t*>(&wc[0][0])[i] = 0;
+  __syncthreads();
+  const uint32_t q = blockIdx.x * kRankTile + tid;
+  uint32_t cls = kNone;
+  if (q < n) {
+    const uint2 w0 = __ldg(reinterpret_cast<const uint2*>(reqs + q));
+    if (w0.x < t.n_envs) {
+      const uint32_t comp = t.env_comp[w0.x];
+      if (comp != kNone && comp_mode[comp] == 1) {
+        const uint32_t slot = cls_find(ct.keys, ((unsigned long long)w0.x << 32) | w0.y);
+        if (slot != kNone) cls = ct.slot_cls[slot];
+      }
+    }
+  }
+  const uint32_t peers = __match_any_sync(0xffffffffu, cls);
+  const uint32_t wrank = __popc(peers & ((1u << lane) - 1));
+  if (cls != kNone && wrank == 0) wc[warp][cls] = (uint16_t)__popc(peers);
+  __syncthreads();
+  // exclusive prefix over the 32 warps, per class; tile total to HBM
+  if (tid < kMaxClasses) {
+    uint32_t run = 0;
+#pragma unroll 4
+    for (int w = 0; w < 32; ++w) {
+      const uint32_t c = wc[w][tid];
+      wc[w][tid] = (uint16_t)run;
+      run += c;
+    }
+    tile_cnt[tid * n_tiles + blockIdx.x] = run;
+  }
+  __syncthreads();
+  if (q < n) {
+    rcls[q] = cls;
+    rrank[q] = cls != kNone ? (uint32_t)wc[warp][cls] + wrank : 0u;
+  }
+}
+
+// tile_off = exclusive scan of tile_cnt over (class-major, tile-minor).
+__global__ void __launch_bounds__(256) k_rank_assign(uint32_t n, uint32_t n_tiles, TopoView t, ClassTable ct,
+                                                     const uint32_t* __restrict__ rcls,
+                                                     const uint32_t* __restrict__ rrank,
+                                                     const uint32_t* __restrict__ tile_off,
+                                                     const uint32_t* __restrict__ list_off, uint32_t n_list_tiles,
+                                                     const uint2* __restrict__ list, ServantArrays sv,
+                                                     uint32_t* __restrict__ res) {
+  const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= n) return;
+  const uint32_t c = rcls[q];
+  if (c == kNone) return;  // not ours: the sequential solver (or nobody) answers it
+  if (ct.cls_nelig[c] == 0) { res[q] = kResEnvNotFound; return; }  // cc:105-108
+  const uint32_t rank = tile_off[c * n_tiles + q / kRankTile] - tile_off[c * n_tiles] + rrank[q];
+  const uint32_t lb = list_off[c * n_list_tiles], le = list_off[(c + 1) * n_list_tiles];
+  if (rank >= le - lb) { res[q] = kResTimeout; return; }  // cc:116-118
+  const uint2 e = list[lb + rank];  // (servant local index, running_tasks value of the slot)
+  const uint32_t li = t.comp_sv_off[ct.cls_comp[c]] + e.x;
+  res[q] = li;
+  const uint32_t pos = t.comp_sv[li];
+  atomicAdd(&sv.run[pos], 1u);   // ++running_tasks, ++ever_assigned_tasks (cc:123-124)
+  atomicAdd(&sv.ever[pos], 1ull);
+}
+
+}  // namespace yd

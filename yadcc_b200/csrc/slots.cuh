@@ -85,7 +85,8 @@ __global__ void __launch_bounds__(256) k_slot_fill(uint32_t S, ServantArrays sv,
                                                    const uint32_t* __restrict__ row_off,
                                                    const uint32_t* __restrict__ row_len,
                                                    uint32_t* __restrict__ codes,
-                                                   unsigned long long* __restrict__ codes_wide) {
+                                                   unsigned long long* __restrict__ codes_wide,
+                                                   uint32_t* __restrict__ slot_owner) {
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t s = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (s >= S) return;
@@ -93,6 +94,7 @@ __global__ void __launch_bounds__(256) k_slot_fill(uint32_t S, ServantArrays sv,
   const uint32_t M = sv.max_tasks[s], P = sv.nproc[s], L = sv.load[s], fl = sv.flags[s];
   const uint32_t r0 = sv.run[s];
   for (uint32_t i = lane; i <= len; i += 32) {
+    if (slot_owner) slot_owner[off + i] = s;  // slot-stream solver: slot -> registry position
     if (i == len) {
       if (kWide) codes_wide[off + i] = ~0ull; else codes[off + i] = kFull;
       break;

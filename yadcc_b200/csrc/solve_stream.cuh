@@ -1,0 +1,268 @@
+// solve_stream.cuh -- the slot-stream assignment solver (solver 2).
+//
+// Observation (DESIGN.md "slot streams"): for fixed heartbeat facts the pick key
+// of servant s at running_tasks r, (tier, r/cap, position), is STATIC and strictly
+// increasing in r, and a servant is free exactly on a prefix of r values.  So the
+// reference's per-request arg-min over servants (task_dispatcher.cc:417-451) always
+// returns the globally smallest *untaken slot* (s, r) among the request's eligible
+// servants.  With all slots sorted once per solve (radix.cuh) and filtered per class
+// (classes.cuh), a decision is: walk the class's list from its front pointer, skip
+// slots already taken (r < running_tasks[s]) and the requestor's own servant, take
+// the first one left; fall back to the own servant's head slot; else Timeout.
+// O(1) amortised per decision instead of O(servants).
+//
+// One CTA per component.  Producer warps stream/filter/compact the request queue
+// exactly as in solve_rowscan.cuh; ONE solver warp makes the decisions, its 32
+// lanes examining 32 consecutive list entries per step (one coalesced 256-byte
+// load, one shared-memory gather of running_tasks, three ballots).
+// running_tasks of the component lives in shared memory for the whole solve.
+#pragma once
+#include "classes.cuh"
+#include "solve_rowscan.cuh"  // bar_sync / bar_arrive, tile constants
+
+namespace yd {
+
+struct StreamArgs {
+  const yd_task_req* reqs;
+  uint32_t n;
+  uint32_t* res;
+  TopoView t;
+  ClassTable ct;
+  ServantArrays sv;
+  const uint32_t* row_len;    // free slots per servant (this solve)
+  const uint32_t* list_off;   // [n_classes * n_list_tiles + 1] scanned counts; class c starts at list_off[c * n_list_tiles]
+  uint32_t n_list_tiles;
+  const uint2* list;          // (servant local index, running_tasks value of the slot)
+  uint32_t max_comp_servants; // dynamic shared memory holds 2 x this many u32
+  const uint32_t* comp_mode;  // [C] 0 = this kernel, 1 = handled by the parallel path
+};
+
+struct StreamShared {
+  uint4 desc[2][kTile];  // {request index, class id, self info, -}
+  uint32_t cnt[2];
+  uint32_t pcnt[2][32];
+  uint32_t front[kMaxClasses];  // list index of the first entry not known to be taken
+  uint32_t end[kMaxClasses];
+  uint8_t fail[kMaxClasses];    // 0 unknown, 1 Timeout for good, 2 EnvironmentNotFound
+};
+
+__device__ __forceinline__ uint32_t stream_fail_res(uint8_t f) { return f == 1 ? kResTimeout : kResEnvNotFound; }
+
+// Same two-pass order-preserving compaction as produce_tile, with the class id
+// resolved through the class table.
+__device__ __forceinline__ void produce_tile_stream(const StreamArgs& a, StreamShared& sh, uint32_t comp,
+                                                    uint32_t buf, uint32_t base, uint32_t tile_end, uint32_t gw,
+                                                    uint32_t gn, uint32_t lane) {
+  const uint32_t chunk = ((kTile + gn - 1) / gn + 31) & ~31u;
+  const uint32_t c0 = min(tile_end, base + gw * chunk), c1 = min(tile_end, c0 + chunk);
+  uint32_t minebits = 0, my_count = 0, it = 0;
+  uint32_t cls_keep[4];  // class ids of my (up to 4 x 32) requests when gn == 8; recomputed otherwise
+#pragma unroll
+  for (int k = 0; k < 4; ++k) cls_keep[k] = kNone;
+  for (uint32_t q0 = c0; q0 < c1; q0 += 32, ++it) {
+    const uint32_t q = q0 + lane;
+    bool mine = false;
+    uint32_t cls = kNone;
+    if (q < c1) {
+      const uint2 w0 = __ldg(reinterpret_cast<const uint2*>(a.reqs + q));
+      const uint32_t env = w0.x, mv = w0.y;
+      if (env < a.t.n_envs && __ldg(a.t.env_comp + env) == comp) {
+        const uint32_t slot = cls_find(a.ct.keys, ((unsigned long long)env << 32) | mv);
+        cls = slot != kNone ? a.ct.slot_cls[slot] : kNone;
+        if (cls != kNone) {
+          const uint8_t f = sh.fail[cls];
+          if (f) a.res[q] = stream_fail_res(f);
+          else mine = true;
+        }
+      }
+    }
+    if (it < 4) cls_keep[it] = cls;
+    minebits |= (mine ? 1u : 0u) << it;
+    my_count += __popc(__ballot_sync(0xffffffffu, mine));
+  }
+  if (lane == 0) sh.pcnt[buf][gw] = my_count;
+  bar_sync(kBarProducer, gn * 32);
+  uint32_t woff = 0;
+  for (uint32_t w = 0; w < gw; ++w) woff += sh.pcnt[buf][w];
+  it = 0;
+  for (uint32_t q0 = c0; q0 < c1; q0 += 32, ++it) {
+    const uint32_t q = q0 + lane;
+    const bool mine = (minebits >> it) & 1u;
+    const uint32_t bal = __ballot_sync(0xffffffffu, mine);
+    if (mine) {
+      const uint2* rp = reinterpret_cast<const uint2*>(a.reqs + q);
+      uint32_t cls;
+      if (it < 4) {
+        cls = cls_keep[it];
+      } else {
+        const uint2 w0 = __ldg(rp);
+        cls = a.ct.slot_cls[cls_find(a.ct.keys, ((unsigned long long)w0.x << 32) | w0.y)];
+      }
+      const uint32_t ip = __ldg(rp + 1).x;
+      uint32_t selfinfo = kNone;
+      if (ip < a.t.n_ips) {
+        uint32_t b = __ldg(a.t.ip_off + ip), e = __ldg(a.t.ip_off + ip + 1);
+        if (e - b == 1) {
+          uint32_t p = __ldg(a.t.ip_sv + b);
+          if (__ldg(a.t.sv_comp + p) == comp) selfinfo = __ldg(a.t.sv_local + p);
+        } else if (e - b > 1) {
+          selfinfo = 0x80000000u | ip;
+        }
+      }
+      sh.desc[buf][woff + __popc(bal & ((1u << lane) - 1))] = make_uint4(q, cls, selfinfo, 0u);
+    }
+    woff += __popc(bal);
+  }
+}
+
+constexpr int kStreamProducers = 8;
+
+__global__ void __launch_bounds__((kStreamProducers + 1) * 32, 1) k_solve_stream(StreamArgs a) {
+  extern __shared__ uint32_t dyn_smem[];  // run_s[max_comp_servants], lim_s[max_comp_servants]
+  __shared__ StreamShared sh;
+  const uint32_t comp = blockIdx.x;
+  if (a.ct.meta[1]) return;  // class table overflow: the host reruns this batch with the row-scan solver
+  if (a.comp_mode[comp] != 0 || a.ct.comp_ncls[comp] == 0) return;  // nothing (for us) to do
+  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t nall = (kStreamProducers + 1) * 32;
+  const uint32_t sv_begin = a.t.comp_sv_off[comp];
+  const uint32_t n_sv = a.t.comp_sv_off[comp + 1] - sv_begin;
+  uint32_t* run_s = dyn_smem;
+  uint32_t* lim_s = dyn_smem + a.max_comp_servants;  // first running_tasks value at which the servant is full
+
+  const uint32_t n_cls = a.ct.meta[0];
+  for (uint32_t c = tid; c < kMaxClasses; c += nall) {
+    uint32_t f = 0, fr = 0, en = 0;
+    if (c < n_cls && a.ct.cls_comp[c] == comp) {
+      fr = a.list_off[c * a.n_list_tiles];
+      en = a.list_off[(c + 1) * a.n_list_tiles];
+      if (a.ct.cls_nelig[c] == 0) f = 2;  // nobody eligible: EnvironmentNotFound, statically
+    }
+    sh.front[c] = fr; sh.end[c] = en; sh.fail[c] = (uint8_t)f;
+  }
+  for (uint32_t i = tid; i < n_sv; i += nall) {
+    const uint32_t pos = a.t.comp_sv[sv_begin + i];
+    const uint32_t r0 = a.sv.run[pos];
+    run_s[i] = r0;
+    lim_s[i] = r0 + a.row_len[pos];
+  }
+  __syncthreads();
+
+  const uint32_t n_tiles = (a.n + kTile - 1) / kTile;
+  // ======================= producer warps (1..8) ==============================
+  if (warp >= 1) {
+    const uint32_t pw = warp - 1;
+    for (uint32_t t = 0; t < n_tiles; ++t) {
+      const uint32_t buf = t & 1, base = t * kTile, tile_end = min(a.n, base + kTile);
+      if (t >= 2) bar_sync(kBarFree0 + buf, nall);
+      produce_tile_stream(a, sh, comp, buf, base, tile_end, pw, kStreamProducers, lane);
+      if (pw == 0 && lane == 0) {
+        uint32_t c = 0;
+        for (uint32_t w = 0; w < kStreamProducers; ++w) c += sh.pcnt[buf][w];
+        sh.cnt[buf] = c;
+      }
+      __threadfence_block();
+      bar_arrive(kBarFull0 + buf, nall);
+    }
+    return;
+  }
+
+  // ======================= the solver warp ======================================
+  for (uint32_t t = 0; t < n_tiles; ++t) {
+    const uint32_t buf = t & 1;
+    bar_sync(kBarFull0 + buf, nall);
+    const uint32_t cnt = sh.cnt[buf];
+    const uint4* __restrict__ dl = sh.desc[buf];
+    uint4 ds = cnt ? dl[0] : make_uint4(0, 0, kNone, 0);
+    for (uint32_t d = 0; d < cnt; ++d) {
+      const uint32_t q = ds.x, c = ds.y;
+      uint32_t selfinfo = ds.z;
+      if (d + 1 < cnt) ds = dl[d + 1];
+      const uint8_t f = sh.fail[c];
+      if (f) {
+        if (lane == 0) a.res[q] = stream_fail_res(f);
+        continue;
+      }
+      // several servants on the requestor's IP: "self" is the first of them that is
+      // eligible for this class and free right now (find_if over the free list, cc:372-375)
+      if (selfinfo != kNone && (selfinfo & 0x80000000u)) {
+        const uint32_t ip = selfinfo & 0x7FFFFFFFu;
+        const uint32_t env = a.ct.cls_env[c], mv = a.ct.cls_mv[c];
+        uint32_t best = kNone;
+        for (uint32_t u0 = a.t.ip_off[ip], e = a.t.ip_off[ip + 1]; u0 < e && best == kNone; u0 += 32) {
+          const uint32_t u = u0 + lane;
+          uint32_t cand = kNone;
+          if (u < e) {
+            const uint32_t p = a.t.ip_sv[u];
+            if (a.t.sv_comp[p] == comp) {
+              const uint32_t l = a.t.sv_local[p];
+              if (a.sv.max_tasks[p] != 0 && (uint32_t)a.sv.version[p] >= mv && run_s[l] < lim_s[l] &&
+                  servant_has_env(a.t, p, env)) {
+                cand = l;
+              }
+            }
+          }
+          best = __reduce_min_sync(0xffffffffu, cand);  // CSR rows are in ascending position order
+        }
+        selfinfo = best;
+      }
+      const uint32_t selfl = selfinfo;
+
+      // ---- walk the class's sorted slot list ---------------------------------
+      const uint32_t end = sh.end[c];
+      uint32_t base = sh.front[c];
+      uint32_t new_front = base;
+      bool front_open = true;
+      uint32_t self_slot = kNone;  // local index; the own servant's head slot if we passed it
+      uint32_t win = kNone;
+      while (base < end) {
+        const uint32_t idx = base + lane;
+        const bool valid = idx < end;
+        uint2 e = make_uint2(0, 0);
+        if (valid) e = a.list[idx];
+        const bool taken = valid && e.y < run_s[e.x];
+        const bool isself = valid && !taken && e.x == selfl;
+        const bool avail = valid && !taken && !isself;
+        const uint32_t bT = __ballot_sync(0xffffffffu, taken);
+        const uint32_t bS = __ballot_sync(0xffffffffu, isself);
+        const uint32_t bA = __ballot_sync(0xffffffffu, avail);
+        if (front_open) {  // the front only ever moves over a contiguous run of taken slots
+          const uint32_t lead = (bT == 0xffffffffu) ? 32u : (uint32_t)(__ffs(~bT) - 1);
+          new_front += lead;
+          if (lead < 32) front_open = false;
+        }
+        if (self_slot == kNone && bS) self_slot = selfl;
+        if (bA) {
+          win = __shfl_sync(0xffffffffu, e.x, __ffs(bA) - 1);
+          break;
+        }
+        base += 32;
+      }
+      if (win == kNone && self_slot != kNone) win = self_slot;  // last resort (cc:394-396)
+      if (lane == 0) {
+        sh.front[c] = new_front;
+        if (win != kNone) {
+          run_s[win] += 1;
+          a.res[q] = sv_begin + win;
+        } else {
+          a.res[q] = kResTimeout;  // the class has eligible servants but none is free (cc:116-118)
+          sh.fail[c] = 1;          // ... and within this batch none will become free again
+        }
+      }
+      __syncwarp();
+    }
+    if (t + 2 < n_tiles) bar_arrive(kBarFree0 + buf, nall);
+  }
+
+  // ---- write back running_tasks / ever_assigned_tasks (cc:123-124) -----------
+  for (uint32_t i = lane; i < n_sv; i += 32) {
+    const uint32_t pos = a.t.comp_sv[sv_begin + i];
+    const uint32_t r0 = a.sv.run[pos], r1 = run_s[i];
+    if (r1 != r0) {
+      a.sv.run[pos] = r1;
+      a.sv.ever[pos] += (unsigned long long)(r1 - r0);
+    }
+  }
+}
+
+}  // namespace yd

@@ -24,7 +24,10 @@
 
 #include "common.cuh"
 #include "slots.cuh"
+#include "radix.cuh"
 #include "solve_rowscan.cuh"
+#include "solve_stream.cuh"
+#include "parallel.cuh"
 #include "tasks.cuh"
 
 namespace {
@@ -143,9 +146,16 @@ struct yd_sched {
   // topology on device
   DevBuf d_env_comp, d_env_local, d_comp_sv_off, d_comp_sv, d_comp_mask_off, d_comp_nwarps, d_envmask,
       d_sv_comp, d_sv_local, d_ip_off, d_ip_sv;
-  uint32_t n_comps = 0, n_envs_dev = 0, n_ips_dev = 0, max_warps = 1;
+  uint32_t n_comps = 0, n_envs_dev = 0, n_ips_dev = 0, max_warps = 1, max_comp_servants = 0;
   bool wide = false;
   PinBuf h_topo;
+
+  // slot-stream solver state
+  DevBuf d_sv_env_off, d_sv_envs, d_comp_mode;
+  DevBuf d_slot_owner, d_sort_k[2], d_sort_v[2], d_hist;
+  DevBuf d_cls_keys, d_cls_u32;  // class table: 8-byte keys; all u32 arrays in one allocation
+  DevBuf d_spos, d_sr, d_scomp, d_list_cnt, d_list, d_rcls, d_rrank, d_rank_cnt;
+  bool stream_attr_set = false;
 
   // lease ring
   DevBuf d_t_exp, d_t_srv, d_t_flags;
@@ -306,13 +316,7 @@ void yd_sched::SyncTopology() {
     sv_off[c] = (uint32_t)flat_sv.size();
     flat_sv.insert(flat_sv.end(), comp_sv[c].begin(), comp_sv[c].end());
     uint32_t w = (uint32_t)((comp_sv[c].size() + 32 * yd::kK - 1) / (32 * yd::kK));
-    if (w > 32) {
-      fprintf(stderr,
-              "ydsched: a digest component has %zu servants; the row-scan solver handles at most %d per "
-              "component\n", comp_sv[c].size(), 32 * 32 * yd::kK);
-      abort();
-    }
-    nwarps[c] = std::max(1u, w);
+    nwarps[c] = std::max(1u, std::min(w, 32u));  // > 32 warps: only the slot-stream solver applies
     max_warps = std::max(max_warps, nwarps[c]);
     mask_off[c] = (uint32_t)mask_bytes;
     mask_bytes += size_t(comp_envs[c].size()) * nwarps[c] * 32;
@@ -362,6 +366,19 @@ void yd_sched::SyncTopology() {
   up(d_sv_local, sv_local.data(), size_t(S) * 4);
   up(d_ip_off, ip_off.data(), size_t(NI + 1) * 4);
   up(d_ip_sv, ip_sv.data(), ip_sv.size() * 4);
+  // digest ids per servant (CSR) for class-eligibility tests on the device
+  std::vector<uint32_t> env_off(S + 1, 0), env_flat;
+  for (uint32_t i = 0; i != S; ++i) {
+    env_off[i] = (uint32_t)env_flat.size();
+    env_flat.insert(env_flat.end(), sv[i].envs.begin(), sv[i].envs.end());
+  }
+  env_off[S] = (uint32_t)env_flat.size();
+  up(d_sv_env_off, env_off.data(), size_t(S + 1) * 4);
+  up(d_sv_envs, env_flat.data(), env_flat.size() * 4);
+  std::vector<uint32_t> comp_mode(std::max(C, 1u), 0);
+  up(d_comp_mode, comp_mode.data(), comp_mode.size() * 4);
+  max_comp_servants = 0;
+  for (uint32_t c = 0; c != C; ++c) max_comp_servants = std::max<uint32_t>(max_comp_servants, (uint32_t)comp_sv[c].size());
   YD_CUDA_CHECK(cudaStreamSynchronize(st));  // sources are pageable temporaries
   n_comps = C;
   n_envs_dev = E;
@@ -446,7 +463,10 @@ void yd_destroy(yd_sched* s) {
                     &s->d_comp_sv_off, &s->d_comp_sv, &s->d_comp_mask_off, &s->d_comp_nwarps, &s->d_envmask,
                     &s->d_sv_comp, &s->d_sv_local, &s->d_ip_off, &s->d_ip_sv, &s->d_t_exp, &s->d_t_srv,
                     &s->d_t_flags, &s->d_reqs, &s->d_res, &s->d_out, &s->d_blk, &s->d_row_off, &s->d_row_len,
-                    &s->d_codes, &s->d_ids, &s->d_ok, &s->d_counters}) {
+                    &s->d_codes, &s->d_ids, &s->d_ok, &s->d_counters, &s->d_sv_env_off, &s->d_sv_envs,
+                    &s->d_comp_mode, &s->d_slot_owner, &s->d_sort_k[0], &s->d_sort_k[1], &s->d_sort_v[0],
+                    &s->d_sort_v[1], &s->d_hist, &s->d_cls_keys, &s->d_cls_u32, &s->d_spos, &s->d_sr, &s->d_scomp,
+                    &s->d_list_cnt, &s->d_list, &s->d_rcls, &s->d_rrank, &s->d_rank_cnt}) {
     b->release();
   }
   for (PinBuf* b : {&s->h_facts, &s->h_topo, &s->h_counters, &s->h_small}) b->release();
@@ -492,6 +512,226 @@ void yd_keep_servant_alive(yd_sched* s, int64_t now_ns, const yd_servant* v, int
   s->facts_dirty = true;
 }
 
+// ---- the two solvers' launch sequences -------------------------------------------
+
+extern "C++" {
+namespace {
+
+constexpr size_t kRowscanMaxComponent = 32 * 32 * yd::kK;  // 8192 servants per component
+constexpr size_t kStreamMaxComponent = 22000;              // 2 x u32 per servant of dynamic shared memory
+
+yd::TopoView MakeTopo(yd_sched* s) {
+  yd::TopoView t{};
+  t.env_comp = s->d_env_comp.as<uint32_t>();
+  t.n_envs = s->n_envs_dev;
+  t.sv_comp = s->d_sv_comp.as<uint32_t>();
+  t.sv_local = s->d_sv_local.as<uint32_t>();
+  t.ip_off = s->d_ip_off.as<uint32_t>();
+  t.ip_sv = s->d_ip_sv.as<uint32_t>();
+  t.n_ips = s->n_ips_dev;
+  t.sv_env_off = s->d_sv_env_off.as<uint32_t>();
+  t.sv_envs = s->d_sv_envs.as<uint32_t>();
+  t.comp_sv_off = s->d_comp_sv_off.as<uint32_t>();
+  t.comp_sv = s->d_comp_sv.as<uint32_t>();
+  return t;
+}
+
+yd::ClassTable MakeClassTable(yd_sched* s) {
+  uint32_t* u = s->d_cls_u32.as<uint32_t>();
+  yd::ClassTable ct{};
+  ct.keys = s->d_cls_keys.as<unsigned long long>();
+  ct.slot_cls = u;                       u += yd::kClsTableSize;
+  ct.meta = u;                           u += 8;
+  ct.cls_env = u;                        u += yd::kMaxClasses;
+  ct.cls_mv = u;                         u += yd::kMaxClasses;
+  ct.cls_comp = u;                       u += yd::kMaxClasses;
+  ct.cls_nelig = u;                      u += yd::kMaxClasses;
+  ct.cls_count = u;                      u += yd::kMaxClasses;
+  ct.comp_flags = u;                     u += s->n_comps;
+  ct.comp_ncls = u;
+  return ct;
+}
+
+// Slot table (both solvers).  Returns the number of kernels launched.
+uint32_t LaunchSlotTable(yd_sched* s, uint32_t N, bool with_owner) {
+  const uint32_t S = (uint32_t)s->sv.size();
+  cudaStream_t st = s->st;
+  yd::ServantArrays arr = s->arrays();
+  yd::k_slot_rows<<<1, 1024, 0, st>>>(S, N, arr, s->d_row_off.as<uint32_t>(), s->d_row_len.as<uint32_t>(),
+                                      s->d_counters.as<Counters>());
+  uint32_t* owner = with_owner ? s->d_slot_owner.as<uint32_t>() : nullptr;
+  if (s->wide) {
+    yd::k_slot_fill<true><<<(S + 7) / 8, 256, 0, st>>>(S, arr, s->d_row_off.as<uint32_t>(),
+                                                       s->d_row_len.as<uint32_t>(), nullptr,
+                                                       s->d_codes.as<unsigned long long>(), owner);
+  } else {
+    yd::k_slot_fill<false><<<(S + 7) / 8, 256, 0, st>>>(S, arr, s->d_row_off.as<uint32_t>(),
+                                                        s->d_row_len.as<uint32_t>(), s->d_codes.as<uint32_t>(),
+                                                        nullptr, owner);
+  }
+  return 2;
+}
+
+// Solver 1: one (task x servant) row per decision.
+uint32_t LaunchRowscan(yd_sched* s, uint32_t N) {
+  cudaStream_t st = s->st;
+  yd::SolveArgs a{};
+  a.reqs = s->d_reqs.as<yd_task_req>();
+  a.n = N;
+  a.res = s->d_res.as<uint32_t>();
+  a.env_comp = s->d_env_comp.as<uint32_t>();
+  a.env_local = s->d_env_local.as<uint32_t>();
+  a.n_envs = s->n_envs_dev;
+  a.comp_sv_off = s->d_comp_sv_off.as<uint32_t>();
+  a.comp_sv = s->d_comp_sv.as<uint32_t>();
+  a.comp_mask_off = s->d_comp_mask_off.as<uint32_t>();
+  a.comp_nwarps = s->d_comp_nwarps.as<uint32_t>();
+  a.envmask = s->d_envmask.as<uint8_t>();
+  a.sv_comp = s->d_sv_comp.as<uint32_t>();
+  a.sv_local = s->d_sv_local.as<uint32_t>();
+  a.ip_off = s->d_ip_off.as<uint32_t>();
+  a.ip_sv = s->d_ip_sv.as<uint32_t>();
+  a.n_ips = s->n_ips_dev;
+  a.sv = s->arrays();
+  a.row_off = s->d_row_off.as<uint32_t>();
+  a.codes = s->d_codes.p;
+  // Two register budgets: up to 8 solver warps (2048 servants per component) plus
+  // 8 producer warps run with <= 128 registers per thread; larger components are
+  // capped at 64 registers.
+  const unsigned threads = std::min(32u, s->max_warps + yd::kMaxProducers) * 32;
+  if (threads <= 512) {
+    if (s->wide) yd::k_solve_rowscan<unsigned long long, 512><<<s->n_comps, threads, 0, st>>>(a);
+    else yd::k_solve_rowscan<uint32_t, 512><<<s->n_comps, threads, 0, st>>>(a);
+  } else {
+    if (s->wide) yd::k_solve_rowscan<unsigned long long, 1024><<<s->n_comps, threads, 0, st>>>(a);
+    else yd::k_solve_rowscan<uint32_t, 1024><<<s->n_comps, threads, 0, st>>>(a);
+  }
+  return 1;
+}
+
+template <typename KeyT>
+uint32_t LaunchSort(yd_sched* s, size_t bound, int first_bit, int last_bit) {
+  cudaStream_t st = s->st;
+  const uint32_t nb = (uint32_t)((bound + yd::kRsTile - 1) / yd::kRsTile);
+  const unsigned long long* n_ptr = &s->d_counters.as<Counters>()->slots;
+  s->d_hist.ensure(size_t(yd::kRsBins) * nb * 4);
+  const KeyT* kin = s->d_codes.as<KeyT>();
+  const uint32_t* vin = nullptr;
+  int cur = 0;
+  uint32_t launches = 0;
+  for (int shift = first_bit; shift <= last_bit; shift += yd::kRsBits) {
+    KeyT* kout = s->d_sort_k[cur].as<KeyT>();
+    uint32_t* vout = s->d_sort_v[cur].as<uint32_t>();
+    yd::k_rs_hist<KeyT><<<nb, yd::kRsThreads, 0, st>>>(kin, n_ptr, shift, nb, s->d_hist.as<uint32_t>());
+    yd::k_scan_u32<<<1, 1024, 0, st>>>(s->d_hist.as<uint32_t>(), yd::kRsBins * nb, nullptr);
+    yd::k_rs_scatter<KeyT><<<nb, yd::kRsThreads, 0, st>>>(kin, vin, n_ptr, shift, nb, s->d_hist.as<uint32_t>(), kout,
+                                                          vout);
+    launches += 3;
+    kin = kout;
+    vin = vout;
+    cur ^= 1;
+  }
+  // result is in buffer cur ^ 1
+  if (cur == 0) {  // odd number of passes leaves it in [0]; even in [1] -> normalise to [0]
+    std::swap(s->d_sort_k[0], s->d_sort_k[1]);
+    std::swap(s->d_sort_v[0], s->d_sort_v[1]);
+  }
+  return launches;
+}
+
+// Solver 2: sorted slot streams.
+uint32_t LaunchStream(yd_sched* s, uint32_t N, size_t slot_bound) {
+  cudaStream_t st = s->st;
+  const uint32_t S = (uint32_t)s->sv.size();
+  uint32_t launches = 0;
+  const size_t ksz = s->wide ? 8 : 4;
+  for (int b = 0; b < 2; ++b) { s->d_sort_k[b].ensure(slot_bound * ksz); s->d_sort_v[b].ensure(slot_bound * 4); }
+  // ---- 1. sort the slot codes (stable; payload = original slot index) ---------
+  if (s->wide) launches += LaunchSort<unsigned long long>(s, slot_bound, 0, 62);
+  else launches += LaunchSort<uint32_t>(s, slot_bound, 3, 30);
+  const uint32_t* sorted_orig = s->d_sort_v[0].as<uint32_t>();
+  const unsigned long long* m_ptr = &s->d_counters.as<Counters>()->slots;
+
+  // ---- 2. classes ------------------------------------------------------------
+  const size_t cls_u32 = yd::kClsTableSize + 8 + 5 * yd::kMaxClasses + 2 * size_t(s->n_comps) + 8;
+  s->d_cls_keys.ensure(yd::kClsTableSize * 8);
+  s->d_cls_u32.ensure(cls_u32 * 4);
+  YD_CUDA_CHECK(cudaMemsetAsync(s->d_cls_keys.p, 0xFF, yd::kClsTableSize * 8, st));
+  YD_CUDA_CHECK(cudaMemsetAsync(s->d_cls_u32.p, 0, cls_u32 * 4, st));
+  yd::TopoView t = MakeTopo(s);
+  yd::ClassTable ct = MakeClassTable(s);
+  yd::ServantArrays arr = s->arrays();
+  yd::k_cls_insert<<<(N + 255) / 256, 256, 0, st>>>(s->d_reqs.as<yd_task_req>(), N, t, ct);
+  yd::k_cls_number<<<1, 1024, 0, st>>>(t, ct);
+  yd::k_cls_elig<<<dim3(std::max(1u, std::min(64u, (s->max_comp_servants + 255) / 256)), yd::kMaxClasses), 256, 0,
+                   st>>>(t, ct, arr);
+  launches += 3;
+
+  // ---- 3. per-class sorted slot lists ------------------------------------------
+  s->d_spos.ensure(slot_bound * 4); s->d_sr.ensure(slot_bound * 4); s->d_scomp.ensure(slot_bound * 4);
+  yd::k_slot_decode<<<(unsigned)((slot_bound + 255) / 256), 256, 0, st>>>(
+      sorted_orig, m_ptr, s->d_slot_owner.as<uint32_t>(), s->d_row_off.as<uint32_t>(), s->d_row_len.as<uint32_t>(),
+      s->d_run.as<uint32_t>(), s->d_sv_comp.as<uint32_t>(), s->d_spos.as<uint32_t>(), s->d_sr.as<uint32_t>(),
+      s->d_scomp.as<uint32_t>());
+  const uint32_t n_tiles = (uint32_t)((slot_bound + yd::kListTile - 1) / yd::kListTile);
+  const size_t n_cnt = size_t(yd::kMaxClasses) * n_tiles + 1;
+  s->d_list_cnt.ensure(n_cnt * 4);
+  YD_CUDA_CHECK(cudaMemsetAsync(s->d_list_cnt.p, 0, n_cnt * 4, st));
+  yd::k_list_count<<<dim3(n_tiles, yd::kMaxClasses), yd::kListTile, 0, st>>>(
+      m_ptr, s->d_spos.as<uint32_t>(), s->d_scomp.as<uint32_t>(), t, ct, arr, n_tiles, s->d_list_cnt.as<uint32_t>());
+  yd::k_scan_u32<<<1, 1024, 0, st>>>(s->d_list_cnt.as<uint32_t>(), (uint32_t)n_cnt, nullptr);
+  // a slot belongs to at most (classes of its component) lists; bound by classes x slots is wasteful,
+  // so size for the common case and let the device tell us (checked after the solve)
+  s->d_list.ensure(std::max<size_t>(slot_bound, 1) * 8 * 4);
+  yd::k_list_fill<<<dim3(n_tiles, yd::kMaxClasses), yd::kListTile, 0, st>>>(
+      m_ptr, s->d_spos.as<uint32_t>(), s->d_sr.as<uint32_t>(), s->d_scomp.as<uint32_t>(), t, ct, arr, n_tiles,
+      s->d_list_cnt.as<uint32_t>(), s->d_list.as<uint2>(), (uint32_t)(slot_bound * 4));
+  launches += 4;
+
+  // ---- 4a. data-parallel path: single-class components without self-requests -----
+  yd::k_comp_mode<<<(s->n_comps + 255) / 256, 256, 0, st>>>(s->n_comps, ct, s->d_comp_mode.as<uint32_t>());
+  const uint32_t n_rtiles = (N + yd::kRankTile - 1) / yd::kRankTile;
+  const size_t n_rcnt = size_t(yd::kMaxClasses) * n_rtiles;
+  s->d_rcls.ensure(size_t(N) * 4); s->d_rrank.ensure(size_t(N) * 4); s->d_rank_cnt.ensure(n_rcnt * 4);
+  yd::k_rank_count<<<n_rtiles, yd::kRankTile, 0, st>>>(s->d_reqs.as<yd_task_req>(), N, t, ct,
+                                                        s->d_comp_mode.as<uint32_t>(), n_rtiles,
+                                                        s->d_rcls.as<uint32_t>(), s->d_rrank.as<uint32_t>(),
+                                                        s->d_rank_cnt.as<uint32_t>());
+  yd::k_scan_u32<<<1, 1024, 0, st>>>(s->d_rank_cnt.as<uint32_t>(), (uint32_t)n_rcnt, nullptr);
+  yd::k_rank_assign<<<(N + 255) / 256, 256, 0, st>>>(N, n_rtiles, t, ct, s->d_rcls.as<uint32_t>(),
+                                                     s->d_rrank.as<uint32_t>(), s->d_rank_cnt.as<uint32_t>(),
+                                                     s->d_list_cnt.as<uint32_t>(), n_tiles, s->d_list.as<uint2>(),
+                                                     arr, s->d_res.as<uint32_t>());
+  launches += 4;
+
+  // ---- 4b. sequential decisions for everything else -------------------------------
+  yd::StreamArgs a{};
+  a.reqs = s->d_reqs.as<yd_task_req>();
+  a.n = N;
+  a.res = s->d_res.as<uint32_t>();
+  a.t = t;
+  a.ct = ct;
+  a.sv = arr;
+  a.row_len = s->d_row_len.as<uint32_t>();
+  a.list_off = s->d_list_cnt.as<uint32_t>();
+  a.n_list_tiles = n_tiles;
+  a.list = s->d_list.as<uint2>();
+  a.max_comp_servants = s->max_comp_servants;
+  a.comp_mode = s->d_comp_mode.as<uint32_t>();
+  const size_t dyn = size_t(s->max_comp_servants) * 8;
+  if (!s->stream_attr_set) {
+    YD_CUDA_CHECK(cudaFuncSetAttribute(yd::k_solve_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, 190 * 1024));
+    s->stream_attr_set = true;
+  }
+  yd::k_solve_stream<<<s->n_comps, (yd::kStreamProducers + 1) * 32, dyn, st>>>(a);
+  launches += 1;
+  (void)S;
+  return launches;
+}
+
+}  // namespace
+}  // extern "C++"
+
 // THE HOT PATH: n sequential WaitForStartingNewTask decisions (cc:93-140).
 void yd_wait_for_starting_new_tasks(yd_sched* s, int64_t now_ns, const yd_task_req* reqs, size_t n,
                                     yd_grant* out) {
@@ -515,70 +755,57 @@ void yd_wait_for_starting_new_tasks(yd_sched* s, int64_t now_ns, const yd_task_r
   s->d_row_len.ensure(size_t(S + 1) * 4);
   size_t slot_bound = 0;
   for (auto&& v : s->sv) slot_bound += size_t(std::min(std::min(v.nproc, v.max_tasks), N)) + 1;
-  s->d_codes.ensure(std::max<size_t>(slot_bound, 1) * (s->wide ? 8 : 4));
+  slot_bound = std::max<size_t>(slot_bound, 1);
+  if (slot_bound > 0xfffffff0ull) { fprintf(stderr, "ydsched: slot table too large\n"); abort(); }
+  s->d_codes.ensure(slot_bound * (s->wide ? 8 : 4));
+  s->d_slot_owner.ensure(slot_bound * 4);
 
+  // solver choice: 2 (slot streams) unless asked otherwise or a component is too big for it
+  uint32_t solver = s->solver_pref == 1 ? 1 : 2;
+  if (solver == 2 && s->max_comp_servants > kStreamMaxComponent) solver = 1;
+  if (solver == 1 && s->max_comp_servants > kRowscanMaxComponent) {
+    fprintf(stderr, "ydsched: a digest component has %u servants: too large for both solvers (%zu / %zu)\n",
+            s->max_comp_servants, kRowscanMaxComponent, kStreamMaxComponent);
+    abort();
+  }
+
+  const bool have_work = S && s->n_comps;
   uint32_t launches = 0;
   YD_CUDA_CHECK(cudaEventRecord(s->ev[0], st));
   YD_CUDA_CHECK(cudaMemcpyAsync(s->d_reqs.p, reqs, size_t(N) * sizeof(yd_task_req), cudaMemcpyHostToDevice, st));
-  YD_CUDA_CHECK(cudaMemsetAsync(s->d_res.p, 0xFF, size_t(N) * 4, st));  // == kResEnvNotFound
-  YD_CUDA_CHECK(cudaEventRecord(s->ev[1], st));
-  yd::ServantArrays arr = s->arrays();
-  if (S && s->n_comps) {
-    yd::k_slot_rows<<<1, 1024, 0, st>>>(S, N, arr, s->d_row_off.as<uint32_t>(), s->d_row_len.as<uint32_t>(),
-                                        s->d_counters.as<Counters>());
-    if (s->wide) {
-      yd::k_slot_fill<true><<<(S + 7) / 8, 256, 0, st>>>(S, arr, s->d_row_off.as<uint32_t>(),
-                                                         s->d_row_len.as<uint32_t>(), nullptr,
-                                                         s->d_codes.as<unsigned long long>());
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    YD_CUDA_CHECK(cudaMemsetAsync(s->d_res.p, 0xFF, size_t(N) * 4, st));  // == kResEnvNotFound
+    YD_CUDA_CHECK(cudaEventRecord(s->ev[1], st));
+    if (have_work) launches += LaunchSlotTable(s, N, solver == 2);
+    if (have_work && solver == 2) {
+      YD_CUDA_CHECK(cudaEventRecord(s->ev[2], st));
+      launches += LaunchStream(s, N, slot_bound);
     } else {
-      yd::k_slot_fill<false><<<(S + 7) / 8, 256, 0, st>>>(S, arr, s->d_row_off.as<uint32_t>(),
-                                                          s->d_row_len.as<uint32_t>(),
-                                                          s->d_codes.as<uint32_t>(), nullptr);
+      YD_CUDA_CHECK(cudaEventRecord(s->ev[2], st));
+      if (have_work) launches += LaunchRowscan(s, N);
     }
-    launches += 2;
-  }
-  YD_CUDA_CHECK(cudaEventRecord(s->ev[2], st));
-  if (S && s->n_comps) {
-    yd::SolveArgs a{};
-    a.reqs = s->d_reqs.as<yd_task_req>();
-    a.n = N;
-    a.res = s->d_res.as<uint32_t>();
-    a.env_comp = s->d_env_comp.as<uint32_t>();
-    a.env_local = s->d_env_local.as<uint32_t>();
-    a.n_envs = s->n_envs_dev;
-    a.comp_sv_off = s->d_comp_sv_off.as<uint32_t>();
-    a.comp_sv = s->d_comp_sv.as<uint32_t>();
-    a.comp_mask_off = s->d_comp_mask_off.as<uint32_t>();
-    a.comp_nwarps = s->d_comp_nwarps.as<uint32_t>();
-    a.envmask = s->d_envmask.as<uint8_t>();
-    a.sv_comp = s->d_sv_comp.as<uint32_t>();
-    a.sv_local = s->d_sv_local.as<uint32_t>();
-    a.ip_off = s->d_ip_off.as<uint32_t>();
-    a.ip_sv = s->d_ip_sv.as<uint32_t>();
-    a.n_ips = s->n_ips_dev;
-    a.sv = arr;
-    a.row_off = s->d_row_off.as<uint32_t>();
-    a.codes = s->d_codes.p;
-    // Two register budgets: up to 8 solver warps (2048 servants per component) plus
-    // 8 producer warps run with <= 128 registers per thread; larger components are
-    // capped at 64 registers.
-    const unsigned threads = std::min(32u, s->max_warps + yd::kMaxProducers) * 32;
-    if (threads <= 512) {
-      if (s->wide) yd::k_solve_rowscan<unsigned long long, 512><<<s->n_comps, threads, 0, st>>>(a);
-      else yd::k_solve_rowscan<uint32_t, 512><<<s->n_comps, threads, 0, st>>>(a);
-    } else {
-      if (s->wide) yd::k_solve_rowscan<unsigned long long, 1024><<<s->n_comps, threads, 0, st>>>(a);
-      else yd::k_solve_rowscan<uint32_t, 1024><<<s->n_comps, threads, 0, st>>>(a);
+    YD_CUDA_CHECK(cudaEventRecord(s->ev[3], st));
+    if (have_work && solver == 2) {
+      // class-table overflow / list overflow => nothing was decided; rerun with solver 1
+      uint32_t* meta = MakeClassTable(s).meta;
+      YD_CUDA_CHECK(cudaMemcpyAsync(s->h_small.p, meta, 8, cudaMemcpyDeviceToHost, st));
+      YD_CUDA_CHECK(cudaStreamSynchronize(st));
+      if (s->h_small.as<uint32_t>()[1] != 0) {
+        if (s->max_comp_servants > kRowscanMaxComponent) {
+          fprintf(stderr, "ydsched: class table overflow and components too large for the row-scan solver\n");
+          abort();
+        }
+        solver = 1;
+        continue;
+      }
     }
-    launches += 1;
+    break;
   }
-  YD_CUDA_CHECK(cudaEventRecord(s->ev[3], st));
   yd::k_final_count<<<nb, 1024, 0, st>>>(s->d_res.as<uint32_t>(), N, s->d_blk.as<uint32_t>());
   yd::k_final_scan<<<1, 1024, 0, st>>>(s->d_blk.as<uint32_t>(), nb, s->d_counters.as<Counters>());
   yd::k_final_write<<<nb, 1024, 0, st>>>(s->d_res.as<uint32_t>(), s->d_reqs.as<yd_task_req>(), N,
                                          s->d_blk.as<uint32_t>(), s->d_comp_sv.as<uint32_t>(), (long long)now_ns,
-                                         s->ring(),
-                                         s->d_out.as<yd_grant>());
+                                         s->ring(), s->d_out.as<yd_grant>());
   launches += 3;
   YD_CUDA_CHECK(cudaGetLastError());
   YD_CUDA_CHECK(cudaEventRecord(s->ev[4], st));
@@ -599,7 +826,7 @@ void yd_wait_for_starting_new_tasks(yd_sched* s, int64_t now_ns, const yd_task_r
   stt.decisions = N;
   stt.granted = c->granted;
   stt.kernel_launches = launches;
-  stt.solver = 1;
+  stt.solver = solver;
   stt.h2d_bytes = size_t(N) * sizeof(yd_task_req);
   stt.d2h_bytes = size_t(N) * sizeof(yd_grant) + sizeof(Counters);
   s->have_stats = true;
