@@ -142,3 +142,34 @@ def test_native_library_is_what_ran(make_dispatcher):
     assert st["kernel_launches"] >= 4 and st["solver"] in (1, 2) and st["decisions"] == 1000
     maps = Path("/proc/self/maps").read_text()
     assert "libydsched.so" in maps
+
+
+@pytest.mark.parametrize("n_classes", [40, 300])
+def test_many_classes(make_dispatcher, n_classes):
+    """More (digest, min_version) classes than the solver provisions for: 40 grows the
+    class bound and retries; 300 exceeds the class table and falls back to the row-scan
+    solver.  Either way the answers are the reference's."""
+    import numpy as np
+    from yadcc_b200 import Servant, PRIORITY_USER, PRIORITY_DEDICATED
+
+    rng = np.random.default_rng(n_classes)
+    digests = [f"{i:064x}" for i in range(n_classes // 2)]
+    results = []
+    for kind in ("cuda", "port"):
+        d = make_dispatcher(kind)
+        r = np.random.default_rng(7)
+        for i in range(400):
+            envs = [digests[j] for j in r.choice(len(digests), size=int(r.integers(1, 4)), replace=False)]
+            d.keep_servant_alive(
+                Servant(f"10.3.{i >> 8}.{i & 255}:8335", None, envs, int(r.choice([7, 8])), 16, int(r.integers(0, 6)),
+                        0, 64 << 30, int(r.integers(0, 9)), PRIORITY_DEDICATED if i % 7 == 0 else PRIORITY_USER),
+                10.0, now=0.0)
+        n = 6000
+        reqs = d.make_requests(n, [digests[j] for j in r.integers(0, len(digests), n)],
+                               [f"10.3.{j >> 8}.{j & 255}" if k % 5 == 0 else "172.16.0.9"
+                                for k, j in enumerate(r.integers(0, 400, n))],
+                               r.choice([7, 8], n).astype(np.uint32))
+        results.append(d.wait_for_starting_new_tasks(reqs, 0.5).copy())
+        results.append(d.servant_state()["running_tasks"].copy())
+    assert (results[0] == results[2]).all()
+    assert (results[1] == results[3]).all()

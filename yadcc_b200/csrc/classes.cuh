@@ -26,7 +26,9 @@ constexpr unsigned long long kClsEmpty = ~0ull;
 struct ClassTable {
   unsigned long long* keys;  // [kClsTableSize] digest id << 32 | min_version, or kClsEmpty
   uint32_t* slot_cls;        // [kClsTableSize] class id of the slot
-  uint32_t* meta;            // [0] number of classes, [1] overflow flag
+  uint32_t* meta;            // [0] number of classes, [1] overflow flag (1: too many classes / table full / list
+                             //     too long -> row-scan solver; 2: more classes than cls_bound -> retry with a bigger bound)
+  uint32_t cls_bound;        // classes the per-class grids / tables of this solve are sized for (<= kMaxClasses)
   uint32_t* cls_env;         // [kMaxClasses]
   uint32_t* cls_mv;
   uint32_t* cls_comp;
@@ -86,15 +88,20 @@ __global__ void __launch_bounds__(256) k_cls_insert(const yd_task_req* __restric
   const uint32_t comp = t.env_comp[env];
   if (comp == kNone) return;
   const unsigned long long key = ((unsigned long long)env << 32) | mv;
-  uint32_t s = cls_hash(key);
-  bool done = false;
-  for (uint32_t probe = 0; probe < kClsTableSize && !done; ++probe) {
-    unsigned long long k = ct.keys[s];
-    if (k == kClsEmpty) k = atomicCAS(&ct.keys[s], kClsEmpty, key);
-    if (k == key || k == kClsEmpty) done = true;
-    else s = (s + 1) & (kClsTableSize - 1);
+  // one lane per distinct key of the warp does the probing (the batch has few classes)
+  const uint32_t active = __activemask();
+  const uint32_t peers = __match_any_sync(active, key);
+  if ((uint32_t)(__ffs(peers) - 1) == (threadIdx.x & 31)) {
+    uint32_t s = cls_hash(key);
+    bool done = false;
+    for (uint32_t probe = 0; probe < kClsTableSize && !done; ++probe) {
+      unsigned long long k = ct.keys[s];
+      if (k == kClsEmpty) k = atomicCAS(&ct.keys[s], kClsEmpty, key);
+      if (k == key || k == kClsEmpty) done = true;
+      else s = (s + 1) & (kClsTableSize - 1);
+    }
+    if (!done) atomicExch(&ct.meta[1], 1u);  // table full -> caller falls back to the row-scan solver
   }
-  if (!done) atomicExch(&ct.meta[1], 1u);  // table full -> caller falls back to the row-scan solver
   // does the requestor's IP belong to a servant of this component?
   const uint32_t ip = __ldg(reinterpret_cast<const uint2*>(reqs + q) + 1).x;
   if (ip < t.n_ips) {
@@ -152,12 +159,16 @@ __global__ void __launch_bounds__(1024) k_cls_number(TopoView t, ClassTable ct) 
         ct.slot_cls[s] = kNone;
         ct.meta[1] = 1;
       }
+      if (id >= ct.cls_bound && id < kMaxClasses) atomicMax(&ct.meta[1], 2u);  // 1 (hard overflow) wins below
     }
     __syncthreads();
     if (tid == 1023) carry_s += warp_sums[31];
     __syncthreads();
   }
-  if (tid == 0) ct.meta[0] = carry_s < kMaxClasses ? carry_s : kMaxClasses;
+  if (tid == 0) {
+    ct.meta[0] = carry_s < kMaxClasses ? carry_s : kMaxClasses;
+    if (carry_s > kMaxClasses) ct.meta[1] = 1;
+  }
 }
 
 // grid.y = class; threads stride over the servants of the class's component.

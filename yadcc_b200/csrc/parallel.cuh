@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(kRankTile) k_rank_count(const yd_task_req* __r
   if (cls != kNone && wrank == 0) wc[warp][cls] = (uint16_t)__popc(peers);
   __syncthreads();
   // exclusive prefix over the 32 warps, per class; tile total to HBM
-  if (tid < kMaxClasses) {
+  if (tid < ct.cls_bound) {
     uint32_t run = 0;
 #pragma unroll 4
     for (int w = 0; w < 32; ++w) {

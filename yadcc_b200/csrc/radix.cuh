@@ -5,8 +5,9 @@
 // order (tier, utilisation, registry position): ties on the code are broken by
 // position exactly like `first minimum wins` (task_dispatcher.cc:444).
 //
-// One pass = three kernels: per-tile digit histogram, one-block exclusive scan of
-// the (digit-major, tile-minor) counts, stable scatter.  Stability inside a tile:
+// One pass = per-tile digit histogram (a kernel for the first pass; later passes get
+// it from the previous scatter), one-block exclusive scan of the (digit-major,
+// tile-minor) counts, stable scatter.  Stability inside a tile:
 // warp w owns a contiguous chunk of the tile and walks it 32 elements at a time;
 // __match_any_sync ranks equal digits inside a group, per-warp digit counters in
 // shared memory carry the rank across groups, and a prefix over the warps' counts
@@ -45,18 +46,29 @@ __global__ void __launch_bounds__(kRsThreads) k_rs_hist(const KeyT* __restrict__
   for (int i = threadIdx.x; i < kRsBins; i += kRsThreads) hist[i * nb + blockIdx.x] = h[i];
 }
 
-// Generic one-block exclusive scan (in place) of `n` u32 values; total -> *total_out.
-__global__ void __launch_bounds__(1024) k_scan_u32(uint32_t* __restrict__ data, uint32_t n,
+// Generic one-block exclusive scan (in place).  Each thread owns 8 consecutive
+// values (two 16-byte loads), so 8192 values need one block-wide round.  The length
+// is n_static, or (*n_dyn) * per_dyn + 1 when n_dyn != nullptr (sizes that only the
+// device knows, e.g. number of classes x tiles).
+constexpr int kScanItems = 8;
+__global__ void __launch_bounds__(1024) k_scan_u32(uint32_t* __restrict__ data, uint32_t n_static,
+                                                   const uint32_t* __restrict__ n_dyn, uint32_t per_dyn,
                                                    uint32_t* __restrict__ total_out) {
   __shared__ uint32_t warp_sums[32];
   __shared__ uint32_t carry_s;
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t n = n_dyn ? (*n_dyn) * per_dyn + 1 : n_static;
   if (tid == 0) carry_s = 0;
   __syncthreads();
-  for (uint32_t base = 0; base < n; base += 1024) {
-    uint32_t i = base + tid;
-    uint32_t v = i < n ? data[i] : 0;
-    uint32_t x = v;
+  for (uint32_t base = 0; base < n; base += 1024 * kScanItems) {
+    const uint32_t i0 = base + tid * kScanItems;
+    uint32_t v[kScanItems];
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k) v[k] = (i0 + k < n) ? data[i0 + k] : 0;
+    uint32_t sum = 0;
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k) sum += v[k];
+    uint32_t x = sum;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
       uint32_t y = __shfl_up_sync(0xffffffffu, x, d);
@@ -74,8 +86,13 @@ __global__ void __launch_bounds__(1024) k_scan_u32(uint32_t* __restrict__ data, 
       warp_sums[lane] = w;
     }
     __syncthreads();
-    uint32_t carry = carry_s;
-    if (i < n) data[i] = carry + (warp ? warp_sums[warp - 1] : 0) + x - v;
+    const uint32_t carry = carry_s;
+    uint32_t run = carry + (warp ? warp_sums[warp - 1] : 0) + x - sum;
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k) {
+      if (i0 + k < n) data[i0 + k] = run;
+      run += v[k];
+    }
     __syncthreads();
     if (tid == 1023) carry_s = carry + warp_sums[31];
     __syncthreads();
@@ -90,7 +107,8 @@ __global__ void __launch_bounds__(kRsThreads) k_rs_scatter(const KeyT* __restric
                                                            int shift, uint32_t nb,
                                                            const uint32_t* __restrict__ hist_scanned,
                                                            KeyT* __restrict__ keys_out,
-                                                           uint32_t* __restrict__ vals_out) {
+                                                           uint32_t* __restrict__ vals_out,
+                                                           int next_shift, uint32_t* __restrict__ hist_next) {
   __shared__ uint32_t wcnt[kRsWarps][kRsBins];  // per-warp digit counts, then running offsets
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t n = (uint32_t)*n_ptr;
@@ -130,6 +148,8 @@ __global__ void __launch_bounds__(kRsThreads) k_rs_scatter(const KeyT* __restric
     if (valid) {
       keys_out[dst] = k;
       vals_out[dst] = vals_in ? vals_in[idx] : idx;  // first pass: payload = original slot index
+      // histogram of the NEXT pass, per tile of the output array (saves a k_rs_hist launch)
+      if (hist_next) atomicAdd(&hist_next[rs_digit(k, next_shift) * nb + dst / kRsTile], 1u);
     }
   }
 }

@@ -13,8 +13,12 @@ namespace yd {
 
 // ---- grants: task ids in FIFO order = exclusive scan over "granted" flags -----
 
+// `abort_flag` (may be null): non-zero means the solver gave up on this batch (class
+// table overflow) and the host will rerun it; the final kernels then leave all state alone.
 __global__ void __launch_bounds__(1024) k_final_count(const uint32_t* __restrict__ res, uint32_t n,
-                                                      uint32_t* __restrict__ block_counts) {
+                                                      uint32_t* __restrict__ block_counts,
+                                                      const uint32_t* __restrict__ abort_flag) {
+  if (abort_flag && *abort_flag) return;
   uint32_t q = blockIdx.x * 1024 + threadIdx.x;
   int granted = (q < n) && (res[q] < kResTimeout);
   int c = __syncthreads_count(granted);
@@ -22,7 +26,9 @@ __global__ void __launch_bounds__(1024) k_final_count(const uint32_t* __restrict
 }
 
 __global__ void __launch_bounds__(1024) k_final_scan(uint32_t* __restrict__ block_counts, uint32_t nb,
-                                                     Counters* __restrict__ counters) {
+                                                     Counters* __restrict__ counters,
+                                                     const uint32_t* __restrict__ abort_flag) {
+  if (abort_flag && *abort_flag) return;
   __shared__ uint32_t warp_sums[32];
   __shared__ uint32_t carry_s;
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -67,7 +73,9 @@ __global__ void __launch_bounds__(1024) k_final_write(const uint32_t* __restrict
                                                       const uint32_t* __restrict__ block_off,
                                                       const uint32_t* __restrict__ comp_sv,
                                                       long long now_ns, TaskRing ring,
-                                                      yd_grant* __restrict__ out) {
+                                                      yd_grant* __restrict__ out,
+                                                      const uint32_t* __restrict__ abort_flag) {
+  if (abort_flag && *abort_flag) return;
   __shared__ uint32_t warp_cnt[32];
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t q = blockIdx.x * 1024 + tid;

@@ -152,7 +152,8 @@ struct yd_sched {
 
   // slot-stream solver state
   DevBuf d_sv_env_off, d_sv_envs, d_comp_mode;
-  DevBuf d_slot_owner, d_sort_k[2], d_sort_v[2], d_hist;
+  DevBuf d_slot_owner, d_sort_k[2], d_sort_v[2], d_hist[2];
+  uint32_t cls_bound = 16;  // classes the per-class grids are sized for; grows on demand (<= yd::kMaxClasses)
   DevBuf d_cls_keys, d_cls_u32;  // class table: 8-byte keys; all u32 arrays in one allocation
   DevBuf d_spos, d_sr, d_scomp, d_list_cnt, d_list, d_rcls, d_rrank, d_rank_cnt;
   bool stream_attr_set = false;
@@ -465,7 +466,7 @@ void yd_destroy(yd_sched* s) {
                     &s->d_t_flags, &s->d_reqs, &s->d_res, &s->d_out, &s->d_blk, &s->d_row_off, &s->d_row_len,
                     &s->d_codes, &s->d_ids, &s->d_ok, &s->d_counters, &s->d_sv_env_off, &s->d_sv_envs,
                     &s->d_comp_mode, &s->d_slot_owner, &s->d_sort_k[0], &s->d_sort_k[1], &s->d_sort_v[0],
-                    &s->d_sort_v[1], &s->d_hist, &s->d_cls_keys, &s->d_cls_u32, &s->d_spos, &s->d_sr, &s->d_scomp,
+                    &s->d_sort_v[1], &s->d_hist[0], &s->d_hist[1], &s->d_cls_keys, &s->d_cls_u32, &s->d_spos, &s->d_sr, &s->d_scomp,
                     &s->d_list_cnt, &s->d_list, &s->d_rcls, &s->d_rrank, &s->d_rank_cnt}) {
     b->release();
   }
@@ -549,6 +550,7 @@ yd::ClassTable MakeClassTable(yd_sched* s) {
   ct.cls_count = u;                      u += yd::kMaxClasses;
   ct.comp_flags = u;                     u += s->n_comps;
   ct.comp_ncls = u;
+  ct.cls_bound = s->cls_bound;
   return ct;
 }
 
@@ -614,25 +616,34 @@ uint32_t LaunchSort(yd_sched* s, size_t bound, int first_bit, int last_bit) {
   cudaStream_t st = s->st;
   const uint32_t nb = (uint32_t)((bound + yd::kRsTile - 1) / yd::kRsTile);
   const unsigned long long* n_ptr = &s->d_counters.as<Counters>()->slots;
-  s->d_hist.ensure(size_t(yd::kRsBins) * nb * 4);
+  const size_t hbytes = size_t(yd::kRsBins) * nb * 4;
+  s->d_hist[0].ensure(hbytes);
+  s->d_hist[1].ensure(hbytes);
   const KeyT* kin = s->d_codes.as<KeyT>();
   const uint32_t* vin = nullptr;
-  int cur = 0;
+  int cur = 0, hcur = 0;
   uint32_t launches = 0;
+  yd::k_rs_hist<KeyT><<<nb, yd::kRsThreads, 0, st>>>(kin, n_ptr, first_bit, nb, s->d_hist[0].as<uint32_t>());
+  ++launches;
   for (int shift = first_bit; shift <= last_bit; shift += yd::kRsBits) {
     KeyT* kout = s->d_sort_k[cur].as<KeyT>();
     uint32_t* vout = s->d_sort_v[cur].as<uint32_t>();
-    yd::k_rs_hist<KeyT><<<nb, yd::kRsThreads, 0, st>>>(kin, n_ptr, shift, nb, s->d_hist.as<uint32_t>());
-    yd::k_scan_u32<<<1, 1024, 0, st>>>(s->d_hist.as<uint32_t>(), yd::kRsBins * nb, nullptr);
-    yd::k_rs_scatter<KeyT><<<nb, yd::kRsThreads, 0, st>>>(kin, vin, n_ptr, shift, nb, s->d_hist.as<uint32_t>(), kout,
-                                                          vout);
-    launches += 3;
+    const bool more = shift + yd::kRsBits <= last_bit;
+    uint32_t* hnext = nullptr;
+    if (more) {
+      hnext = s->d_hist[hcur ^ 1].as<uint32_t>();
+      YD_CUDA_CHECK(cudaMemsetAsync(hnext, 0, hbytes, st));
+    }
+    yd::k_scan_u32<<<1, 1024, 0, st>>>(s->d_hist[hcur].as<uint32_t>(), yd::kRsBins * nb, nullptr, 0, nullptr);
+    yd::k_rs_scatter<KeyT><<<nb, yd::kRsThreads, 0, st>>>(kin, vin, n_ptr, shift, nb, s->d_hist[hcur].as<uint32_t>(),
+                                                          kout, vout, shift + yd::kRsBits, hnext);
+    launches += 2;
     kin = kout;
     vin = vout;
     cur ^= 1;
+    hcur ^= 1;
   }
-  // result is in buffer cur ^ 1
-  if (cur == 0) {  // odd number of passes leaves it in [0]; even in [1] -> normalise to [0]
+  if (cur == 0) {  // an even number of passes leaves the result in [1]: normalise to [0]
     std::swap(s->d_sort_k[0], s->d_sort_k[1]);
     std::swap(s->d_sort_v[0], s->d_sort_v[1]);
   }
@@ -663,8 +674,9 @@ uint32_t LaunchStream(yd_sched* s, uint32_t N, size_t slot_bound) {
   yd::ServantArrays arr = s->arrays();
   yd::k_cls_insert<<<(N + 255) / 256, 256, 0, st>>>(s->d_reqs.as<yd_task_req>(), N, t, ct);
   yd::k_cls_number<<<1, 1024, 0, st>>>(t, ct);
-  yd::k_cls_elig<<<dim3(std::max(1u, std::min(64u, (s->max_comp_servants + 255) / 256)), yd::kMaxClasses), 256, 0,
-                   st>>>(t, ct, arr);
+  const uint32_t CB = s->cls_bound;
+  yd::k_cls_elig<<<dim3(std::max(1u, std::min(64u, (s->max_comp_servants + 255) / 256)), CB), 256, 0, st>>>(t, ct,
+                                                                                                             arr);
   launches += 3;
 
   // ---- 3. per-class sorted slot lists ------------------------------------------
@@ -674,16 +686,16 @@ uint32_t LaunchStream(yd_sched* s, uint32_t N, size_t slot_bound) {
       s->d_run.as<uint32_t>(), s->d_sv_comp.as<uint32_t>(), s->d_spos.as<uint32_t>(), s->d_sr.as<uint32_t>(),
       s->d_scomp.as<uint32_t>());
   const uint32_t n_tiles = (uint32_t)((slot_bound + yd::kListTile - 1) / yd::kListTile);
-  const size_t n_cnt = size_t(yd::kMaxClasses) * n_tiles + 1;
+  const size_t n_cnt = size_t(CB) * n_tiles + 1;
   s->d_list_cnt.ensure(n_cnt * 4);
   YD_CUDA_CHECK(cudaMemsetAsync(s->d_list_cnt.p, 0, n_cnt * 4, st));
-  yd::k_list_count<<<dim3(n_tiles, yd::kMaxClasses), yd::kListTile, 0, st>>>(
+  yd::k_list_count<<<dim3(n_tiles, CB), yd::kListTile, 0, st>>>(
       m_ptr, s->d_spos.as<uint32_t>(), s->d_scomp.as<uint32_t>(), t, ct, arr, n_tiles, s->d_list_cnt.as<uint32_t>());
-  yd::k_scan_u32<<<1, 1024, 0, st>>>(s->d_list_cnt.as<uint32_t>(), (uint32_t)n_cnt, nullptr);
+  yd::k_scan_u32<<<1, 1024, 0, st>>>(s->d_list_cnt.as<uint32_t>(), 0, ct.meta, n_tiles, nullptr);
   // a slot belongs to at most (classes of its component) lists; bound by classes x slots is wasteful,
   // so size for the common case and let the device tell us (checked after the solve)
   s->d_list.ensure(std::max<size_t>(slot_bound, 1) * 8 * 4);
-  yd::k_list_fill<<<dim3(n_tiles, yd::kMaxClasses), yd::kListTile, 0, st>>>(
+  yd::k_list_fill<<<dim3(n_tiles, CB), yd::kListTile, 0, st>>>(
       m_ptr, s->d_spos.as<uint32_t>(), s->d_sr.as<uint32_t>(), s->d_scomp.as<uint32_t>(), t, ct, arr, n_tiles,
       s->d_list_cnt.as<uint32_t>(), s->d_list.as<uint2>(), (uint32_t)(slot_bound * 4));
   launches += 4;
@@ -691,13 +703,13 @@ uint32_t LaunchStream(yd_sched* s, uint32_t N, size_t slot_bound) {
   // ---- 4a. data-parallel path: single-class components without self-requests -----
   yd::k_comp_mode<<<(s->n_comps + 255) / 256, 256, 0, st>>>(s->n_comps, ct, s->d_comp_mode.as<uint32_t>());
   const uint32_t n_rtiles = (N + yd::kRankTile - 1) / yd::kRankTile;
-  const size_t n_rcnt = size_t(yd::kMaxClasses) * n_rtiles;
+  const size_t n_rcnt = size_t(CB) * n_rtiles + 1;
   s->d_rcls.ensure(size_t(N) * 4); s->d_rrank.ensure(size_t(N) * 4); s->d_rank_cnt.ensure(n_rcnt * 4);
   yd::k_rank_count<<<n_rtiles, yd::kRankTile, 0, st>>>(s->d_reqs.as<yd_task_req>(), N, t, ct,
                                                         s->d_comp_mode.as<uint32_t>(), n_rtiles,
                                                         s->d_rcls.as<uint32_t>(), s->d_rrank.as<uint32_t>(),
                                                         s->d_rank_cnt.as<uint32_t>());
-  yd::k_scan_u32<<<1, 1024, 0, st>>>(s->d_rank_cnt.as<uint32_t>(), (uint32_t)n_rcnt, nullptr);
+  yd::k_scan_u32<<<1, 1024, 0, st>>>(s->d_rank_cnt.as<uint32_t>(), 0, ct.meta, n_rtiles, nullptr);
   yd::k_rank_assign<<<(N + 255) / 256, 256, 0, st>>>(N, n_rtiles, t, ct, s->d_rcls.as<uint32_t>(),
                                                      s->d_rrank.as<uint32_t>(), s->d_rank_cnt.as<uint32_t>(),
                                                      s->d_list_cnt.as<uint32_t>(), n_tiles, s->d_list.as<uint2>(),
@@ -773,46 +785,50 @@ void yd_wait_for_starting_new_tasks(yd_sched* s, int64_t now_ns, const yd_task_r
   uint32_t launches = 0;
   YD_CUDA_CHECK(cudaEventRecord(s->ev[0], st));
   YD_CUDA_CHECK(cudaMemcpyAsync(s->d_reqs.p, reqs, size_t(N) * sizeof(yd_task_req), cudaMemcpyHostToDevice, st));
-  for (int attempt = 0; attempt < 2; ++attempt) {
+  for (int attempt = 0;; ++attempt) {
     YD_CUDA_CHECK(cudaMemsetAsync(s->d_res.p, 0xFF, size_t(N) * 4, st));  // == kResEnvNotFound
     YD_CUDA_CHECK(cudaEventRecord(s->ev[1], st));
     if (have_work) launches += LaunchSlotTable(s, N, solver == 2);
+    YD_CUDA_CHECK(cudaEventRecord(s->ev[2], st));
+    const uint32_t* abort_flag = nullptr;
     if (have_work && solver == 2) {
-      YD_CUDA_CHECK(cudaEventRecord(s->ev[2], st));
       launches += LaunchStream(s, N, slot_bound);
-    } else {
-      YD_CUDA_CHECK(cudaEventRecord(s->ev[2], st));
-      if (have_work) launches += LaunchRowscan(s, N);
+      abort_flag = MakeClassTable(s).meta + 1;
+    } else if (have_work) {
+      launches += LaunchRowscan(s, N);
     }
     YD_CUDA_CHECK(cudaEventRecord(s->ev[3], st));
-    if (have_work && solver == 2) {
-      // class-table overflow / list overflow => nothing was decided; rerun with solver 1
-      uint32_t* meta = MakeClassTable(s).meta;
-      YD_CUDA_CHECK(cudaMemcpyAsync(s->h_small.p, meta, 8, cudaMemcpyDeviceToHost, st));
-      YD_CUDA_CHECK(cudaStreamSynchronize(st));
-      if (s->h_small.as<uint32_t>()[1] != 0) {
+    yd::k_final_count<<<nb, 1024, 0, st>>>(s->d_res.as<uint32_t>(), N, s->d_blk.as<uint32_t>(), abort_flag);
+    yd::k_final_scan<<<1, 1024, 0, st>>>(s->d_blk.as<uint32_t>(), nb, s->d_counters.as<Counters>(), abort_flag);
+    yd::k_final_write<<<nb, 1024, 0, st>>>(s->d_res.as<uint32_t>(), s->d_reqs.as<yd_task_req>(), N,
+                                           s->d_blk.as<uint32_t>(), s->d_comp_sv.as<uint32_t>(), (long long)now_ns,
+                                           s->ring(), s->d_out.as<yd_grant>(), abort_flag);
+    launches += 3;
+    YD_CUDA_CHECK(cudaGetLastError());
+    YD_CUDA_CHECK(cudaEventRecord(s->ev[4], st));
+    YD_CUDA_CHECK(cudaMemcpyAsync(out, s->d_out.p, size_t(N) * sizeof(yd_grant), cudaMemcpyDeviceToHost, st));
+    YD_CUDA_CHECK(cudaMemcpyAsync(s->h_counters.p, s->d_counters.p, sizeof(Counters), cudaMemcpyDeviceToHost, st));
+    if (abort_flag) {
+      YD_CUDA_CHECK(cudaMemcpyAsync(s->h_small.p, abort_flag - 1, 8, cudaMemcpyDeviceToHost, st));
+    }
+    YD_CUDA_CHECK(cudaEventRecord(s->ev[5], st));
+    YD_CUDA_CHECK(cudaStreamSynchronize(st));
+    if (abort_flag && s->h_small.as<uint32_t>()[1] != 0) {
+      // Nothing was decided (the stream solver and the final kernels all stood down).
+      const uint32_t flag = s->h_small.as<uint32_t>()[1], ncls = s->h_small.as<uint32_t>()[0];
+      if (flag == 2 && attempt < 3) {  // more classes than provisioned: grow and go again
+        while (s->cls_bound < ncls && s->cls_bound < yd::kMaxClasses) s->cls_bound *= 2;
+      } else {
         if (s->max_comp_servants > kRowscanMaxComponent) {
           fprintf(stderr, "ydsched: class table overflow and components too large for the row-scan solver\n");
           abort();
         }
         solver = 1;
-        continue;
       }
+      continue;
     }
     break;
   }
-  yd::k_final_count<<<nb, 1024, 0, st>>>(s->d_res.as<uint32_t>(), N, s->d_blk.as<uint32_t>());
-  yd::k_final_scan<<<1, 1024, 0, st>>>(s->d_blk.as<uint32_t>(), nb, s->d_counters.as<Counters>());
-  yd::k_final_write<<<nb, 1024, 0, st>>>(s->d_res.as<uint32_t>(), s->d_reqs.as<yd_task_req>(), N,
-                                         s->d_blk.as<uint32_t>(), s->d_comp_sv.as<uint32_t>(), (long long)now_ns,
-                                         s->ring(), s->d_out.as<yd_grant>());
-  launches += 3;
-  YD_CUDA_CHECK(cudaGetLastError());
-  YD_CUDA_CHECK(cudaEventRecord(s->ev[4], st));
-  YD_CUDA_CHECK(cudaMemcpyAsync(out, s->d_out.p, size_t(N) * sizeof(yd_grant), cudaMemcpyDeviceToHost, st));
-  YD_CUDA_CHECK(cudaMemcpyAsync(s->h_counters.p, s->d_counters.p, sizeof(Counters), cudaMemcpyDeviceToHost, st));
-  YD_CUDA_CHECK(cudaEventRecord(s->ev[5], st));
-  YD_CUDA_CHECK(cudaStreamSynchronize(st));
   const Counters* c = s->h_counters.as<Counters>();
   s->next_id += c->granted;
 
