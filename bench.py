@@ -59,6 +59,8 @@ def build_workload(name: str, rank: int):
         return S.config2(100_000, 2000, 8, seed=seed, variant="random")
     if name == "cfg1":
         return S.config1(seed=seed)
+    if name == "cfg-self":
+        return S.config_self(seed=seed)
     if name == "cfg3":
         return S.config3(1_000_000, 4000, 8, seed=seed)
     raise SystemExit(f"unknown workload {name}")
@@ -269,6 +271,7 @@ def run_ours(args):
             "cpu_baseline": cpu,
             "clocks": sampler.summary(),
             "wall_s_timed_loop": t_wall1 - t_wall0,
+            "e2e_ms_steps": [round(x, 3) for x in e2e_ms],
             "latency_ms": {"p50": float(np.percentile(e2e_ms, 50)), "p99": float(np.percentile(e2e_ms, 99)),
                            "what": "enqueue->grant for every request of the batch (whole-batch call)"},
         }

@@ -14,8 +14,8 @@ from yadcc_b200 import TaskDispatcher  # noqa: E402
 from yadcc_b200 import streams as S  # noqa: E402
 
 REF = ROOT / "oracle" / "_ref" / "libydref.so"
-NAMES = ["cfg1", "cfg2-mod-small", "cfg2-random-small", "cfg3-small", "cfg3-mod-small"] + [f"fuzz-{i}" for i in range(40)]
-BIG = ["cfg2-mod", "cfg2-random"]  # full BASELINE sizes; ~2-4 s each on the reference
+NAMES = ["cfg1", "cfg2-mod-small", "cfg2-random-small", "cfg3-small", "cfg3-mod-small", "cfg-self-small"] + [f"fuzz-{i}" for i in range(40)]
+BIG = ["cfg2-mod", "cfg2-random", "cfg-self"]  # full BASELINE sizes; ~2-4 s each on the reference
 
 
 def main():

@@ -56,7 +56,8 @@ def test_fuzz_large_components(make_dispatcher, seed, solver):
 
 
 @pytest.mark.parametrize("solver", [1, 2], ids=SOLVERS.get)
-@pytest.mark.parametrize("name", ["cfg1", "cfg2-mod-small", "cfg2-random-small", "cfg3-small", "cfg3-mod-small"])
+@pytest.mark.parametrize("name", ["cfg1", "cfg2-mod-small", "cfg2-random-small", "cfg3-small", "cfg3-mod-small",
+                                  "cfg-self-small", "cfg-self"])
 def test_small_configs(make_dispatcher, name, solver):
     tr = _parity(make_dispatcher, name, solver=solver)
     golden = json.loads((GOLDEN / "digests.json").read_text())["streams"]

@@ -48,7 +48,8 @@ struct Counters {
   unsigned long long zombies;   // live leases marked zombie
   unsigned long long min_live;  // smallest live id seen by the last tick (or ~0)
   unsigned long long slots;     // slot-table entries of the last solve
-  unsigned long long pad[3];
+  unsigned long long spare;
+  unsigned long long pad[4];    // solver diagnostics (see solve_stream.cuh)
 };
 
 struct ServantArrays {

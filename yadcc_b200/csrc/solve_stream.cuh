@@ -12,9 +12,10 @@
 // O(1) amortised per decision instead of O(servants).
 //
 // One CTA per component.  Producer warps stream/filter/compact the request queue
-// exactly as in solve_rowscan.cuh; ONE solver warp makes the decisions, its 32
-// lanes examining 32 consecutive list entries per step (one coalesced 256-byte
-// load, one shared-memory gather of running_tasks, three ballots).
+// exactly as in solve_rowscan.cuh; ONE solver warp makes the decisions, up to 32
+// per step (speculate-and-commit, see below), falling back to an exact one-request
+// walk (32 list entries per step: one coalesced 256-byte load, one shared-memory
+// gather of running_tasks, three ballots) for the first request that does not fit.
 // running_tasks of the component lives in shared memory for the whole solve.
 #pragma once
 #include "classes.cuh"
@@ -35,6 +36,7 @@ struct StreamArgs {
   const uint2* list;          // (servant local index, running_tasks value of the slot)
   uint32_t max_comp_servants; // dynamic shared memory holds 2 x this many u32
   const uint32_t* comp_mode;  // [C] 0 = this kernel, 1 = handled by the parallel path
+  Counters* counters;         // pad[0..3]: speculation steps, lanes committed by them, exact walks, walk windows
 };
 
 struct StreamShared {
@@ -115,6 +117,20 @@ __device__ __forceinline__ void produce_tile_stream(const StreamArgs& a, StreamS
   }
 }
 
+// Position of the (k+1)-th set bit of `m` (k = 0 .. 31), or 32 if m has fewer set bits.
+// Five popc steps instead of the software loop behind __fns.
+__device__ __forceinline__ uint32_t kth_set_bit(uint32_t m, uint32_t k) {
+  if (__popc(m) <= (int)k) return 32;
+  uint32_t pos = 0;
+#pragma unroll
+  for (int w = 16; w >= 1; w >>= 1) {
+    const uint32_t lowmask = (1u << w) - 1;
+    const uint32_t cnt = __popc((m >> pos) & lowmask);
+    if (k >= cnt) { k -= cnt; pos += w; }
+  }
+  return pos;
+}
+
 constexpr int kStreamProducers = 8;
 
 __global__ void __launch_bounds__((kStreamProducers + 1) * 32, 1) k_solve_stream(StreamArgs a) {
@@ -168,31 +184,131 @@ __global__ void __launch_bounds__((kStreamProducers + 1) * 32, 1) k_solve_stream
   }
 
   // ======================= the solver warp ======================================
+  // Up to 32 consecutive requests are decided per step.  Lane i speculates that the
+  // sequential fold would hand it entry front[class] + (its rank among the group's
+  // earlier requests of the same class); that is exactly right iff
+  //   (1) that entry and those of all lower-ranked same-class lanes are untaken and not the
+  //       respective requestor's own servant (nobody skips anything), and
+  //   (2) no earlier lane of ANOTHER class claims the same slot (s, r).
+  // [Why (2) suffices: a slot of s can only be passed over once it is taken, and slots of
+  // one servant are taken in r order, so any interference between classes shows up as two
+  // lanes claiming the same (s, r).]  The longest prefix of lanes satisfying (1)-(2) is
+  // committed at once; the first offender is decided by the exact one-request walk below,
+  // and the next step starts after it.
+  // Speculation is adaptive: when other classes keep consuming the slots at a class's
+  // front (heavily shared servants), groups commit one or two lanes and the attempt is
+  // pure overhead; after a short commit the next `cooldown` requests go straight to the
+  // exact walk.
+  const uint32_t lt_mask = (1u << lane) - 1;
+  uint32_t cooldown = 0;
+  unsigned long long st_steps = 0, st_lanes = 0, st_walks = 0, st_windows = 0;
   for (uint32_t t = 0; t < n_tiles; ++t) {
     const uint32_t buf = t & 1;
     bar_sync(kBarFull0 + buf, nall);
     const uint32_t cnt = sh.cnt[buf];
     const uint4* __restrict__ dl = sh.desc[buf];
-    uint4 ds = cnt ? dl[0] : make_uint4(0, 0, kNone, 0);
-    for (uint32_t d = 0; d < cnt; ++d) {
-      const uint32_t q = ds.x, c = ds.y;
-      uint32_t selfinfo = ds.z;
-      if (d + 1 < cnt) ds = dl[d + 1];
-      const uint8_t f = sh.fail[c];
-      if (f) {
-        if (lane == 0) a.res[q] = stream_fail_res(f);
+    uint32_t at = 0;
+    while (at < cnt) {
+      if (cooldown == 0) {
+        const uint32_t g = min(32u, cnt - at);
+        const bool act = lane < g;
+        const uint32_t act_mask = g == 32 ? 0xffffffffu : ((1u << g) - 1);
+        const uint4 ds = act ? dl[at + lane] : make_uint4(0, kNone, kNone, 0);
+        const uint32_t c = ds.y;
+        const uint32_t c0 = __shfl_sync(0xffffffffu, c, 0);
+        const bool one_class = __all_sync(0xffffffffu, !act || c == c0);
+        const bool multi_self = ds.z != kNone && (ds.z & 0x80000000u);  // several own servants: exact path
+        bool ok = act;
+        uint2 e = make_uint2(kNone, lane);
+        bool has_slot = false;
+        uint32_t win_pos = 0, peers = act_mask, rank = lane;
+        uint8_t f;
+        if (one_class) {
+          // All lanes of one class (the common shape: one dominant compiler): look at the 32
+          // list entries from the front together and hand the k-th UNTAKEN one to the lane of
+          // rank k -- tolerant of slots other classes consumed since the front last moved.
+          f = sh.fail[c0];
+          const uint32_t idx = sh.front[c0] + lane;
+          uint2 w = make_uint2(0, 0);
+          const bool valid = !f && idx < sh.end[c0];
+          if (valid) w = a.list[idx];
+          const uint32_t U = __ballot_sync(0xffffffffu, valid && !(w.y < run_s[w.x]));
+          const uint32_t p = kth_set_bit(U, lane);  // 32 if there are not that many
+          const uint32_t src = p & 31;
+          const uint32_t ex = __shfl_sync(0xffffffffu, w.x, src), ey = __shfl_sync(0xffffffffu, w.y, src);
+          if (act && !f) {
+            ok = p < 32 && !multi_self && ex != ds.z;  // got one, and it is not my own servant
+            if (ok) { e = make_uint2(ex, ey); has_slot = true; win_pos = p; }
+          }
+          if (__ballot_sync(0xffffffffu, act && !ok) & lt_mask) ok = false;  // (1): lower ranks must be clean
+        } else {
+          f = act ? sh.fail[c] : (uint8_t)0;
+          peers = __match_any_sync(0xffffffffu, c);  // inactive lanes share class kNone
+          rank = __popc(peers & lt_mask);
+          if (act && !f) {
+            const uint32_t idx = sh.front[c] + rank;
+            ok = idx < sh.end[c] && !multi_self;
+            if (ok) {
+              e = a.list[idx];
+              ok = !(e.y < run_s[e.x]) && e.x != ds.z;  // untaken, and not my own servant
+              has_slot = ok;
+              if (!ok) e = make_uint2(kNone, lane);
+            }
+          }
+          const uint32_t okb = __ballot_sync(0xffffffffu, ok);
+          if (peers & lt_mask & ~okb) ok = false;  // (1): a lower-ranked lane of my class broke the pattern
+          // (2): an earlier lane of another class owns that very slot
+          const unsigned long long slot = ((unsigned long long)e.x << 32) | e.y;
+          const uint32_t same = __match_any_sync(0xffffffffu, slot);
+          if (has_slot && (same & lt_mask)) ok = false;
+        }
+        const uint32_t bad = ~__ballot_sync(0xffffffffu, ok) & act_mask;
+        const uint32_t n_ok = bad ? (uint32_t)(__ffs(bad) - 1) : g;
+        // ---- commit the clean prefix -----------------------------------------------
+        if (lane < n_ok) {
+          if (f) {
+            a.res[ds.x] = stream_fail_res(f);
+          } else {
+            atomicMax(&run_s[e.x], e.y + 1);  // several lanes may take consecutive slots of one servant
+            a.res[ds.x] = sv_begin + e.x;
+            if (one_class) {
+              if (lane == n_ok - 1) sh.front[c] += win_pos + 1;  // everything up to my entry is taken now
+            } else {
+              const uint32_t mine = peers & ((n_ok == 32) ? 0xffffffffu : ((1u << n_ok) - 1));
+              if (rank == 0) sh.front[c] += __popc(mine);  // they took front .. front + count - 1
+            }
+          }
+        }
+        __syncwarp();
+        at += n_ok;
+        ++st_steps; st_lanes += n_ok;
+        if (n_ok == g) continue;
+        if (n_ok < (one_class ? 1u : 6u)) cooldown = 48;  // not worth it right now
+      } else {
+        --cooldown;
+      }
+
+      // ---- the first request that did not fit the pattern: exact walk ----------------
+      const uint4 d1 = dl[at];
+      ++at;
+      ++st_walks;
+      const uint32_t q = d1.x, c1 = d1.y;
+      uint32_t selfinfo = d1.z;
+      const uint8_t f1 = sh.fail[c1];
+      if (f1) {
+        if (lane == 0) a.res[q] = stream_fail_res(f1);
         continue;
       }
       // several servants on the requestor's IP: "self" is the first of them that is
       // eligible for this class and free right now (find_if over the free list, cc:372-375)
       if (selfinfo != kNone && (selfinfo & 0x80000000u)) {
         const uint32_t ip = selfinfo & 0x7FFFFFFFu;
-        const uint32_t env = a.ct.cls_env[c], mv = a.ct.cls_mv[c];
+        const uint32_t env = a.ct.cls_env[c1], mv = a.ct.cls_mv[c1];
         uint32_t best = kNone;
-        for (uint32_t u0 = a.t.ip_off[ip], e = a.t.ip_off[ip + 1]; u0 < e && best == kNone; u0 += 32) {
+        for (uint32_t u0 = a.t.ip_off[ip], ue = a.t.ip_off[ip + 1]; u0 < ue && best == kNone; u0 += 32) {
           const uint32_t u = u0 + lane;
           uint32_t cand = kNone;
-          if (u < e) {
+          if (u < ue) {
             const uint32_t p = a.t.ip_sv[u];
             if (a.t.sv_comp[p] == comp) {
               const uint32_t l = a.t.sv_local[p];
@@ -207,21 +323,20 @@ __global__ void __launch_bounds__((kStreamProducers + 1) * 32, 1) k_solve_stream
         selfinfo = best;
       }
       const uint32_t selfl = selfinfo;
-
-      // ---- walk the class's sorted slot list ---------------------------------
-      const uint32_t end = sh.end[c];
-      uint32_t base = sh.front[c];
+      const uint32_t end = sh.end[c1];
+      uint32_t base = sh.front[c1];
       uint32_t new_front = base;
       bool front_open = true;
-      uint32_t self_slot = kNone;  // local index; the own servant's head slot if we passed it
+      uint32_t self_slot = kNone;  // the own servant's head slot, if the walk passed it
       uint32_t win = kNone;
       while (base < end) {
+        ++st_windows;
         const uint32_t idx = base + lane;
         const bool valid = idx < end;
-        uint2 e = make_uint2(0, 0);
-        if (valid) e = a.list[idx];
-        const bool taken = valid && e.y < run_s[e.x];
-        const bool isself = valid && !taken && e.x == selfl;
+        uint2 w = make_uint2(0, 0);
+        if (valid) w = a.list[idx];
+        const bool taken = valid && w.y < run_s[w.x];
+        const bool isself = valid && !taken && w.x == selfl;
         const bool avail = valid && !taken && !isself;
         const uint32_t bT = __ballot_sync(0xffffffffu, taken);
         const uint32_t bS = __ballot_sync(0xffffffffu, isself);
@@ -233,20 +348,22 @@ __global__ void __launch_bounds__((kStreamProducers + 1) * 32, 1) k_solve_stream
         }
         if (self_slot == kNone && bS) self_slot = selfl;
         if (bA) {
-          win = __shfl_sync(0xffffffffu, e.x, __ffs(bA) - 1);
+          const uint32_t wl = __ffs(bA) - 1;
+          win = __shfl_sync(0xffffffffu, w.x, wl);
+          if (base + wl == new_front) ++new_front;  // granted the front entry itself: it is taken now
           break;
         }
         base += 32;
       }
       if (win == kNone && self_slot != kNone) win = self_slot;  // last resort (cc:394-396)
       if (lane == 0) {
-        sh.front[c] = new_front;
+        sh.front[c1] = new_front;
         if (win != kNone) {
           run_s[win] += 1;
           a.res[q] = sv_begin + win;
         } else {
           a.res[q] = kResTimeout;  // the class has eligible servants but none is free (cc:116-118)
-          sh.fail[c] = 1;          // ... and within this batch none will become free again
+          sh.fail[c1] = 1;         // ... and within this batch none will become free again
         }
       }
       __syncwarp();
@@ -254,6 +371,10 @@ __global__ void __launch_bounds__((kStreamProducers + 1) * 32, 1) k_solve_stream
     if (t + 2 < n_tiles) bar_arrive(kBarFree0 + buf, nall);
   }
 
+  if (lane == 0 && a.counters) {
+    atomicAdd(&a.counters->pad[0], st_steps); atomicAdd(&a.counters->pad[1], st_lanes);
+    atomicAdd(&a.counters->pad[2], st_walks); atomicAdd(&a.counters->pad[3], st_windows);
+  }
   // ---- write back running_tasks / ever_assigned_tasks (cc:123-124) -----------
   for (uint32_t i = lane; i < n_sv; i += 32) {
     const uint32_t pos = a.t.comp_sv[sv_begin + i];

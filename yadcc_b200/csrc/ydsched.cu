@@ -730,6 +730,8 @@ uint32_t LaunchStream(yd_sched* s, uint32_t N, size_t slot_bound) {
   a.list = s->d_list.as<uint2>();
   a.max_comp_servants = s->max_comp_servants;
   a.comp_mode = s->d_comp_mode.as<uint32_t>();
+  a.counters = s->d_counters.as<Counters>();
+  YD_CUDA_CHECK(cudaMemsetAsync(&s->d_counters.as<Counters>()->pad[0], 0, 32, st));
   const size_t dyn = size_t(s->max_comp_servants) * 8;
   if (!s->stream_attr_set) {
     YD_CUDA_CHECK(cudaFuncSetAttribute(yd::k_solve_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, 190 * 1024));
@@ -846,6 +848,10 @@ void yd_wait_for_starting_new_tasks(yd_sched* s, int64_t now_ns, const yd_task_r
   stt.h2d_bytes = size_t(N) * sizeof(yd_task_req);
   stt.d2h_bytes = size_t(N) * sizeof(yd_grant) + sizeof(Counters);
   s->have_stats = true;
+  if (getenv("YDSCHED_DEBUG")) {
+    fprintf(stderr, "ydsched: solver %u spec_steps %llu spec_lanes %llu walks %llu windows %llu solve_ms %.3f\n", solver,
+            c->pad[0], c->pad[1], c->pad[2], c->pad[3], stt.solve_ms);
+  }
 }
 
 // KeepTaskAlive x n, cc:142-165.

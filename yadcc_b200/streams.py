@@ -285,6 +285,29 @@ def config2(n_tasks: int = 100_000, n_servants: int = 2000, n_digests: int = 8, 
                     {"tasks": n_tasks, "servants": n_servants, "digests": n_digests, "variant": variant})
 
 
+def config_self(n_tasks: int = 100_000, n_servants: int = 2000, seed: int = 44, run_len: int = 4) -> Workload:
+    """Production-like: ONE compiler digest, every requestor is itself a servant (so the
+    self-exclusion rule, task_dispatcher.cc:372-379, is live for every request) and requests
+    arrive in runs of `run_len` from the same machine (immediate_reqs > 1 per RPC)."""
+    rng = np.random.default_rng(seed)
+    dg = hex_digest(rng)
+    servants = [
+        Servant(f"{servant_ip(i)}:8335", None, [dg], 8, 128, int(rng.integers(0, 20)), 256 * GiB, 200 * GiB, 51,
+                _abi.PRIORITY_DEDICATED if i % 10 == 0 else _abi.PRIORITY_USER)
+        for i in range(n_servants)
+    ]
+
+    def build(d: TaskDispatcher) -> np.ndarray:
+        e = d.intern_env(dg)
+        ips = np.asarray([d.intern_ip(servant_ip(i)) for i in range(n_servants)], dtype=np.uint32)
+        r = np.random.default_rng(seed + 1)
+        who = np.repeat(r.integers(0, n_servants, (n_tasks + run_len - 1) // run_len), run_len)[:n_tasks]
+        return _requests(d, np.full(n_tasks, e, np.uint32), ips[who], 8)
+
+    return Workload("cfg-self", servants, [dg], build,
+                    {"tasks": n_tasks, "servants": n_servants, "digests": 1, "self": "every requestor is a servant"})
+
+
 def _mixed_servants(n_servants: int, dgs: list[str], rng: np.random.Generator, envs_per: str = "mod") -> list[Servant]:
     """cfg 3/5 servant mix: nproc in {32,64,96,128}; USER 40% / DEDICATED 95% capacity
     (daemon/cloud/execution_engine.cc:132,153); load ~ U[0,nproc]; 15% low memory;
@@ -481,6 +504,10 @@ def named_stream(name: str, d: TaskDispatcher) -> Stream:
         return config2(variant="mod").stream(d)
     if name == "cfg2-random":
         return config2(variant="random").stream(d)
+    if name == "cfg-self-small":
+        return config_self(6000, 150).stream(d)
+    if name == "cfg-self":
+        return config_self().stream(d)
     if name == "cfg3-small":
         return rounds_stream(config3(20000, 300, 8), d, max_rounds=4)
     if name == "cfg3-mod-small":
