@@ -67,6 +67,8 @@ typedef struct yd_config {
   /* Solver selection for the CUDA backend: 0 = auto, 1 = row-scan solver,
    * 2 = slot-stream solver.  Ignored by the oracles. */
   uint32_t solver;
+  /* bit 0: CUDA backend launches the solve kernel by kernel instead of replaying a
+   * captured CUDA graph, so yd_solve_stats can split prep / solve / final. */
   uint32_t reserved;
 } yd_config;
 

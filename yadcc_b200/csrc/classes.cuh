@@ -78,10 +78,10 @@ __device__ __forceinline__ bool servant_has_env(const TopoView& t, uint32_t pos,
   return false;
 }
 
-__global__ void __launch_bounds__(256) k_cls_insert(const yd_task_req* __restrict__ reqs, uint32_t n, TopoView t,
-                                                    ClassTable ct) {
+__global__ void __launch_bounds__(256) k_cls_insert(const yd_task_req* __restrict__ reqs,
+                                                    const DynParams* __restrict__ dp, TopoView t, ClassTable ct) {
   uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
-  if (q >= n) return;
+  if (q >= dp->n) return;
   const uint2 w0 = __ldg(reinterpret_cast<const uint2*>(reqs + q));
   const uint32_t env = w0.x, mv = w0.y;
   if (env >= t.n_envs) return;

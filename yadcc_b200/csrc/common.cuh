@@ -52,6 +52,16 @@ struct Counters {
   unsigned long long pad[4];    // solver diagnostics (see solve_stream.cuh)
 };
 
+// Per-call scalars.  They live in device memory (copied from a pinned host struct by the
+// first node of the captured solve graph) so that one CUDA graph replays for every call
+// of the same size class.
+struct DynParams {
+  uint32_t n;  // exact number of requests (grids are sized for the next power of two)
+  uint32_t pad;
+  long long now_ns;
+  unsigned long long ring_lo, ring_next;
+};
+
 struct ServantArrays {
   uint32_t* nproc;
   uint32_t* load;

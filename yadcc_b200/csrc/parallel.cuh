@@ -28,8 +28,8 @@ __global__ void k_comp_mode(uint32_t n_comps, ClassTable ct, uint32_t* __restric
 
 constexpr int kRankTile = 1024;
 
-__global__ void __launch_bounds__(kRankTile) k_rank_count(const yd_task_req* __restrict__ reqs, uint32_t n,
-                                                          TopoView t, ClassTable ct,
+__global__ void __launch_bounds__(kRankTile) k_rank_count(const yd_task_req* __restrict__ reqs,
+                                                          const DynParams* __restrict__ dp, TopoView t, ClassTable ct,
                                                           const uint32_t* __restrict__ comp_mode, uint32_t n_tiles,
                                                           uint32_t* __restrict__ rcls,   // [n] class or kNone
                                                           uint32_t* __restrict__ rrank,  // [n] rank inside the tile
@@ -38,6 +38,7 @@ __global__ void __launch_bounds__(kRankTile) k_rank_count(const yd_task_req* __r
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   for (uint32_t i = tid; i < 32 * kMaxClasses / 2; i += kRankTile) reinterpret_cast<uint32_t*>(&wc[0][0])[i] = 0;
   __syncthreads();
+  const uint32_t n = dp->n;
   const uint32_t q = blockIdx.x * kRankTile + tid;
   uint32_t cls = kNone;
   if (q < n) {
@@ -73,7 +74,8 @@ __global__ void __launch_bounds__(kRankTile) k_rank_count(const yd_task_req* __r
 }
 
 // tile_off = exclusive scan of tile_cnt over (class-major, tile-minor).
-__global__ void __launch_bounds__(256) k_rank_assign(uint32_t n, uint32_t n_tiles, TopoView t, ClassTable ct,
+__global__ void __launch_bounds__(256) k_rank_assign(const DynParams* __restrict__ dp, uint32_t n_tiles, TopoView t,
+                                                     ClassTable ct,
                                                      const uint32_t* __restrict__ rcls,
                                                      const uint32_t* __restrict__ rrank,
                                                      const uint32_t* __restrict__ tile_off,
@@ -81,7 +83,7 @@ __global__ void __launch_bounds__(256) k_rank_assign(uint32_t n, uint32_t n_tile
                                                      const uint2* __restrict__ list, ServantArrays sv,
                                                      uint32_t* __restrict__ res) {
   const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
-  if (q >= n) return;
+  if (q >= dp->n) return;
   const uint32_t c = rcls[q];
   if (c == kNone) return;  // not ours: the sequential solver (or nobody) answers it
   if (ct.cls_nelig[c] == 0) { res[q] = kResEnvNotFound; return; }  // cc:105-108

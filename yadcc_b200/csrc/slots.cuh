@@ -24,13 +24,14 @@ namespace yd {
 
 // Single CTA: row lengths + exclusive scan -> row offsets.  S is a few thousand,
 // so one 1024-thread block with a running carry is launch-latency bound anyway.
-__global__ void __launch_bounds__(1024) k_slot_rows(uint32_t S, uint32_t n_requests,
+__global__ void __launch_bounds__(1024) k_slot_rows(uint32_t S, const DynParams* __restrict__ dp,
                                                     ServantArrays sv, uint32_t* __restrict__ row_off,
                                                     uint32_t* __restrict__ row_len,
                                                     Counters* __restrict__ counters) {
   __shared__ uint32_t warp_sums[32];
   __shared__ uint32_t carry_s;
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t n_requests = dp->n;
   if (tid == 0) carry_s = 0;
   __syncthreads();
   for (uint32_t base = 0; base < S; base += 1024) {

@@ -46,7 +46,7 @@ constexpr int kBarSolver = 1, kBarProducer = 2, kBarFull0 = 3, kBarFree0 = 5;
 
 struct SolveArgs {
   const yd_task_req* reqs;
-  uint32_t n;
+  const DynParams* dp;  // dp->n requests
   uint32_t* res;  // per request: index into comp_sv of the picked servant, or kRes*
   // topology (rebuilt on the host when the servant set / digests change)
   const uint32_t* env_comp;   // [n_envs] component of a digest id, kNone if nobody holds it
@@ -217,13 +217,14 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_solve_rowscan(SolveArgs a) {
   for (uint32_t i = tid; i < kFailSlots; i += nall) sh.fail[i] = ~0ull;  // el = 0x7FFFFFFF never occurs
   __syncthreads();  // everyone is still here (exited warps count as arrived)
 
-  const uint32_t n_tiles = (a.n + kTile - 1) / kTile;
+  const uint32_t n_req = a.dp->n;
+  const uint32_t n_tiles = (n_req + kTile - 1) / kTile;
 
   // ======================= producer warps ===================================
   if (warp >= nwarps) {
     const uint32_t pw = warp - nwarps;
     for (uint32_t t = 0; t < n_tiles; ++t) {
-      const uint32_t buf = t & 1, base = t * kTile, tile_end = min(a.n, base + kTile);
+      const uint32_t buf = t & 1, base = t * kTile, tile_end = min(n_req, base + kTile);
       if (t >= 2) bar_sync(kBarFree0 + buf, nall);  // solvers are done with this buffer
       produce_tile(a, sh, comp, buf, base, tile_end, pw, nprod, lane, kBarProducer);
       if (pw == 0 && lane == 0) {
@@ -285,7 +286,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_solve_rowscan(SolveArgs a) {
     if (specialised) {
       bar_sync(kBarFull0 + buf, nall);
     } else {
-      const uint32_t base = t * kTile, tile_end = min(a.n, base + kTile);
+      const uint32_t base = t * kTile, tile_end = min(n_req, base + kTile);
       produce_tile(a, sh, comp, buf, base, tile_end, warp, nwarps, lane, kBarSolver);
       if (tid == 0) {
         uint32_t c = 0;

@@ -25,7 +25,7 @@ namespace yd {
 
 struct StreamArgs {
   const yd_task_req* reqs;
-  uint32_t n;
+  const DynParams* dp;  // dp->n requests
   uint32_t* res;
   TopoView t;
   ClassTable ct;
@@ -164,12 +164,13 @@ __global__ void __launch_bounds__((kStreamProducers + 1) * 32, 1) k_solve_stream
   }
   __syncthreads();
 
-  const uint32_t n_tiles = (a.n + kTile - 1) / kTile;
+  const uint32_t n_req = a.dp->n;
+  const uint32_t n_tiles = (n_req + kTile - 1) / kTile;
   // ======================= producer warps (1..8) ==============================
   if (warp >= 1) {
     const uint32_t pw = warp - 1;
     for (uint32_t t = 0; t < n_tiles; ++t) {
-      const uint32_t buf = t & 1, base = t * kTile, tile_end = min(a.n, base + kTile);
+      const uint32_t buf = t & 1, base = t * kTile, tile_end = min(n_req, base + kTile);
       if (t >= 2) bar_sync(kBarFree0 + buf, nall);
       produce_tile_stream(a, sh, comp, buf, base, tile_end, pw, kStreamProducers, lane);
       if (pw == 0 && lane == 0) {

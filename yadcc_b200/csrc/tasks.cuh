@@ -15,12 +15,13 @@ namespace yd {
 
 // `abort_flag` (may be null): non-zero means the solver gave up on this batch (class
 // table overflow) and the host will rerun it; the final kernels then leave all state alone.
-__global__ void __launch_bounds__(1024) k_final_count(const uint32_t* __restrict__ res, uint32_t n,
+__global__ void __launch_bounds__(1024) k_final_count(const uint32_t* __restrict__ res,
+                                                      const DynParams* __restrict__ dp,
                                                       uint32_t* __restrict__ block_counts,
                                                       const uint32_t* __restrict__ abort_flag) {
   if (abort_flag && *abort_flag) return;
   uint32_t q = blockIdx.x * 1024 + threadIdx.x;
-  int granted = (q < n) && (res[q] < kResTimeout);
+  int granted = (q < dp->n) && (res[q] < kResTimeout);
   int c = __syncthreads_count(granted);
   if (threadIdx.x == 0) block_counts[blockIdx.x] = (uint32_t)c;
 }
@@ -69,13 +70,16 @@ __global__ void __launch_bounds__(1024) k_final_scan(uint32_t* __restrict__ bloc
 
 // Writes yd_grant records and creates the TaskDesc of every grant (cc:126-135).
 __global__ void __launch_bounds__(1024) k_final_write(const uint32_t* __restrict__ res,
-                                                      const yd_task_req* __restrict__ reqs, uint32_t n,
+                                                      const yd_task_req* __restrict__ reqs,
+                                                      const DynParams* __restrict__ dp,
                                                       const uint32_t* __restrict__ block_off,
-                                                      const uint32_t* __restrict__ comp_sv,
-                                                      long long now_ns, TaskRing ring,
+                                                      const uint32_t* __restrict__ comp_sv, TaskRing ring,
                                                       yd_grant* __restrict__ out,
                                                       const uint32_t* __restrict__ abort_flag) {
   if (abort_flag && *abort_flag) return;
+  const uint32_t n = dp->n;
+  const long long now_ns = dp->now_ns;
+  ring.next = dp->ring_next;  // pointers and mask come by value; the window bounds are per call
   __shared__ uint32_t warp_cnt[32];
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t q = blockIdx.x * 1024 + tid;

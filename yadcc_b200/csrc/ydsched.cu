@@ -37,6 +37,9 @@ using yd::kNone;
 
 // ---- small helpers ---------------------------------------------------------
 
+// Bumped whenever any device buffer moves: captured graphs hold raw pointers.
+static unsigned long long g_buf_generation = 0;
+
 struct DevBuf {  // grow-only device allocation
   void* p = nullptr;
   size_t cap = 0;
@@ -54,11 +57,13 @@ struct DevBuf {  // grow-only device allocation
     }
     p = np;
     cap = ncap;
+    ++g_buf_generation;
   }
   void release() {
     if (p) cudaFree(p);
     p = nullptr;
     cap = 0;
+    ++g_buf_generation;
   }
 };
 
@@ -173,6 +178,25 @@ struct yd_sched {
   // operation sequence as the reference, hence the same iteration order.
   std::unordered_map<std::string, std::vector<RunningRec>> running;
   std::vector<RunningRec> running_cache;
+
+  // captured solve graphs, keyed by size class
+  struct GraphKey {
+    uint32_t Nb = 0, S = 0, n_comps = 0, max_comp = 0, cls_bound = 0, solver = 0, wide = 0;
+    size_t slot_b = 0;
+    unsigned long long gen = 0, topo_gen = 0;  // buffer reallocations; topology rebuilds (n_envs, n_ips, ... are baked in)
+    uint64_t ring_cap = 0;
+    bool operator==(const GraphKey& o) const {
+      return Nb == o.Nb && S == o.S && n_comps == o.n_comps && max_comp == o.max_comp && cls_bound == o.cls_bound &&
+             solver == o.solver && wide == o.wide && slot_b == o.slot_b && gen == o.gen && topo_gen == o.topo_gen &&
+             ring_cap == o.ring_cap;
+    }
+  };
+  struct GraphEntry { GraphKey key; cudaGraphExec_t exec = nullptr; uint32_t launches = 0; };
+  std::vector<GraphEntry> graphs;
+  unsigned long long topo_gen = 0;
+  bool use_graphs = true;
+  DevBuf d_dyn;
+  PinBuf h_dyn, h_meta;
 
   cudaEvent_t ev[6] = {};
   yd_solve_stats stats{};
@@ -385,6 +409,7 @@ void yd_sched::SyncTopology() {
   n_envs_dev = E;
   n_ips_dev = NI;
   topo_dirty = false;
+  ++topo_gen;
 }
 
 void yd_sched::EnsureRing(uint64_t need_ids) {
@@ -443,6 +468,7 @@ yd_sched* yd_create(const yd_config* cfg) {
   s->device = cfg->device;
   s->min_mem = min_mem;
   s->solver_pref = cfg->solver;
+  s->use_graphs = !(cfg->reserved & 1u) && !getenv("YDSCHED_NO_GRAPH");
   YD_CUDA_CHECK(cudaStreamCreateWithFlags(&s->st, cudaStreamNonBlocking));
   for (auto& e : s->ev) YD_CUDA_CHECK(cudaEventCreate(&e));
   s->ips.emplace_back();  // id 0 == YD_IP_NONE == the empty requestor string
@@ -451,6 +477,9 @@ yd_sched* yd_create(const yd_config* cfg) {
   YD_CUDA_CHECK(cudaMemsetAsync(s->d_counters.p, 0, sizeof(Counters), s->st));
   s->h_counters.ensure(sizeof(Counters));
   s->h_small.ensure(1 << 16);
+  s->d_dyn.ensure(sizeof(yd::DynParams));
+  s->h_dyn.ensure(sizeof(yd::DynParams));
+  s->h_meta.ensure(64);
   s->EnsureRing(0);
   return s;
 }
@@ -470,7 +499,9 @@ void yd_destroy(yd_sched* s) {
                     &s->d_list_cnt, &s->d_list, &s->d_rcls, &s->d_rrank, &s->d_rank_cnt}) {
     b->release();
   }
-  for (PinBuf* b : {&s->h_facts, &s->h_topo, &s->h_counters, &s->h_small}) b->release();
+  for (auto& g : s->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
+  s->d_dyn.release();
+  for (PinBuf* b : {&s->h_facts, &s->h_topo, &s->h_counters, &s->h_small, &s->h_dyn, &s->h_meta}) b->release();
   for (auto& e : s->ev) cudaEventDestroy(e);
   cudaStreamDestroy(s->st);
   delete s;
@@ -555,12 +586,12 @@ yd::ClassTable MakeClassTable(yd_sched* s) {
 }
 
 // Slot table (both solvers).  Returns the number of kernels launched.
-uint32_t LaunchSlotTable(yd_sched* s, uint32_t N, bool with_owner) {
+uint32_t LaunchSlotTable(yd_sched* s, bool with_owner) {
   const uint32_t S = (uint32_t)s->sv.size();
   cudaStream_t st = s->st;
   yd::ServantArrays arr = s->arrays();
-  yd::k_slot_rows<<<1, 1024, 0, st>>>(S, N, arr, s->d_row_off.as<uint32_t>(), s->d_row_len.as<uint32_t>(),
-                                      s->d_counters.as<Counters>());
+  yd::k_slot_rows<<<1, 1024, 0, st>>>(S, s->d_dyn.as<yd::DynParams>(), arr, s->d_row_off.as<uint32_t>(),
+                                      s->d_row_len.as<uint32_t>(), s->d_counters.as<Counters>());
   uint32_t* owner = with_owner ? s->d_slot_owner.as<uint32_t>() : nullptr;
   if (s->wide) {
     yd::k_slot_fill<true><<<(S + 7) / 8, 256, 0, st>>>(S, arr, s->d_row_off.as<uint32_t>(),
@@ -575,11 +606,11 @@ uint32_t LaunchSlotTable(yd_sched* s, uint32_t N, bool with_owner) {
 }
 
 // Solver 1: one (task x servant) row per decision.
-uint32_t LaunchRowscan(yd_sched* s, uint32_t N) {
+uint32_t LaunchRowscan(yd_sched* s) {
   cudaStream_t st = s->st;
   yd::SolveArgs a{};
   a.reqs = s->d_reqs.as<yd_task_req>();
-  a.n = N;
+  a.dp = s->d_dyn.as<yd::DynParams>();
   a.res = s->d_res.as<uint32_t>();
   a.env_comp = s->d_env_comp.as<uint32_t>();
   a.env_local = s->d_env_local.as<uint32_t>();
@@ -650,6 +681,30 @@ uint32_t LaunchSort(yd_sched* s, size_t bound, int first_bit, int last_bit) {
   return launches;
 }
 
+// Allocates everything LaunchStream touches for size class (Nb, slot_b); called before a
+// graph capture so that no allocation happens inside it.
+void PrepareStreamBuffers(yd_sched* s, uint32_t Nb, size_t slot_b) {
+  const size_t ksz = s->wide ? 8 : 4;
+  for (int b = 0; b < 2; ++b) { s->d_sort_k[b].ensure(slot_b * ksz); s->d_sort_v[b].ensure(slot_b * 4); }
+  const uint32_t nb_sort = (uint32_t)((slot_b + yd::kRsTile - 1) / yd::kRsTile);
+  s->d_hist[0].ensure(size_t(yd::kRsBins) * nb_sort * 4);
+  s->d_hist[1].ensure(size_t(yd::kRsBins) * nb_sort * 4);
+  const size_t cls_u32 = yd::kClsTableSize + 8 + 5 * yd::kMaxClasses + 2 * size_t(s->n_comps) + 8;
+  s->d_cls_keys.ensure(yd::kClsTableSize * 8);
+  s->d_cls_u32.ensure(cls_u32 * 4);
+  s->d_spos.ensure(slot_b * 4); s->d_sr.ensure(slot_b * 4); s->d_scomp.ensure(slot_b * 4);
+  const uint32_t n_tiles = (uint32_t)((slot_b + yd::kListTile - 1) / yd::kListTile);
+  s->d_list_cnt.ensure((size_t(s->cls_bound) * n_tiles + 1) * 4);
+  s->d_list.ensure(slot_b * 8 * 4);
+  const uint32_t n_rtiles = (Nb + yd::kRankTile - 1) / yd::kRankTile;
+  s->d_rcls.ensure(size_t(Nb) * 4); s->d_rrank.ensure(size_t(Nb) * 4);
+  s->d_rank_cnt.ensure((size_t(s->cls_bound) * n_rtiles + 1) * 4);
+  if (!s->stream_attr_set) {
+    YD_CUDA_CHECK(cudaFuncSetAttribute(yd::k_solve_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, 190 * 1024));
+    s->stream_attr_set = true;
+  }
+}
+
 // Solver 2: sorted slot streams.
 uint32_t LaunchStream(yd_sched* s, uint32_t N, size_t slot_bound) {
   cudaStream_t st = s->st;
@@ -672,7 +727,8 @@ uint32_t LaunchStream(yd_sched* s, uint32_t N, size_t slot_bound) {
   yd::TopoView t = MakeTopo(s);
   yd::ClassTable ct = MakeClassTable(s);
   yd::ServantArrays arr = s->arrays();
-  yd::k_cls_insert<<<(N + 255) / 256, 256, 0, st>>>(s->d_reqs.as<yd_task_req>(), N, t, ct);
+  const yd::DynParams* dp = s->d_dyn.as<yd::DynParams>();
+  yd::k_cls_insert<<<(N + 255) / 256, 256, 0, st>>>(s->d_reqs.as<yd_task_req>(), dp, t, ct);
   yd::k_cls_number<<<1, 1024, 0, st>>>(t, ct);
   const uint32_t CB = s->cls_bound;
   yd::k_cls_elig<<<dim3(std::max(1u, std::min(64u, (s->max_comp_servants + 255) / 256)), CB), 256, 0, st>>>(t, ct,
@@ -705,12 +761,12 @@ uint32_t LaunchStream(yd_sched* s, uint32_t N, size_t slot_bound) {
   const uint32_t n_rtiles = (N + yd::kRankTile - 1) / yd::kRankTile;
   const size_t n_rcnt = size_t(CB) * n_rtiles + 1;
   s->d_rcls.ensure(size_t(N) * 4); s->d_rrank.ensure(size_t(N) * 4); s->d_rank_cnt.ensure(n_rcnt * 4);
-  yd::k_rank_count<<<n_rtiles, yd::kRankTile, 0, st>>>(s->d_reqs.as<yd_task_req>(), N, t, ct,
+  yd::k_rank_count<<<n_rtiles, yd::kRankTile, 0, st>>>(s->d_reqs.as<yd_task_req>(), dp, t, ct,
                                                         s->d_comp_mode.as<uint32_t>(), n_rtiles,
                                                         s->d_rcls.as<uint32_t>(), s->d_rrank.as<uint32_t>(),
                                                         s->d_rank_cnt.as<uint32_t>());
   yd::k_scan_u32<<<1, 1024, 0, st>>>(s->d_rank_cnt.as<uint32_t>(), 0, ct.meta, n_rtiles, nullptr);
-  yd::k_rank_assign<<<(N + 255) / 256, 256, 0, st>>>(N, n_rtiles, t, ct, s->d_rcls.as<uint32_t>(),
+  yd::k_rank_assign<<<(N + 255) / 256, 256, 0, st>>>(dp, n_rtiles, t, ct, s->d_rcls.as<uint32_t>(),
                                                      s->d_rrank.as<uint32_t>(), s->d_rank_cnt.as<uint32_t>(),
                                                      s->d_list_cnt.as<uint32_t>(), n_tiles, s->d_list.as<uint2>(),
                                                      arr, s->d_res.as<uint32_t>());
@@ -719,7 +775,7 @@ uint32_t LaunchStream(yd_sched* s, uint32_t N, size_t slot_bound) {
   // ---- 4b. sequential decisions for everything else -------------------------------
   yd::StreamArgs a{};
   a.reqs = s->d_reqs.as<yd_task_req>();
-  a.n = N;
+  a.dp = dp;
   a.res = s->d_res.as<uint32_t>();
   a.t = t;
   a.ct = ct;
@@ -733,13 +789,58 @@ uint32_t LaunchStream(yd_sched* s, uint32_t N, size_t slot_bound) {
   a.counters = s->d_counters.as<Counters>();
   YD_CUDA_CHECK(cudaMemsetAsync(&s->d_counters.as<Counters>()->pad[0], 0, 32, st));
   const size_t dyn = size_t(s->max_comp_servants) * 8;
-  if (!s->stream_attr_set) {
-    YD_CUDA_CHECK(cudaFuncSetAttribute(yd::k_solve_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, 190 * 1024));
-    s->stream_attr_set = true;
-  }
   yd::k_solve_stream<<<s->n_comps, (yd::kStreamProducers + 1) * 32, dyn, st>>>(a);
   launches += 1;
   (void)S;
+  return launches;
+}
+
+}  // namespace
+}  // extern "C++"
+
+extern "C++" {
+namespace {
+
+uint64_t NextPow2(uint64_t v, uint64_t lo) {
+  uint64_t r = lo;
+  while (r < v) r <<= 1;
+  return r;
+}
+
+// Everything between the request upload and the grant download, for size class
+// (Nb, slot_b): the sequence that is captured into a CUDA graph.
+uint32_t EnqueueSolve(yd_sched* s, uint32_t Nb, size_t slot_b, uint32_t solver, bool record_events) {
+  cudaStream_t st = s->st;
+  const uint32_t S = (uint32_t)s->sv.size();
+  const bool have_work = S && s->n_comps;
+  const uint32_t nb = (Nb + 1023) / 1024;
+  uint32_t launches = 0;
+  const yd::DynParams* dp = s->d_dyn.as<yd::DynParams>();
+  YD_CUDA_CHECK(cudaMemcpyAsync(s->d_dyn.p, s->h_dyn.p, sizeof(yd::DynParams), cudaMemcpyHostToDevice, st));
+  YD_CUDA_CHECK(cudaMemsetAsync(s->d_res.p, 0xFF, size_t(Nb) * 4, st));  // == kResEnvNotFound
+  if (record_events) YD_CUDA_CHECK(cudaEventRecord(s->ev[1], st));
+  if (have_work) launches += LaunchSlotTable(s, solver == 2);
+  if (record_events) YD_CUDA_CHECK(cudaEventRecord(s->ev[2], st));
+  const uint32_t* abort_flag = nullptr;
+  if (have_work && solver == 2) {
+    launches += LaunchStream(s, Nb, slot_b);
+    abort_flag = MakeClassTable(s).meta + 1;
+  } else if (have_work) {
+    launches += LaunchRowscan(s);
+  }
+  if (record_events) YD_CUDA_CHECK(cudaEventRecord(s->ev[3], st));
+  yd::k_final_count<<<nb, 1024, 0, st>>>(s->d_res.as<uint32_t>(), dp, s->d_blk.as<uint32_t>(), abort_flag);
+  yd::k_final_scan<<<1, 1024, 0, st>>>(s->d_blk.as<uint32_t>(), nb, s->d_counters.as<Counters>(), abort_flag);
+  yd::k_final_write<<<nb, 1024, 0, st>>>(s->d_res.as<uint32_t>(), s->d_reqs.as<yd_task_req>(), dp,
+                                         s->d_blk.as<uint32_t>(), s->d_comp_sv.as<uint32_t>(), s->ring(),
+                                         s->d_out.as<yd_grant>(), abort_flag);
+  launches += 3;
+  YD_CUDA_CHECK(cudaGetLastError());
+  if (record_events) YD_CUDA_CHECK(cudaEventRecord(s->ev[4], st));
+  YD_CUDA_CHECK(cudaMemcpyAsync(s->h_counters.p, s->d_counters.p, sizeof(Counters), cudaMemcpyDeviceToHost, st));
+  if (abort_flag) {
+    YD_CUDA_CHECK(cudaMemcpyAsync(s->h_meta.p, abort_flag - 1, 8, cudaMemcpyDeviceToHost, st));
+  }
   return launches;
 }
 
@@ -750,7 +851,7 @@ uint32_t LaunchStream(yd_sched* s, uint32_t N, size_t slot_bound) {
 void yd_wait_for_starting_new_tasks(yd_sched* s, int64_t now_ns, const yd_task_req* reqs, size_t n,
                                     yd_grant* out) {
   if (n == 0) return;
-  if (n > 0x7fffffffull) { fprintf(stderr, "ydsched: batch too large\n"); abort(); }
+  if (n > 0x40000000ull) { fprintf(stderr, "ydsched: batch too large\n"); abort(); }
   YD_CUDA_CHECK(cudaSetDevice(s->device));
   cudaStream_t st = s->st;
   const uint32_t N = (uint32_t)n;
@@ -760,19 +861,22 @@ void yd_wait_for_starting_new_tasks(yd_sched* s, int64_t now_ns, const yd_task_r
   s->SyncTopology();
   s->EnsureRing(N);
 
-  const uint32_t nb = (N + 1023) / 1024;
-  s->d_reqs.ensure(size_t(N) * sizeof(yd_task_req));
-  s->d_res.ensure(size_t(N) * 4);
-  s->d_out.ensure(size_t(N) * sizeof(yd_grant));
+  // Size classes: grids, scratch arrays and memsets are dimensioned for the next power of
+  // two; kernels read the exact n from DynParams.
+  const uint32_t Nb = (uint32_t)NextPow2(N, 1024);
+  size_t slot_bound = 0;
+  for (auto&& v : s->sv) slot_bound += size_t(std::min(std::min(v.nproc, v.max_tasks), N)) + 1;
+  if (slot_bound > 0x7ffffff0ull) { fprintf(stderr, "ydsched: slot table too large\n"); abort(); }
+  const size_t slot_b = (size_t)NextPow2(std::max<size_t>(slot_bound, 1), 4096);
+  const uint32_t nb = (Nb + 1023) / 1024;
+  s->d_reqs.ensure(size_t(Nb) * sizeof(yd_task_req));
+  s->d_res.ensure(size_t(Nb) * 4);
+  s->d_out.ensure(size_t(Nb) * sizeof(yd_grant));
   s->d_blk.ensure(size_t(nb) * 4);
   s->d_row_off.ensure(size_t(S + 1) * 4);
   s->d_row_len.ensure(size_t(S + 1) * 4);
-  size_t slot_bound = 0;
-  for (auto&& v : s->sv) slot_bound += size_t(std::min(std::min(v.nproc, v.max_tasks), N)) + 1;
-  slot_bound = std::max<size_t>(slot_bound, 1);
-  if (slot_bound > 0xfffffff0ull) { fprintf(stderr, "ydsched: slot table too large\n"); abort(); }
-  s->d_codes.ensure(slot_bound * (s->wide ? 8 : 4));
-  s->d_slot_owner.ensure(slot_bound * 4);
+  s->d_codes.ensure(slot_b * (s->wide ? 8 : 4));
+  s->d_slot_owner.ensure(slot_b * 4);
 
   // solver choice: 2 (slot streams) unless asked otherwise or a component is too big for it
   uint32_t solver = s->solver_pref == 1 ? 1 : 2;
@@ -783,41 +887,59 @@ void yd_wait_for_starting_new_tasks(yd_sched* s, int64_t now_ns, const yd_task_r
     abort();
   }
 
-  const bool have_work = S && s->n_comps;
+  yd::DynParams* hd = s->h_dyn.as<yd::DynParams>();
+  hd->n = N;
+  hd->now_ns = now_ns;
+  hd->ring_lo = s->lo;
+  hd->ring_next = s->next_id;
+
   uint32_t launches = 0;
   YD_CUDA_CHECK(cudaEventRecord(s->ev[0], st));
   YD_CUDA_CHECK(cudaMemcpyAsync(s->d_reqs.p, reqs, size_t(N) * sizeof(yd_task_req), cudaMemcpyHostToDevice, st));
+  bool graphed = false;
   for (int attempt = 0;; ++attempt) {
-    YD_CUDA_CHECK(cudaMemsetAsync(s->d_res.p, 0xFF, size_t(N) * 4, st));  // == kResEnvNotFound
-    YD_CUDA_CHECK(cudaEventRecord(s->ev[1], st));
-    if (have_work) launches += LaunchSlotTable(s, N, solver == 2);
-    YD_CUDA_CHECK(cudaEventRecord(s->ev[2], st));
-    const uint32_t* abort_flag = nullptr;
-    if (have_work && solver == 2) {
-      launches += LaunchStream(s, N, slot_bound);
-      abort_flag = MakeClassTable(s).meta + 1;
-    } else if (have_work) {
-      launches += LaunchRowscan(s, N);
+    s->h_meta.as<uint32_t>()[0] = s->h_meta.as<uint32_t>()[1] = 0;
+    graphed = false;
+    if (s->use_graphs) {
+      // make sure every buffer the sequence touches exists BEFORE capturing (no allocation
+      // inside a capture), then look the size class up
+      if (solver == 2) PrepareStreamBuffers(s, Nb, slot_b);
+      yd_sched::GraphKey key;
+      key.Nb = Nb; key.S = S; key.n_comps = s->n_comps; key.max_comp = s->max_comp_servants;
+      key.cls_bound = s->cls_bound; key.solver = solver; key.wide = s->wide; key.slot_b = slot_b;
+      key.gen = g_buf_generation; key.topo_gen = s->topo_gen; key.ring_cap = s->ring_cap;
+      yd_sched::GraphEntry* hit = nullptr;
+      for (auto& g : s->graphs) if (g.key == key) { hit = &g; break; }
+      if (!hit) {
+        cudaGraph_t graph = nullptr;
+        YD_CUDA_CHECK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+        uint32_t l = EnqueueSolve(s, Nb, slot_b, solver, false);
+        YD_CUDA_CHECK(cudaStreamEndCapture(st, &graph));
+        cudaGraphExec_t exec = nullptr;
+        YD_CUDA_CHECK(cudaGraphInstantiate(&exec, graph, 0));
+        YD_CUDA_CHECK(cudaGraphDestroy(graph));
+        if (s->graphs.size() >= 16) {  // drop the oldest size class
+          cudaGraphExecDestroy(s->graphs.front().exec);
+          s->graphs.erase(s->graphs.begin());
+        }
+        s->graphs.push_back({key, exec, l});
+        hit = &s->graphs.back();
+      }
+      YD_CUDA_CHECK(cudaEventRecord(s->ev[1], st));
+      YD_CUDA_CHECK(cudaGraphLaunch(hit->exec, st));
+      YD_CUDA_CHECK(cudaEventRecord(s->ev[4], st));
+      launches += hit->launches;
+      graphed = true;
+    } else {
+      if (solver == 2) PrepareStreamBuffers(s, Nb, slot_b);
+      launches += EnqueueSolve(s, Nb, slot_b, solver, true);
     }
-    YD_CUDA_CHECK(cudaEventRecord(s->ev[3], st));
-    yd::k_final_count<<<nb, 1024, 0, st>>>(s->d_res.as<uint32_t>(), N, s->d_blk.as<uint32_t>(), abort_flag);
-    yd::k_final_scan<<<1, 1024, 0, st>>>(s->d_blk.as<uint32_t>(), nb, s->d_counters.as<Counters>(), abort_flag);
-    yd::k_final_write<<<nb, 1024, 0, st>>>(s->d_res.as<uint32_t>(), s->d_reqs.as<yd_task_req>(), N,
-                                           s->d_blk.as<uint32_t>(), s->d_comp_sv.as<uint32_t>(), (long long)now_ns,
-                                           s->ring(), s->d_out.as<yd_grant>(), abort_flag);
-    launches += 3;
-    YD_CUDA_CHECK(cudaGetLastError());
-    YD_CUDA_CHECK(cudaEventRecord(s->ev[4], st));
     YD_CUDA_CHECK(cudaMemcpyAsync(out, s->d_out.p, size_t(N) * sizeof(yd_grant), cudaMemcpyDeviceToHost, st));
-    YD_CUDA_CHECK(cudaMemcpyAsync(s->h_counters.p, s->d_counters.p, sizeof(Counters), cudaMemcpyDeviceToHost, st));
-    if (abort_flag) {
-      YD_CUDA_CHECK(cudaMemcpyAsync(s->h_small.p, abort_flag - 1, 8, cudaMemcpyDeviceToHost, st));
-    }
     YD_CUDA_CHECK(cudaEventRecord(s->ev[5], st));
     YD_CUDA_CHECK(cudaStreamSynchronize(st));
-    if (abort_flag && s->h_small.as<uint32_t>()[1] != 0) {
+    if (solver == 2 && S && s->n_comps && s->h_meta.as<uint32_t>()[1] != 0) {
       // Nothing was decided (the stream solver and the final kernels all stood down).
-      const uint32_t flag = s->h_small.as<uint32_t>()[1], ncls = s->h_small.as<uint32_t>()[0];
+      const uint32_t flag = s->h_meta.as<uint32_t>()[1], ncls = s->h_meta.as<uint32_t>()[0];
       if (flag == 2 && attempt < 3) {  // more classes than provisioned: grow and go again
         while (s->cls_bound < ncls && s->cls_bound < yd::kMaxClasses) s->cls_bound *= 2;
       } else {
@@ -838,19 +960,24 @@ void yd_wait_for_starting_new_tasks(yd_sched* s, int64_t now_ns, const yd_task_r
   yd_solve_stats& stt = s->stats;
   stt = yd_solve_stats{};
   cudaEventElapsedTime(&ms, s->ev[0], s->ev[5]); stt.total_ms = ms;
-  cudaEventElapsedTime(&ms, s->ev[1], s->ev[2]); stt.prep_ms = ms;
-  cudaEventElapsedTime(&ms, s->ev[2], s->ev[3]); stt.solve_ms = ms;
-  cudaEventElapsedTime(&ms, s->ev[3], s->ev[4]); stt.final_ms = ms;
+  if (graphed) {
+    // inside a graph the phases are not separable: solve_ms is the whole device pipeline
+    cudaEventElapsedTime(&ms, s->ev[1], s->ev[4]); stt.solve_ms = ms;
+  } else {
+    cudaEventElapsedTime(&ms, s->ev[1], s->ev[2]); stt.prep_ms = ms;
+    cudaEventElapsedTime(&ms, s->ev[2], s->ev[3]); stt.solve_ms = ms;
+    cudaEventElapsedTime(&ms, s->ev[3], s->ev[4]); stt.final_ms = ms;
+  }
   stt.decisions = N;
   stt.granted = c->granted;
   stt.kernel_launches = launches;
   stt.solver = solver;
-  stt.h2d_bytes = size_t(N) * sizeof(yd_task_req);
-  stt.d2h_bytes = size_t(N) * sizeof(yd_grant) + sizeof(Counters);
+  stt.h2d_bytes = size_t(N) * sizeof(yd_task_req) + sizeof(yd::DynParams);
+  stt.d2h_bytes = size_t(N) * sizeof(yd_grant) + sizeof(Counters) + 8;
   s->have_stats = true;
   if (getenv("YDSCHED_DEBUG")) {
-    fprintf(stderr, "ydsched: solver %u spec_steps %llu spec_lanes %llu walks %llu windows %llu solve_ms %.3f\n", solver,
-            c->pad[0], c->pad[1], c->pad[2], c->pad[3], stt.solve_ms);
+    fprintf(stderr, "ydsched: solver %u graph %d spec_steps %llu spec_lanes %llu walks %llu windows %llu solve_ms %.3f\n",
+            solver, (int)graphed, c->pad[0], c->pad[1], c->pad[2], c->pad[3], stt.solve_ms);
   }
 }
 

@@ -85,6 +85,7 @@ class TaskDispatcher:
         device: int = 0,
         servant_min_memory_for_accepting_new_task: str | None = None,
         solver: int = 0,
+        graphs: bool = True,
     ):
         self._lib = library if isinstance(library, C.CDLL) else _abi.load_library(library)
         cfg = _abi.yd_config(
@@ -96,6 +97,7 @@ class TaskDispatcher:
                 else None
             ),
             solver=solver,
+            reserved=0 if graphs else 1,  # bit 0: do not capture the solve into a CUDA graph (per-phase timing)
         )
         self._h = self._lib.yd_create(C.byref(cfg))
         if not self._h:

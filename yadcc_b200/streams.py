@@ -188,8 +188,10 @@ def first_mismatch(a: Sequence[np.ndarray], b: Sequence[np.ndarray]) -> str:
     for k, (x, y) in enumerate(zip(a, b)):
         if x.shape != y.shape or x.dtype != y.dtype:
             return f"event-output {k}: shape/dtype {x.shape}/{x.dtype} vs {y.shape}/{y.dtype}"
+        if not x.size:
+            continue
         neq = np.nonzero(np.asarray(x != y).reshape(len(x), -1).any(axis=1))[0] if x.ndim else np.array([0])
-        if x.size and (x != y).any():
+        if (x != y).any():
             i = int(neq[0])
             return f"event-output {k}, row {i}: {x[i]!r} vs {y[i]!r} ({len(neq)} rows differ)"
     if len(a) != len(b):
