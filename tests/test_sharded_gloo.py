@@ -1,0 +1,120 @@
+"""N > 1 path on CPU: two gloo ranks, each running the CPU oracle behind the same C ABI,
+must reproduce a single scheduler's answers (statuses, GLOBAL task ids, servant
+locations) for the whole queue.  This exercises ShardedDispatcher's ownership routing
+and its one collective (all-reduce of grant flags -> global FIFO task ids)."""
+import os
+import socket
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+PORT_LIB = ROOT / "oracle" / "libydoracle.so"
+
+
+def _free_port() -> int:
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _workload(seed=5, n_servants=120, n_tasks=4000, n_digests=6):
+    from yadcc_b200 import Servant, PRIORITY_DEDICATED, PRIORITY_USER
+
+    rng = np.random.default_rng(seed)
+    digests = [f"{i:064x}" for i in range(n_digests)]
+    servants = []
+    for i in range(n_servants):
+        d = digests[i % n_digests]
+        # digests 2k and 2k+1 sometimes share a servant: they must live on the same rank
+        envs = [d] + ([digests[(i % n_digests) ^ 1]] if rng.random() < 0.3 else [])
+        servants.append(Servant(f"10.7.{i >> 8}.{i & 255}:8335", None, envs, int(rng.choice([7, 8])), 16,
+                                int(rng.integers(0, 8)), 0, 64 << 30, int(rng.integers(0, 10)),
+                                PRIORITY_DEDICATED if i % 9 == 0 else PRIORITY_USER))
+    req_digest = rng.integers(0, n_digests + 1, n_tasks)  # n_digests == "nobody has it"
+    req_ip = rng.integers(0, n_servants + 40, n_tasks)
+    req_mv = rng.choice([7, 8], n_tasks)
+    return digests, servants, req_digest, req_ip, req_mv
+
+
+def _ip(j, n_servants):
+    return f"10.7.{j >> 8}.{j & 255}" if j < n_servants else f"172.16.1.{j - n_servants}"
+
+
+def _owner(digest: str, world: int) -> int:
+    return (int(digest, 16) // 2) % world  # pairs (2k, 2k+1) stay together
+
+
+def _rank_main(rank, world, port, out_dir):
+    import torch
+    import torch.distributed as dist
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from yadcc_b200 import TaskDispatcher
+    from yadcc_b200.sharded import ShardedDispatcher
+
+    digests, servants, req_digest, req_ip, req_mv = _workload()
+    d = TaskDispatcher(str(PORT_LIB))
+    sd = ShardedDispatcher(d, rank, world, device=torch.device("cpu"), digest_owner=_owner)
+    for sv in servants:
+        sd.keep_servant_alive(sv, 10.0, now=0.0)
+    owners = np.asarray([_owner(digests[k], world) if k < len(digests) else -1 for k in req_digest])
+    mine = np.nonzero(owners == rank)[0]
+    all_d = digests + ["ff" * 32]
+    results = []
+    for rnd in range(2):  # two solves: the second one continues the global id space
+        reqs = d.make_requests(len(mine), [all_d[req_digest[i]] for i in mine],
+                               [_ip(int(req_ip[i]), len(servants)) for i in mine], req_mv[mine].astype(np.uint32))
+        g = sd.wait_for_starting_new_tasks(None, owners, reqs, now=0.5 + rnd)
+        loc = np.asarray([d.servant_location(int(x)) or "" for x in g["servant_index"]])
+        results.append((mine, g["status"].copy(), g["task_id"].copy(), loc))
+        # free every third grant through the GLOBAL ids, then renew the rest
+        ok = g["status"] == 2
+        sd.free_tasks(g["task_id"][ok][::3])
+    np.save(Path(out_dir) / f"rank{rank}.npy", np.asarray(results, dtype=object), allow_pickle=True)
+    assert sd.collective_bytes > 0
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_ranks_equal_one_scheduler(tmp_path, port_lib):
+    import torch.multiprocessing as mp
+    from yadcc_b200 import TaskDispatcher
+
+    world = 2
+    mp.spawn(_rank_main, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+
+    digests, servants, req_digest, req_ip, req_mv = _workload()
+    one = TaskDispatcher(port_lib)
+    for sv in servants:
+        one.keep_servant_alive(sv, 10.0, now=0.0)
+    all_d = digests + ["ff" * 32]
+    ranks = [np.load(tmp_path / f"rank{r}.npy", allow_pickle=True) for r in range(world)]
+    for rnd in range(2):
+        reqs = one.make_requests(len(req_digest), [all_d[k] for k in req_digest],
+                                 [_ip(int(j), len(servants)) for j in req_ip], req_mv.astype(np.uint32))
+        g = one.wait_for_starting_new_tasks(reqs, 0.5 + rnd)
+        loc = np.asarray([one.servant_location(int(x)) or "" for x in g["servant_index"]])
+        seen = np.zeros(len(g), dtype=bool)
+        for r in range(world):
+            mine, status, task_id, rloc = ranks[r][rnd]
+            mine = np.asarray(mine, dtype=np.int64)
+            status, task_id = np.asarray(status, dtype=np.uint32), np.asarray(task_id, dtype=np.uint64)
+            rloc = np.asarray(rloc, dtype=str)
+            seen[mine] = True
+            assert (status == g["status"][mine]).all()
+            ok = status == 2
+            assert (task_id[ok] == g["task_id"][mine][ok]).all(), "global task ids"
+            assert (rloc[ok] == loc[mine][ok]).all()
+        # requests nobody owns are exactly the unknown-digest ones: EnvironmentNotFound
+        assert (g["status"][~seen] == 0).all()
+        # mirror the per-rank "free every third of MY grants"
+        for r in range(world):
+            mine, status, task_id, _ = ranks[r][rnd]
+            status, task_id = np.asarray(status, dtype=np.uint32), np.asarray(task_id, dtype=np.uint64)
+            one.free_tasks(task_id[status == 2][::3])

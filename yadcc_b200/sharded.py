@@ -1,0 +1,121 @@
+"""One logical scheduler over several GPUs (option 1).
+
+Decisions couple only through per-servant `running_tasks`, so servants that share no
+compiler digest never interact: the connected components of the digest<->servant graph
+are independent FIFO sub-queues (the sharding the reference's authors propose at
+yadcc/scheduler/task_dispatcher.h:286-288).  `ShardedDispatcher` gives every rank a
+subset of the components -- their servants, their digests and the requests for them --
+and one process per GPU runs an ordinary `TaskDispatcher` on its share.  No servant
+state ever crosses ranks.
+
+What does cross ranks is the task-id space: the reference numbers grants in global FIFO
+order (`next_task_id++`, task_dispatcher.cc:127), so rank r must know how many requests
+EARLIER in the global queue were granted by other ranks.  That is the one real exchange
+step of the path: an all-reduce (sum) of the per-request grant flags, followed by a
+local prefix sum.  Everything else (heartbeats, frees, keep-alives, ticks) is routed to
+the owning rank by the caller-visible `owner_of_*` maps.
+
+The class is backend-agnostic (any library speaking the ydsched C ABI) and
+transport-agnostic (any torch.distributed backend), so the N>1 logic is tested on CPU
+with gloo + the oracle and runs unchanged with NCCL on B200s.
+"""
+from __future__ import annotations
+
+import zlib
+from typing import Callable, Sequence
+
+import numpy as np
+
+from ._abi import GRANT_DTYPE, REQ_DTYPE, STATUS_ENVIRONMENT_NOT_FOUND, STATUS_GRANTED
+from .dispatcher import Servant, TaskDispatcher
+
+
+def default_digest_owner(digest: str, world: int) -> int:
+    """Stable digest -> rank map.  Digests that co-occur on one servant must map to the
+    same rank (they are one component); `keep_servant_alive` checks this."""
+    return zlib.crc32(digest.encode()) % world
+
+
+class ShardedDispatcher:
+    def __init__(self, local: TaskDispatcher, rank: int, world: int, *, group=None, device=None,
+                 digest_owner: Callable[[str, int], int] = default_digest_owner):
+        self.local = local
+        self.rank = rank
+        self.world = world
+        self.group = group
+        self.device = device  # torch device for the collective (cuda:LOCAL_RANK with NCCL, cpu with gloo)
+        self.digest_owner = digest_owner
+        self.next_task_id = 0  # global id space
+        # global task id -> local task id, for the grants this rank owns
+        self._g2l: dict[int, int] = {}
+        self.collective_bytes = 0
+
+    # -- ownership -----------------------------------------------------------
+    def owner_of_digest(self, digest: str) -> int:
+        return self.digest_owner(digest, self.world)
+
+    def owner_of_servant(self, servant: Servant) -> int:
+        owners = {self.owner_of_digest(d) for d in servant.environments}
+        if len(owners) > 1:
+            raise ValueError(
+                f"servant {servant.observed_location} holds digests owned by ranks {sorted(owners)}: "
+                "the digest_owner map must keep a component on one rank"
+            )
+        return owners.pop() if owners else 0
+
+    # -- servant maintenance ---------------------------------------------------
+    def keep_servant_alive(self, servant: Servant, expires_in: float, *, now: float = 0.0) -> None:
+        if self.owner_of_servant(servant) == self.rank:
+            self.local.keep_servant_alive(servant, expires_in, now=now)
+
+    def on_expiration_timer(self, *, now: float) -> None:
+        self.local.on_expiration_timer(now=now)
+
+    # -- the hot path ------------------------------------------------------------
+    def wait_for_starting_new_tasks(self, digests: Sequence[str], owners: np.ndarray, local_reqs: np.ndarray,
+                                    now: float = 0.0) -> np.ndarray:
+        """`owners[i]` = owning rank of global request i (or -1 if nobody holds its digest);
+        `local_reqs` = REQ array of this rank's requests, in global order.  Returns a
+        GRANT array for this rank's requests with GLOBAL task ids."""
+        import torch
+        import torch.distributed as dist
+
+        del digests
+        mine = np.nonzero(owners == self.rank)[0]
+        assert len(mine) == len(local_reqs)
+        g = self.local.wait_for_starting_new_tasks(local_reqs, now).copy() if len(mine) else np.zeros(0, GRANT_DTYPE)
+        ok = g["status"] == STATUS_GRANTED
+        # the one exchange step: who was granted, over the whole global queue
+        flags = torch.zeros(len(owners), dtype=torch.int32, device=self.device)
+        if len(mine):
+            flags[torch.as_tensor(mine, device=self.device)] = torch.as_tensor(ok.astype(np.int32), device=self.device)
+        if self.world > 1:
+            dist.all_reduce(flags, op=dist.ReduceOp.SUM, group=self.group)
+            self.collective_bytes += flags.numel() * 4
+        before = torch.cumsum(flags, 0) - flags  # grants strictly earlier in the global FIFO
+        total = int(flags.sum().item())
+        if len(mine):
+            gids = self.next_task_id + before[torch.as_tensor(mine, device=self.device)].cpu().numpy().astype(np.uint64)
+            for gid, lid in zip(gids[ok].tolist(), g["task_id"][ok].tolist()):
+                self._g2l[gid] = lid
+            g["task_id"][ok] = gids[ok]
+        self.next_task_id += total
+        return g
+
+    # -- lease maintenance, routed by global id -------------------------------------
+    def free_tasks(self, global_ids) -> None:
+        local = [self._g2l.pop(int(i)) for i in global_ids if int(i) in self._g2l]
+        if local:
+            self.local.free_tasks(np.asarray(local, dtype=np.uint64))
+
+    def keep_tasks_alive(self, global_ids, new_expires_in: float, *, now: float = 0.0) -> np.ndarray:
+        """Statuses for the ids this rank owns (False for ids owned elsewhere; the caller
+        ORs the ranks' answers)."""
+        ids = [int(i) for i in global_ids]
+        out = np.zeros(len(ids), dtype=bool)
+        idx = [k for k, i in enumerate(ids) if i in self._g2l]
+        if idx:
+            st = self.local.keep_tasks_alive(np.asarray([self._g2l[ids[k]] for k in idx], dtype=np.uint64),
+                                             new_expires_in, now=now)
+            out[idx] = st
+        return out
