@@ -80,6 +80,9 @@ __device__ __forceinline__ bool servant_has_env(const TopoView& t, uint32_t pos,
 
 __global__ void __launch_bounds__(256) k_cls_insert(const yd_task_req* __restrict__ reqs,
                                                     const DynParams* __restrict__ dp, TopoView t, ClassTable ct) {
+  __shared__ unsigned long long s_seen[64];
+  if (threadIdx.x < 64) s_seen[threadIdx.x] = kClsEmpty;
+  __syncthreads();
   uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= dp->n) return;
   const uint2 w0 = __ldg(reinterpret_cast<const uint2*>(reqs + q));
@@ -88,10 +91,20 @@ __global__ void __launch_bounds__(256) k_cls_insert(const yd_task_req* __restric
   const uint32_t comp = t.env_comp[env];
   if (comp == kNone) return;
   const unsigned long long key = ((unsigned long long)env << 32) | mv;
-  // one lane per distinct key of the warp does the probing (the batch has few classes)
-  const uint32_t active = __activemask();
-  const uint32_t peers = __match_any_sync(active, key);
-  if ((uint32_t)(__ffs(peers) - 1) == (threadIdx.x & 31)) {
+  // A batch has few classes and 100 k requests: dedupe inside the block first (a 64-slot
+  // shared-memory set), so the HBM table sees ~one insert per (block, class).
+  bool first_in_block = true;
+  {
+    uint32_t h = cls_hash(key) & 63u;
+    for (int probe = 0; probe < 64; ++probe) {
+      unsigned long long k = s_seen[h];
+      if (k == kClsEmpty) k = atomicCAS(&s_seen[h], kClsEmpty, key);
+      if (k == key) { first_in_block = false; break; }   // somebody in this block has it
+      if (k == kClsEmpty) break;                         // I claimed the slot: I insert globally
+      h = (h + 1) & 63u;
+    }
+  }
+  if (first_in_block) {
     uint32_t s = cls_hash(key);
     bool done = false;
     for (uint32_t probe = 0; probe < kClsTableSize && !done; ++probe) {
@@ -114,10 +127,14 @@ __global__ void __launch_bounds__(256) k_cls_insert(const yd_task_req* __restric
   }
 }
 
-// One block: deterministic class ids = rank of the occupied slot.
-__global__ void __launch_bounds__(1024) k_cls_number(TopoView t, ClassTable ct) {
+// One block: deterministic class ids (= rank of the occupied table slot), per-class
+// eligible-servant counts, and the solver mode of every component:
+//   comp_mode 1 = data-parallel path (one class, no request from one of its own servants),
+//             0 = sequential slot-stream solver.
+__global__ void __launch_bounds__(1024) k_cls_finalize(TopoView t, ClassTable ct, ServantArrays sv, uint32_t n_comps,
+                                                       uint32_t* __restrict__ comp_mode) {
   __shared__ uint32_t warp_sums[32];
-  __shared__ uint32_t carry_s;
+  __shared__ uint32_t carry_s, s_sum;
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) carry_s = 0;
   __syncthreads();
@@ -152,8 +169,6 @@ __global__ void __launch_bounds__(1024) k_cls_number(TopoView t, ClassTable ct) 
         ct.cls_env[id] = env;
         ct.cls_mv[id] = (uint32_t)k;
         ct.cls_comp[id] = comp;
-        ct.cls_nelig[id] = 0;
-        ct.cls_count[id] = 0;
         atomicAdd(&ct.comp_ncls[comp], 1u);
       } else {
         ct.slot_cls[s] = kNone;
@@ -165,105 +180,99 @@ __global__ void __launch_bounds__(1024) k_cls_number(TopoView t, ClassTable ct) 
     if (tid == 1023) carry_s += warp_sums[31];
     __syncthreads();
   }
+  const uint32_t ncls = carry_s < kMaxClasses ? carry_s : kMaxClasses;
   if (tid == 0) {
-    ct.meta[0] = carry_s < kMaxClasses ? carry_s : kMaxClasses;
+    ct.meta[0] = ncls;
     if (carry_s > kMaxClasses) ct.meta[1] = 1;
   }
-}
-
-// grid.y = class; threads stride over the servants of the class's component.
-__global__ void __launch_bounds__(256) k_cls_elig(TopoView t, ClassTable ct, ServantArrays sv) {
-  const uint32_t c = blockIdx.y;
-  if (c >= ct.meta[0]) return;
-  const uint32_t comp = ct.cls_comp[c], env = ct.cls_env[c], mv = ct.cls_mv[c];
-  const uint32_t b = t.comp_sv_off[comp], e = t.comp_sv_off[comp + 1];
-  int mine = 0;
-  for (uint32_t i = b + blockIdx.x * blockDim.x + threadIdx.x; i < e; i += gridDim.x * blockDim.x) {
-    const uint32_t pos = t.comp_sv[i];
-    mine += (sv.max_tasks[pos] != 0 && (uint32_t)sv.version[pos] >= mv && servant_has_env(t, pos, env)) ? 1 : 0;
+  __threadfence_block();
+  __syncthreads();
+  // eligible servants per class: max_tasks != 0, digest held, version >= min_version (cc:316-344)
+  for (uint32_t c = 0; c < ncls; ++c) {
+    if (tid == 0) s_sum = 0;
+    __syncthreads();
+    const uint32_t comp = ct.cls_comp[c], env = ct.cls_env[c], mv = ct.cls_mv[c];
+    uint32_t mine = 0;
+    for (uint32_t i = t.comp_sv_off[comp] + tid, e = t.comp_sv_off[comp + 1]; i < e; i += 1024) {
+      const uint32_t pos = t.comp_sv[i];
+      mine += (sv.max_tasks[pos] != 0 && (uint32_t)sv.version[pos] >= mv && servant_has_env(t, pos, env)) ? 1u : 0u;
+    }
+    if (mine) atomicAdd(&s_sum, mine);
+    __syncthreads();
+    if (tid == 0) ct.cls_nelig[c] = s_sum;
+    __syncthreads();
   }
-  __shared__ uint32_t s_sum;
-  if (threadIdx.x == 0) s_sum = 0;
-  __syncthreads();
-  if (mine) atomicAdd(&s_sum, (uint32_t)mine);
-  __syncthreads();
-  if (threadIdx.x == 0 && s_sum) atomicAdd(&ct.cls_nelig[c], s_sum);
+  const bool healthy = ct.meta[1] == 0;
+  for (uint32_t c = tid; c < n_comps; c += 1024) {
+    comp_mode[c] = (healthy && ct.comp_ncls[c] == 1 && !(ct.comp_flags[c] & 1u)) ? 1u : 0u;
+  }
 }
 
-// sorted slot i -> owner position, running_tasks value of the slot, component.
-__global__ void __launch_bounds__(256) k_slot_decode(const uint32_t* __restrict__ sorted_orig,
-                                                     const unsigned long long* __restrict__ m_ptr,
-                                                     const uint32_t* __restrict__ slot_owner,
-                                                     const uint32_t* __restrict__ row_off,
-                                                     const uint32_t* __restrict__ row_len,
-                                                     const uint32_t* __restrict__ run,
-                                                     const uint32_t* __restrict__ sv_comp,
-                                                     uint32_t* __restrict__ s_pos, uint32_t* __restrict__ s_r,
-                                                     uint32_t* __restrict__ s_comp) {
-  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (uint32_t)*m_ptr) return;
-  const uint32_t orig = sorted_orig[i];
-  const uint32_t pos = slot_owner[orig];
-  const uint32_t k = orig - row_off[pos];
-  s_pos[i] = pos;
-  s_r[i] = run[pos] + k;
-  s_comp[i] = (k < row_len[pos]) ? sv_comp[pos] : kNone;  // the row's sentinel is nobody's slot
-}
-
+// Per-class sorted slot lists.  A block owns a tile of 1024 SORTED slots, decodes each
+// slot once (owner position, running_tasks value, component) and loops over the classes:
+// class c's list keeps the slots whose servant is eligible for c, in sorted order.
 constexpr int kListTile = 1024;
 
-__device__ __forceinline__ bool slot_in_class(const TopoView& t, const ClassTable& ct, const ServantArrays& sv,
-                                              uint32_t c_comp, uint32_t c_env, uint32_t c_mv, uint32_t pos,
-                                              uint32_t comp) {
-  return comp == c_comp && (uint32_t)sv.version[pos] >= c_mv && servant_has_env(t, pos, c_env);
+struct SlotDecode {
+  const uint32_t* sorted_orig;  // sorted order -> original slot index (radix payload)
+  const uint32_t* slot_owner;   // original slot index -> registry position
+  const uint32_t* row_off;
+  const uint32_t* row_len;
+  const uint32_t* run;
+};
+
+__device__ __forceinline__ bool decode_slot(const SlotDecode& d, const TopoView& t, uint32_t i, uint32_t m,
+                                            uint32_t& pos, uint32_t& r, uint32_t& comp) {
+  pos = 0; r = 0; comp = kNone;
+  if (i >= m) return false;
+  const uint32_t orig = d.sorted_orig[i];
+  pos = d.slot_owner[orig];
+  const uint32_t k = orig - d.row_off[pos];
+  if (k >= d.row_len[pos]) return false;  // the row's sentinel is nobody's slot
+  r = d.run[pos] + k;
+  comp = t.sv_comp[pos];
+  return comp != kNone;
 }
 
-// grid = (tiles, classes): per (class, tile) number of member slots.
-__global__ void __launch_bounds__(kListTile) k_list_count(const unsigned long long* __restrict__ m_ptr,
-                                                          const uint32_t* __restrict__ s_pos,
-                                                          const uint32_t* __restrict__ s_comp, TopoView t,
-                                                          ClassTable ct, ServantArrays sv, uint32_t n_tiles,
-                                                          uint32_t* __restrict__ counts) {
-  const uint32_t c = blockIdx.y;
-  if (c >= ct.meta[0]) return;
-  const uint32_t m = (uint32_t)*m_ptr;
-  const uint32_t i = blockIdx.x * kListTile + threadIdx.x;
-  bool in = false;
-  if (i < m) in = slot_in_class(t, ct, sv, ct.cls_comp[c], ct.cls_env[c], ct.cls_mv[c], s_pos[i], s_comp[i]);
-  const int cnt = __syncthreads_count(in);
-  if (threadIdx.x == 0) counts[c * n_tiles + blockIdx.x] = (uint32_t)cnt;
+__global__ void __launch_bounds__(kListTile) k_list_count(const unsigned long long* __restrict__ m_ptr, SlotDecode d,
+                                                          TopoView t, ClassTable ct, ServantArrays sv,
+                                                          uint32_t n_tiles, uint32_t* __restrict__ counts) {
+  const uint32_t ncls = min(ct.meta[0], ct.cls_bound);
+  uint32_t pos, r, comp;
+  const bool live = decode_slot(d, t, blockIdx.x * kListTile + threadIdx.x, (uint32_t)*m_ptr, pos, r, comp);
+  const uint32_t ver = live ? (uint32_t)sv.version[pos] : 0u;
+  for (uint32_t c = 0; c < ncls; ++c) {
+    const bool in = live && comp == ct.cls_comp[c] && ver >= ct.cls_mv[c] && servant_has_env(t, pos, ct.cls_env[c]);
+    const int cnt = __syncthreads_count(in);
+    if (threadIdx.x == 0) counts[c * n_tiles + blockIdx.x] = (uint32_t)cnt;
+  }
 }
 
-// counts[] has been exclusive-scanned over (class-major, tile-minor); counts[C*n_tiles] = total.
-__global__ void __launch_bounds__(kListTile) k_list_fill(const unsigned long long* __restrict__ m_ptr,
-                                                         const uint32_t* __restrict__ s_pos,
-                                                         const uint32_t* __restrict__ s_r,
-                                                         const uint32_t* __restrict__ s_comp, TopoView t,
-                                                         ClassTable ct, ServantArrays sv, uint32_t n_tiles,
+// counts[] has been exclusive-scanned over (class-major, tile-minor).
+__global__ void __launch_bounds__(kListTile) k_list_fill(const unsigned long long* __restrict__ m_ptr, SlotDecode d,
+                                                         TopoView t, ClassTable ct, ServantArrays sv, uint32_t n_tiles,
                                                          const uint32_t* __restrict__ offs,
                                                          uint2* __restrict__ list, uint32_t list_cap) {
   __shared__ uint32_t warp_cnt[32];
-  const uint32_t c = blockIdx.y;
-  if (c >= ct.meta[0]) return;
+  const uint32_t ncls = min(ct.meta[0], ct.cls_bound);
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const uint32_t m = (uint32_t)*m_ptr;
-  const uint32_t i = blockIdx.x * kListTile + tid;
-  bool in = false;
-  uint32_t pos = 0;
-  if (i < m) {
-    pos = s_pos[i];
-    in = slot_in_class(t, ct, sv, ct.cls_comp[c], ct.cls_env[c], ct.cls_mv[c], pos, s_comp[i]);
-  }
-  const uint32_t bal = __ballot_sync(0xffffffffu, in);
-  if (lane == 0) warp_cnt[warp] = __popc(bal);
-  __syncthreads();
-  uint32_t before = 0;
-  for (uint32_t w = 0; w < warp; ++w) before += warp_cnt[w];
-  before += __popc(bal & ((1u << lane) - 1));
-  if (in) {
-    const uint32_t dst = offs[c * n_tiles + blockIdx.x] + before;
-    if (dst < list_cap) list[dst] = make_uint2(t.sv_local[pos], s_r[i]);
-    else ct.meta[1] = 1;  // more (class, slot) pairs than provisioned: the host reruns with solver 1
+  uint32_t pos, r, comp;
+  const bool live = decode_slot(d, t, blockIdx.x * kListTile + tid, (uint32_t)*m_ptr, pos, r, comp);
+  const uint32_t ver = live ? (uint32_t)sv.version[pos] : 0u;
+  const uint32_t local = live ? t.sv_local[pos] : 0u;
+  for (uint32_t c = 0; c < ncls; ++c) {
+    const bool in = live && comp == ct.cls_comp[c] && ver >= ct.cls_mv[c] && servant_has_env(t, pos, ct.cls_env[c]);
+    const uint32_t bal = __ballot_sync(0xffffffffu, in);
+    __syncthreads();  // warp_cnt of the previous class has been consumed
+    if (lane == 0) warp_cnt[warp] = __popc(bal);
+    __syncthreads();
+    if (in) {
+      uint32_t before = __popc(bal & ((1u << lane) - 1));
+      for (uint32_t w = 0; w < warp; ++w) before += warp_cnt[w];
+      const uint32_t dst = offs[c * n_tiles + blockIdx.x] + before;
+      if (dst < list_cap) list[dst] = make_uint2(local, r);
+      else ct.meta[1] = 1;  // more (class, slot) pairs than provisioned: the host reruns with solver 1
+    }
   }
 }
 

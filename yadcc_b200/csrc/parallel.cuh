@@ -8,8 +8,8 @@
 // beyond the list's end time out.  That is a per-class exclusive prefix count
 // (the FIFO rank) followed by one gather -- no dependency between decisions.
 //
-//   k_comp_mode    marks such components (comp_mode = 1); the sequential solver
-//                  (solve_stream.cuh) skips them
+//   (k_cls_finalize marks such components, comp_mode = 1; the sequential solver
+//    in solve_stream.cuh skips them)
 //   k_rank_count   per 1024-request tile: class of each request, its rank among the
 //                  tile's requests of the same class (warp __match_any_sync + a
 //                  32 x 256 shared-memory count table), per-(class, tile) totals
@@ -19,12 +19,6 @@
 #include "classes.cuh"
 
 namespace yd {
-
-__global__ void k_comp_mode(uint32_t n_comps, ClassTable ct, uint32_t* __restrict__ comp_mode) {
-  uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= n_comps) return;
-  comp_mode[c] = (ct.meta[1] == 0 && ct.comp_ncls[c] == 1 && !(ct.comp_flags[c] & 1u)) ? 1u : 0u;
-}
 
 constexpr int kRankTile = 1024;
 

@@ -5,9 +5,9 @@
 // order (tier, utilisation, registry position): ties on the code are broken by
 // position exactly like `first minimum wins` (task_dispatcher.cc:444).
 //
-// One pass = per-tile digit histogram (a kernel for the first pass; later passes get
-// it from the previous scatter), one-block exclusive scan of the (digit-major,
-// tile-minor) counts, stable scatter.  Stability inside a tile:
+// One pass = two kernels: per-tile digit histogram (shared-memory atomics), then a stable
+// scatter in which every block derives its own global bases from the raw tile histograms
+// (so there is no separate scan kernel on the critical path).  Stability inside a tile:
 // warp w owns a contiguous chunk of the tile and walks it 32 elements at a time;
 // __match_any_sync ranks equal digits inside a group, per-warp digit counters in
 // shared memory carry the rank across groups, and a prefix over the warps' counts
@@ -105,11 +105,12 @@ __global__ void __launch_bounds__(kRsThreads) k_rs_scatter(const KeyT* __restric
                                                            const uint32_t* __restrict__ vals_in,
                                                            const unsigned long long* __restrict__ n_ptr,
                                                            int shift, uint32_t nb,
-                                                           const uint32_t* __restrict__ hist_scanned,
+                                                           const uint32_t* __restrict__ hist /* raw [bin][tile] */,
                                                            KeyT* __restrict__ keys_out,
-                                                           uint32_t* __restrict__ vals_out,
-                                                           int next_shift, uint32_t* __restrict__ hist_next) {
+                                                           uint32_t* __restrict__ vals_out) {
   __shared__ uint32_t wcnt[kRsWarps][kRsBins];  // per-warp digit counts, then running offsets
+  __shared__ uint32_t dig_base[kRsBins];        // global base of (digit, this tile)
+  __shared__ uint32_t wsum[kRsThreads / 32];
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t n = (uint32_t)*n_ptr;
   for (int i = tid; i < kRsWarps * kRsBins; i += kRsThreads) (&wcnt[0][0])[i] = 0;
@@ -121,9 +122,36 @@ __global__ void __launch_bounds__(kRsThreads) k_rs_scatter(const KeyT* __restric
     if (idx < n) atomicAdd(&wcnt[warp][rs_digit(keys_in[idx], shift)], 1u);
   }
   __syncthreads();
+  // This tile's global base per digit, straight from the raw tile histograms (no separate
+  // scan kernel): base(d) = sum of all tiles' counts of smaller digits
+  //                        + counts of digit d in earlier tiles.
+  {
+    uint32_t total = 0, before = 0;
+    if (tid < kRsBins) {
+      const uint32_t* row = hist + tid * nb;
+      for (uint32_t b = 0; b < nb; ++b) {
+        const uint32_t c = row[b];
+        before += b < blockIdx.x ? c : 0u;
+        total += c;
+      }
+    }
+    // exclusive scan of `total` over the digits (kRsBins <= kRsThreads)
+    uint32_t x = total;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      uint32_t y = __shfl_up_sync(0xffffffffu, x, d);
+      if (lane >= d) x += y;
+    }
+    if (lane == 31) wsum[warp] = x;
+    __syncthreads();
+    uint32_t woff = 0;
+    for (uint32_t w = 0; w < warp; ++w) woff += wsum[w];
+    if (tid < kRsBins) dig_base[tid] = woff + x - total + before;
+    __syncthreads();
+  }
   // per digit: exclusive prefix over warps, offset by this tile's global base
   for (int d = tid; d < kRsBins; d += kRsThreads) {
-    uint32_t run = hist_scanned[d * nb + blockIdx.x];
+    uint32_t run = dig_base[d];
 #pragma unroll
     for (int w = 0; w < kRsWarps; ++w) {
       uint32_t c = wcnt[w][d];
@@ -148,8 +176,6 @@ __global__ void __launch_bounds__(kRsThreads) k_rs_scatter(const KeyT* __restric
     if (valid) {
       keys_out[dst] = k;
       vals_out[dst] = vals_in ? vals_in[idx] : idx;  // first pass: payload = original slot index
-      // histogram of the NEXT pass, per tile of the output array (saves a k_rs_hist launch)
-      if (hist_next) atomicAdd(&hist_next[rs_digit(k, next_shift) * nb + dst / kRsTile], 1u);
     }
   }
 }

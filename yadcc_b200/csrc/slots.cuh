@@ -75,6 +75,7 @@ __global__ void __launch_bounds__(1024) k_slot_rows(uint32_t S, const DynParams*
   if (tid == 0) {
     row_off[S] = carry_s;
     counters->slots = carry_s;
+    counters->pad[0] = counters->pad[1] = counters->pad[2] = counters->pad[3] = 0;  // solver diagnostics
   }
 }
 

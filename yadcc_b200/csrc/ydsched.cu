@@ -157,11 +157,18 @@ struct yd_sched {
 
   // slot-stream solver state
   DevBuf d_sv_env_off, d_sv_envs, d_comp_mode;
-  DevBuf d_slot_owner, d_sort_k[2], d_sort_v[2], d_hist[2];
+  DevBuf d_slot_owner, d_sort_k[2], d_sort_v[2];
+  // one zero-filled scratch region per solve: radix histograms (one per pass), the class
+  // table's u32 arrays, the per-(class, tile) list counts -- a single memset node
+  DevBuf d_zero;
+  size_t z_hist_off[10] = {}, z_cls_off = 0, z_listcnt_off = 0, z_bytes = 0;
+  uint32_t sort_nb = 0;
+  cudaStream_t st2 = nullptr, st_copy = nullptr;  // class/rank branch; request upload
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_h2d = nullptr;
   uint32_t cls_bound = 16;  // classes the per-class grids are sized for; grows on demand (<= yd::kMaxClasses)
-  DevBuf d_cls_keys, d_cls_u32;  // class table: 8-byte keys; all u32 arrays in one allocation
-  DevBuf d_spos, d_sr, d_scomp, d_list_cnt, d_list, d_rcls, d_rrank, d_rank_cnt;
+  DevBuf d_list, d_rcls, d_rrank, d_rank_cnt;
   bool stream_attr_set = false;
+  size_t res_words = 0;  // u32 words of res[] in d_res (the class-table keys follow)
 
   // lease ring
   DevBuf d_t_exp, d_t_srv, d_t_flags;
@@ -470,7 +477,12 @@ yd_sched* yd_create(const yd_config* cfg) {
   s->solver_pref = cfg->solver;
   s->use_graphs = !(cfg->reserved & 1u) && !getenv("YDSCHED_NO_GRAPH");
   YD_CUDA_CHECK(cudaStreamCreateWithFlags(&s->st, cudaStreamNonBlocking));
+  YD_CUDA_CHECK(cudaStreamCreateWithFlags(&s->st2, cudaStreamNonBlocking));
+  YD_CUDA_CHECK(cudaStreamCreateWithFlags(&s->st_copy, cudaStreamNonBlocking));
   for (auto& e : s->ev) YD_CUDA_CHECK(cudaEventCreate(&e));
+  YD_CUDA_CHECK(cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming));
+  YD_CUDA_CHECK(cudaEventCreateWithFlags(&s->ev_join, cudaEventDisableTiming));
+  YD_CUDA_CHECK(cudaEventCreateWithFlags(&s->ev_h2d, cudaEventDisableTiming));
   s->ips.emplace_back();  // id 0 == YD_IP_NONE == the empty requestor string
   s->ip_ids.emplace("", 0);
   s->d_counters.ensure(sizeof(Counters));
@@ -495,14 +507,15 @@ void yd_destroy(yd_sched* s) {
                     &s->d_t_flags, &s->d_reqs, &s->d_res, &s->d_out, &s->d_blk, &s->d_row_off, &s->d_row_len,
                     &s->d_codes, &s->d_ids, &s->d_ok, &s->d_counters, &s->d_sv_env_off, &s->d_sv_envs,
                     &s->d_comp_mode, &s->d_slot_owner, &s->d_sort_k[0], &s->d_sort_k[1], &s->d_sort_v[0],
-                    &s->d_sort_v[1], &s->d_hist[0], &s->d_hist[1], &s->d_cls_keys, &s->d_cls_u32, &s->d_spos, &s->d_sr, &s->d_scomp,
-                    &s->d_list_cnt, &s->d_list, &s->d_rcls, &s->d_rrank, &s->d_rank_cnt}) {
+                    &s->d_sort_v[1], &s->d_zero, &s->d_list, &s->d_rcls, &s->d_rrank, &s->d_rank_cnt}) {
     b->release();
   }
   for (auto& g : s->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
   s->d_dyn.release();
   for (PinBuf* b : {&s->h_facts, &s->h_topo, &s->h_counters, &s->h_small, &s->h_dyn, &s->h_meta}) b->release();
   for (auto& e : s->ev) cudaEventDestroy(e);
+  cudaEventDestroy(s->ev_fork); cudaEventDestroy(s->ev_join); cudaEventDestroy(s->ev_h2d);
+  cudaStreamDestroy(s->st2); cudaStreamDestroy(s->st_copy);
   cudaStreamDestroy(s->st);
   delete s;
 }
@@ -569,9 +582,10 @@ yd::TopoView MakeTopo(yd_sched* s) {
 }
 
 yd::ClassTable MakeClassTable(yd_sched* s) {
-  uint32_t* u = s->d_cls_u32.as<uint32_t>();
+  uint32_t* u = reinterpret_cast<uint32_t*>(static_cast<char*>(s->d_zero.p) + s->z_cls_off);
   yd::ClassTable ct{};
-  ct.keys = s->d_cls_keys.as<unsigned long long>();
+  // the 8-byte keys sit right behind res[] so one 0xFF memset initialises both
+  ct.keys = reinterpret_cast<unsigned long long*>(s->d_res.as<uint32_t>() + s->res_words);
   ct.slot_cls = u;                       u += yd::kClsTableSize;
   ct.meta = u;                           u += 8;
   ct.cls_env = u;                        u += yd::kMaxClasses;
@@ -585,14 +599,15 @@ yd::ClassTable MakeClassTable(yd_sched* s) {
   return ct;
 }
 
-// Slot table (both solvers).  Returns the number of kernels launched.
-uint32_t LaunchSlotTable(yd_sched* s, bool with_owner) {
+// Slot table (both solvers).  For the slot-stream solver it also records slot owners.
+// Returns the number of kernels launched.
+uint32_t LaunchSlotTable(yd_sched* s, bool for_stream) {
   const uint32_t S = (uint32_t)s->sv.size();
   cudaStream_t st = s->st;
   yd::ServantArrays arr = s->arrays();
   yd::k_slot_rows<<<1, 1024, 0, st>>>(S, s->d_dyn.as<yd::DynParams>(), arr, s->d_row_off.as<uint32_t>(),
                                       s->d_row_len.as<uint32_t>(), s->d_counters.as<Counters>());
-  uint32_t* owner = with_owner ? s->d_slot_owner.as<uint32_t>() : nullptr;
+  uint32_t* owner = for_stream ? s->d_slot_owner.as<uint32_t>() : nullptr;
   if (s->wide) {
     yd::k_slot_fill<true><<<(S + 7) / 8, 256, 0, st>>>(S, arr, s->d_row_off.as<uint32_t>(),
                                                        s->d_row_len.as<uint32_t>(), nullptr,
@@ -643,36 +658,24 @@ uint32_t LaunchRowscan(yd_sched* s) {
 }
 
 template <typename KeyT>
-uint32_t LaunchSort(yd_sched* s, size_t bound, int first_bit, int last_bit) {
+uint32_t LaunchSort(yd_sched* s, int first_bit, int last_bit) {
   cudaStream_t st = s->st;
-  const uint32_t nb = (uint32_t)((bound + yd::kRsTile - 1) / yd::kRsTile);
+  const uint32_t nb = s->sort_nb;
   const unsigned long long* n_ptr = &s->d_counters.as<Counters>()->slots;
-  const size_t hbytes = size_t(yd::kRsBins) * nb * 4;
-  s->d_hist[0].ensure(hbytes);
-  s->d_hist[1].ensure(hbytes);
+  auto hist = [&](int pass) { return reinterpret_cast<uint32_t*>(static_cast<char*>(s->d_zero.p) + s->z_hist_off[pass]); };
   const KeyT* kin = s->d_codes.as<KeyT>();
   const uint32_t* vin = nullptr;
-  int cur = 0, hcur = 0;
+  int cur = 0, pass = 0;
   uint32_t launches = 0;
-  yd::k_rs_hist<KeyT><<<nb, yd::kRsThreads, 0, st>>>(kin, n_ptr, first_bit, nb, s->d_hist[0].as<uint32_t>());
-  ++launches;
-  for (int shift = first_bit; shift <= last_bit; shift += yd::kRsBits) {
+  for (int shift = first_bit; shift <= last_bit; shift += yd::kRsBits, ++pass) {
     KeyT* kout = s->d_sort_k[cur].as<KeyT>();
     uint32_t* vout = s->d_sort_v[cur].as<uint32_t>();
-    const bool more = shift + yd::kRsBits <= last_bit;
-    uint32_t* hnext = nullptr;
-    if (more) {
-      hnext = s->d_hist[hcur ^ 1].as<uint32_t>();
-      YD_CUDA_CHECK(cudaMemsetAsync(hnext, 0, hbytes, st));
-    }
-    yd::k_scan_u32<<<1, 1024, 0, st>>>(s->d_hist[hcur].as<uint32_t>(), yd::kRsBins * nb, nullptr, 0, nullptr);
-    yd::k_rs_scatter<KeyT><<<nb, yd::kRsThreads, 0, st>>>(kin, vin, n_ptr, shift, nb, s->d_hist[hcur].as<uint32_t>(),
-                                                          kout, vout, shift + yd::kRsBits, hnext);
+    yd::k_rs_hist<KeyT><<<nb, yd::kRsThreads, 0, st>>>(kin, n_ptr, shift, nb, hist(pass));
+    yd::k_rs_scatter<KeyT><<<nb, yd::kRsThreads, 0, st>>>(kin, vin, n_ptr, shift, nb, hist(pass), kout, vout);
     launches += 2;
     kin = kout;
     vin = vout;
     cur ^= 1;
-    hcur ^= 1;
   }
   if (cur == 0) {  // an even number of passes leaves the result in [1]: normalise to [0]
     std::swap(s->d_sort_k[0], s->d_sort_k[1]);
@@ -681,20 +684,23 @@ uint32_t LaunchSort(yd_sched* s, size_t bound, int first_bit, int last_bit) {
   return launches;
 }
 
-// Allocates everything LaunchStream touches for size class (Nb, slot_b); called before a
-// graph capture so that no allocation happens inside it.
+// Allocates everything the slot-stream sequence touches for size class (Nb, slot_b) and
+// lays out the zero-initialised scratch region; called before a graph capture so that no
+// allocation happens inside it.
 void PrepareStreamBuffers(yd_sched* s, uint32_t Nb, size_t slot_b) {
   const size_t ksz = s->wide ? 8 : 4;
   for (int b = 0; b < 2; ++b) { s->d_sort_k[b].ensure(slot_b * ksz); s->d_sort_v[b].ensure(slot_b * 4); }
-  const uint32_t nb_sort = (uint32_t)((slot_b + yd::kRsTile - 1) / yd::kRsTile);
-  s->d_hist[0].ensure(size_t(yd::kRsBins) * nb_sort * 4);
-  s->d_hist[1].ensure(size_t(yd::kRsBins) * nb_sort * 4);
-  const size_t cls_u32 = yd::kClsTableSize + 8 + 5 * yd::kMaxClasses + 2 * size_t(s->n_comps) + 8;
-  s->d_cls_keys.ensure(yd::kClsTableSize * 8);
-  s->d_cls_u32.ensure(cls_u32 * 4);
-  s->d_spos.ensure(slot_b * 4); s->d_sr.ensure(slot_b * 4); s->d_scomp.ensure(slot_b * 4);
+  s->sort_nb = (uint32_t)((slot_b + yd::kRsTile - 1) / yd::kRsTile);
+  const int passes = s->wide ? 9 : 4;
+  size_t off = 0;
+  for (int p = 0; p < passes; ++p) { s->z_hist_off[p] = off; off += size_t(yd::kRsBins) * s->sort_nb * 4; }
+  s->z_cls_off = off;
+  off += (yd::kClsTableSize + 8 + 5 * yd::kMaxClasses + 2 * size_t(s->n_comps) + 8) * 4;
   const uint32_t n_tiles = (uint32_t)((slot_b + yd::kListTile - 1) / yd::kListTile);
-  s->d_list_cnt.ensure((size_t(s->cls_bound) * n_tiles + 1) * 4);
+  s->z_listcnt_off = off;
+  off += (size_t(s->cls_bound) * n_tiles + 1) * 4;
+  s->z_bytes = (off + 255) & ~size_t(255);
+  s->d_zero.ensure(s->z_bytes);
   s->d_list.ensure(slot_b * 8 * 4);
   const uint32_t n_rtiles = (Nb + yd::kRankTile - 1) / yd::kRankTile;
   s->d_rcls.ensure(size_t(Nb) * 4); s->d_rrank.ensure(size_t(Nb) * 4);
@@ -705,74 +711,60 @@ void PrepareStreamBuffers(yd_sched* s, uint32_t Nb, size_t slot_b) {
   }
 }
 
-// Solver 2: sorted slot streams.
-uint32_t LaunchStream(yd_sched* s, uint32_t N, size_t slot_bound) {
-  cudaStream_t st = s->st;
-  const uint32_t S = (uint32_t)s->sv.size();
+// Solver 2: sorted slot streams.  Two concurrent branches:
+//   st  : slot table (+ first histogram) -> radix passes
+//   st2 : [wait for the request upload] class table -> finalize -> FIFO ranks -> scan
+// joined before the per-class lists.  `capturing` selects the external-event flavour of
+// the wait on the upload (the upload itself is never part of the graph).
+uint32_t LaunchStream(yd_sched* s, uint32_t N, size_t slot_b, bool capturing) {
+  cudaStream_t st = s->st, st2 = s->st2;
   uint32_t launches = 0;
-  const size_t ksz = s->wide ? 8 : 4;
-  for (int b = 0; b < 2; ++b) { s->d_sort_k[b].ensure(slot_bound * ksz); s->d_sort_v[b].ensure(slot_bound * 4); }
-  // ---- 1. sort the slot codes (stable; payload = original slot index) ---------
-  if (s->wide) launches += LaunchSort<unsigned long long>(s, slot_bound, 0, 62);
-  else launches += LaunchSort<uint32_t>(s, slot_bound, 3, 30);
-  const uint32_t* sorted_orig = s->d_sort_v[0].as<uint32_t>();
-  const unsigned long long* m_ptr = &s->d_counters.as<Counters>()->slots;
-
-  // ---- 2. classes ------------------------------------------------------------
-  const size_t cls_u32 = yd::kClsTableSize + 8 + 5 * yd::kMaxClasses + 2 * size_t(s->n_comps) + 8;
-  s->d_cls_keys.ensure(yd::kClsTableSize * 8);
-  s->d_cls_u32.ensure(cls_u32 * 4);
-  YD_CUDA_CHECK(cudaMemsetAsync(s->d_cls_keys.p, 0xFF, yd::kClsTableSize * 8, st));
-  YD_CUDA_CHECK(cudaMemsetAsync(s->d_cls_u32.p, 0, cls_u32 * 4, st));
   yd::TopoView t = MakeTopo(s);
   yd::ClassTable ct = MakeClassTable(s);
   yd::ServantArrays arr = s->arrays();
   const yd::DynParams* dp = s->d_dyn.as<yd::DynParams>();
-  yd::k_cls_insert<<<(N + 255) / 256, 256, 0, st>>>(s->d_reqs.as<yd_task_req>(), dp, t, ct);
-  yd::k_cls_number<<<1, 1024, 0, st>>>(t, ct);
-  const uint32_t CB = s->cls_bound;
-  yd::k_cls_elig<<<dim3(std::max(1u, std::min(64u, (s->max_comp_servants + 255) / 256)), CB), 256, 0, st>>>(t, ct,
-                                                                                                             arr);
+  uint32_t* list_cnt = reinterpret_cast<uint32_t*>(static_cast<char*>(s->d_zero.p) + s->z_listcnt_off);
+  const uint32_t n_tiles = (uint32_t)((slot_b + yd::kListTile - 1) / yd::kListTile);
+  const uint32_t n_rtiles = (N + yd::kRankTile - 1) / yd::kRankTile;
+
+  // ---- fork ---------------------------------------------------------------------
+  YD_CUDA_CHECK(cudaEventRecord(s->ev_fork, st));
+  YD_CUDA_CHECK(cudaStreamWaitEvent(st2, s->ev_fork, 0));
+  // branch B: classes and FIFO ranks (needs the requests in HBM)
+  YD_CUDA_CHECK(cudaStreamWaitEvent(st2, s->ev_h2d, capturing ? cudaEventWaitExternal : 0));
+  yd::k_cls_insert<<<(N + 255) / 256, 256, 0, st2>>>(s->d_reqs.as<yd_task_req>(), dp, t, ct);
+  yd::k_cls_finalize<<<1, 1024, 0, st2>>>(t, ct, arr, s->n_comps, s->d_comp_mode.as<uint32_t>());
+  yd::k_rank_count<<<n_rtiles, yd::kRankTile, 0, st2>>>(s->d_reqs.as<yd_task_req>(), dp, t, ct,
+                                                         s->d_comp_mode.as<uint32_t>(), n_rtiles,
+                                                         s->d_rcls.as<uint32_t>(), s->d_rrank.as<uint32_t>(),
+                                                         s->d_rank_cnt.as<uint32_t>());
+  yd::k_scan_u32<<<1, 1024, 0, st2>>>(s->d_rank_cnt.as<uint32_t>(), 0, ct.meta, n_rtiles, nullptr);
+  YD_CUDA_CHECK(cudaEventRecord(s->ev_join, st2));
+  launches += 4;
+  // branch A: slot table and its sort
+  launches += LaunchSlotTable(s, true);
+  if (s->wide) launches += LaunchSort<unsigned long long>(s, 0, 62);
+  else launches += LaunchSort<uint32_t>(s, 3, 30);
+  // ---- join -----------------------------------------------------------------------
+  YD_CUDA_CHECK(cudaStreamWaitEvent(st, s->ev_join, 0));
+
+  // ---- per-class sorted slot lists ----------------------------------------------------
+  const unsigned long long* m_ptr = &s->d_counters.as<Counters>()->slots;
+  yd::SlotDecode dec{s->d_sort_v[0].as<uint32_t>(), s->d_slot_owner.as<uint32_t>(), s->d_row_off.as<uint32_t>(),
+                     s->d_row_len.as<uint32_t>(), s->d_run.as<uint32_t>()};
+  yd::k_list_count<<<n_tiles, yd::kListTile, 0, st>>>(m_ptr, dec, t, ct, arr, n_tiles, list_cnt);
+  yd::k_scan_u32<<<1, 1024, 0, st>>>(list_cnt, 0, ct.meta, n_tiles, nullptr);
+  yd::k_list_fill<<<n_tiles, yd::kListTile, 0, st>>>(m_ptr, dec, t, ct, arr, n_tiles, list_cnt,
+                                                     s->d_list.as<uint2>(), (uint32_t)(slot_b * 4));
   launches += 3;
 
-  // ---- 3. per-class sorted slot lists ------------------------------------------
-  s->d_spos.ensure(slot_bound * 4); s->d_sr.ensure(slot_bound * 4); s->d_scomp.ensure(slot_bound * 4);
-  yd::k_slot_decode<<<(unsigned)((slot_bound + 255) / 256), 256, 0, st>>>(
-      sorted_orig, m_ptr, s->d_slot_owner.as<uint32_t>(), s->d_row_off.as<uint32_t>(), s->d_row_len.as<uint32_t>(),
-      s->d_run.as<uint32_t>(), s->d_sv_comp.as<uint32_t>(), s->d_spos.as<uint32_t>(), s->d_sr.as<uint32_t>(),
-      s->d_scomp.as<uint32_t>());
-  const uint32_t n_tiles = (uint32_t)((slot_bound + yd::kListTile - 1) / yd::kListTile);
-  const size_t n_cnt = size_t(CB) * n_tiles + 1;
-  s->d_list_cnt.ensure(n_cnt * 4);
-  YD_CUDA_CHECK(cudaMemsetAsync(s->d_list_cnt.p, 0, n_cnt * 4, st));
-  yd::k_list_count<<<dim3(n_tiles, CB), yd::kListTile, 0, st>>>(
-      m_ptr, s->d_spos.as<uint32_t>(), s->d_scomp.as<uint32_t>(), t, ct, arr, n_tiles, s->d_list_cnt.as<uint32_t>());
-  yd::k_scan_u32<<<1, 1024, 0, st>>>(s->d_list_cnt.as<uint32_t>(), 0, ct.meta, n_tiles, nullptr);
-  // a slot belongs to at most (classes of its component) lists; bound by classes x slots is wasteful,
-  // so size for the common case and let the device tell us (checked after the solve)
-  s->d_list.ensure(std::max<size_t>(slot_bound, 1) * 8 * 4);
-  yd::k_list_fill<<<dim3(n_tiles, CB), yd::kListTile, 0, st>>>(
-      m_ptr, s->d_spos.as<uint32_t>(), s->d_sr.as<uint32_t>(), s->d_scomp.as<uint32_t>(), t, ct, arr, n_tiles,
-      s->d_list_cnt.as<uint32_t>(), s->d_list.as<uint2>(), (uint32_t)(slot_bound * 4));
-  launches += 4;
-
-  // ---- 4a. data-parallel path: single-class components without self-requests -----
-  yd::k_comp_mode<<<(s->n_comps + 255) / 256, 256, 0, st>>>(s->n_comps, ct, s->d_comp_mode.as<uint32_t>());
-  const uint32_t n_rtiles = (N + yd::kRankTile - 1) / yd::kRankTile;
-  const size_t n_rcnt = size_t(CB) * n_rtiles + 1;
-  s->d_rcls.ensure(size_t(N) * 4); s->d_rrank.ensure(size_t(N) * 4); s->d_rank_cnt.ensure(n_rcnt * 4);
-  yd::k_rank_count<<<n_rtiles, yd::kRankTile, 0, st>>>(s->d_reqs.as<yd_task_req>(), dp, t, ct,
-                                                        s->d_comp_mode.as<uint32_t>(), n_rtiles,
-                                                        s->d_rcls.as<uint32_t>(), s->d_rrank.as<uint32_t>(),
-                                                        s->d_rank_cnt.as<uint32_t>());
-  yd::k_scan_u32<<<1, 1024, 0, st>>>(s->d_rank_cnt.as<uint32_t>(), 0, ct.meta, n_rtiles, nullptr);
+  // ---- data-parallel path: single-class components without self-requests ----------------
   yd::k_rank_assign<<<(N + 255) / 256, 256, 0, st>>>(dp, n_rtiles, t, ct, s->d_rcls.as<uint32_t>(),
-                                                     s->d_rrank.as<uint32_t>(), s->d_rank_cnt.as<uint32_t>(),
-                                                     s->d_list_cnt.as<uint32_t>(), n_tiles, s->d_list.as<uint2>(),
-                                                     arr, s->d_res.as<uint32_t>());
-  launches += 4;
+                                                     s->d_rrank.as<uint32_t>(), s->d_rank_cnt.as<uint32_t>(), list_cnt,
+                                                     n_tiles, s->d_list.as<uint2>(), arr, s->d_res.as<uint32_t>());
+  launches += 1;
 
-  // ---- 4b. sequential decisions for everything else -------------------------------
+  // ---- sequential decisions for everything else ---------------------------------------------
   yd::StreamArgs a{};
   a.reqs = s->d_reqs.as<yd_task_req>();
   a.dp = dp;
@@ -781,17 +773,15 @@ uint32_t LaunchStream(yd_sched* s, uint32_t N, size_t slot_bound) {
   a.ct = ct;
   a.sv = arr;
   a.row_len = s->d_row_len.as<uint32_t>();
-  a.list_off = s->d_list_cnt.as<uint32_t>();
+  a.list_off = list_cnt;
   a.n_list_tiles = n_tiles;
   a.list = s->d_list.as<uint2>();
   a.max_comp_servants = s->max_comp_servants;
   a.comp_mode = s->d_comp_mode.as<uint32_t>();
   a.counters = s->d_counters.as<Counters>();
-  YD_CUDA_CHECK(cudaMemsetAsync(&s->d_counters.as<Counters>()->pad[0], 0, 32, st));
   const size_t dyn = size_t(s->max_comp_servants) * 8;
   yd::k_solve_stream<<<s->n_comps, (yd::kStreamProducers + 1) * 32, dyn, st>>>(a);
   launches += 1;
-  (void)S;
   return launches;
 }
 
@@ -809,7 +799,7 @@ uint64_t NextPow2(uint64_t v, uint64_t lo) {
 
 // Everything between the request upload and the grant download, for size class
 // (Nb, slot_b): the sequence that is captured into a CUDA graph.
-uint32_t EnqueueSolve(yd_sched* s, uint32_t Nb, size_t slot_b, uint32_t solver, bool record_events) {
+uint32_t EnqueueSolve(yd_sched* s, uint32_t Nb, size_t slot_b, uint32_t solver, bool record_events, bool capturing) {
   cudaStream_t st = s->st;
   const uint32_t S = (uint32_t)s->sv.size();
   const bool have_work = S && s->n_comps;
@@ -817,16 +807,21 @@ uint32_t EnqueueSolve(yd_sched* s, uint32_t Nb, size_t slot_b, uint32_t solver, 
   uint32_t launches = 0;
   const yd::DynParams* dp = s->d_dyn.as<yd::DynParams>();
   YD_CUDA_CHECK(cudaMemcpyAsync(s->d_dyn.p, s->h_dyn.p, sizeof(yd::DynParams), cudaMemcpyHostToDevice, st));
-  YD_CUDA_CHECK(cudaMemsetAsync(s->d_res.p, 0xFF, size_t(Nb) * 4, st));  // == kResEnvNotFound
+  // res[] = kResEnvNotFound, and (slot-stream) the class-table keys behind it = empty
+  YD_CUDA_CHECK(cudaMemsetAsync(s->d_res.p, 0xFF, size_t(Nb) * 4 + (solver == 2 ? yd::kClsTableSize * 8 : 0), st));
+  if (solver == 2 && have_work) YD_CUDA_CHECK(cudaMemsetAsync(s->d_zero.p, 0, s->z_bytes, st));
   if (record_events) YD_CUDA_CHECK(cudaEventRecord(s->ev[1], st));
-  if (have_work) launches += LaunchSlotTable(s, solver == 2);
-  if (record_events) YD_CUDA_CHECK(cudaEventRecord(s->ev[2], st));
   const uint32_t* abort_flag = nullptr;
   if (have_work && solver == 2) {
-    launches += LaunchStream(s, Nb, slot_b);
+    if (record_events) YD_CUDA_CHECK(cudaEventRecord(s->ev[2], st));
+    launches += LaunchStream(s, Nb, slot_b, capturing);
     abort_flag = MakeClassTable(s).meta + 1;
-  } else if (have_work) {
-    launches += LaunchRowscan(s);
+  } else {
+    if (have_work) launches += LaunchSlotTable(s, false);
+    if (record_events) YD_CUDA_CHECK(cudaEventRecord(s->ev[2], st));
+    // the row-scan kernels read the requests: they were uploaded on the copy stream
+    YD_CUDA_CHECK(cudaStreamWaitEvent(st, s->ev_h2d, capturing ? cudaEventWaitExternal : 0));
+    if (have_work) launches += LaunchRowscan(s);
   }
   if (record_events) YD_CUDA_CHECK(cudaEventRecord(s->ev[3], st));
   yd::k_final_count<<<nb, 1024, 0, st>>>(s->d_res.as<uint32_t>(), dp, s->d_blk.as<uint32_t>(), abort_flag);
@@ -870,7 +865,8 @@ void yd_wait_for_starting_new_tasks(yd_sched* s, int64_t now_ns, const yd_task_r
   const size_t slot_b = (size_t)NextPow2(std::max<size_t>(slot_bound, 1), 4096);
   const uint32_t nb = (Nb + 1023) / 1024;
   s->d_reqs.ensure(size_t(Nb) * sizeof(yd_task_req));
-  s->d_res.ensure(size_t(Nb) * 4);
+  s->res_words = Nb;
+  s->d_res.ensure(size_t(Nb) * 4 + yd::kClsTableSize * 8);
   s->d_out.ensure(size_t(Nb) * sizeof(yd_grant));
   s->d_blk.ensure(size_t(nb) * 4);
   s->d_row_off.ensure(size_t(S + 1) * 4);
@@ -895,7 +891,11 @@ void yd_wait_for_starting_new_tasks(yd_sched* s, int64_t now_ns, const yd_task_r
 
   uint32_t launches = 0;
   YD_CUDA_CHECK(cudaEventRecord(s->ev[0], st));
-  YD_CUDA_CHECK(cudaMemcpyAsync(s->d_reqs.p, reqs, size_t(N) * sizeof(yd_task_req), cudaMemcpyHostToDevice, st));
+  // The request upload runs on its own stream so that the slot table and its sort (which
+  // do not read the requests) overlap it; consumers wait on ev_h2d.
+  YD_CUDA_CHECK(cudaMemcpyAsync(s->d_reqs.p, reqs, size_t(N) * sizeof(yd_task_req), cudaMemcpyHostToDevice,
+                                s->st_copy));
+  YD_CUDA_CHECK(cudaEventRecord(s->ev_h2d, s->st_copy));
   bool graphed = false;
   for (int attempt = 0;; ++attempt) {
     s->h_meta.as<uint32_t>()[0] = s->h_meta.as<uint32_t>()[1] = 0;
@@ -913,7 +913,7 @@ void yd_wait_for_starting_new_tasks(yd_sched* s, int64_t now_ns, const yd_task_r
       if (!hit) {
         cudaGraph_t graph = nullptr;
         YD_CUDA_CHECK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-        uint32_t l = EnqueueSolve(s, Nb, slot_b, solver, false);
+        uint32_t l = EnqueueSolve(s, Nb, slot_b, solver, false, true);
         YD_CUDA_CHECK(cudaStreamEndCapture(st, &graph));
         cudaGraphExec_t exec = nullptr;
         YD_CUDA_CHECK(cudaGraphInstantiate(&exec, graph, 0));
@@ -932,7 +932,7 @@ void yd_wait_for_starting_new_tasks(yd_sched* s, int64_t now_ns, const yd_task_r
       graphed = true;
     } else {
       if (solver == 2) PrepareStreamBuffers(s, Nb, slot_b);
-      launches += EnqueueSolve(s, Nb, slot_b, solver, true);
+      launches += EnqueueSolve(s, Nb, slot_b, solver, true, false);
     }
     YD_CUDA_CHECK(cudaMemcpyAsync(out, s->d_out.p, size_t(N) * sizeof(yd_grant), cudaMemcpyDeviceToHost, st));
     YD_CUDA_CHECK(cudaEventRecord(s->ev[5], st));

@@ -46,8 +46,12 @@ class ShardedDispatcher:
         self.device = device  # torch device for the collective (cuda:LOCAL_RANK with NCCL, cpu with gloo)
         self.digest_owner = digest_owner
         self.next_task_id = 0  # global id space
-        # global task id -> local task id, for the grants this rank owns
-        self._g2l: dict[int, int] = {}
+        # global task id -> local task id for the grants this rank owns: two parallel arrays,
+        # sorted by global id (ids only ever grow), dead entries compacted lazily
+        self._gid = np.zeros(0, dtype=np.uint64)
+        self._lid = np.zeros(0, dtype=np.uint64)
+        self._alive = np.zeros(0, dtype=bool)
+        self._owners_cache = None  # (owners array object, mine, mine on the collective's device)
         self.collective_bytes = 0
 
     # -- ownership -----------------------------------------------------------
@@ -81,41 +85,59 @@ class ShardedDispatcher:
         import torch.distributed as dist
 
         del digests
-        mine = np.nonzero(owners == self.rank)[0]
+        if self._owners_cache is None or self._owners_cache[0] is not owners:
+            mine = np.nonzero(owners == self.rank)[0]
+            self._owners_cache = (owners, mine, torch.as_tensor(mine, device=self.device))
+        _, mine, mine_t = self._owners_cache
         assert len(mine) == len(local_reqs)
         g = self.local.wait_for_starting_new_tasks(local_reqs, now).copy() if len(mine) else np.zeros(0, GRANT_DTYPE)
         ok = g["status"] == STATUS_GRANTED
         # the one exchange step: who was granted, over the whole global queue
         flags = torch.zeros(len(owners), dtype=torch.int32, device=self.device)
         if len(mine):
-            flags[torch.as_tensor(mine, device=self.device)] = torch.as_tensor(ok.astype(np.int32), device=self.device)
+            flags[mine_t] = torch.as_tensor(ok.astype(np.int32)).to(self.device, non_blocking=True)
         if self.world > 1:
             dist.all_reduce(flags, op=dist.ReduceOp.SUM, group=self.group)
             self.collective_bytes += flags.numel() * 4
-        before = torch.cumsum(flags, 0) - flags  # grants strictly earlier in the global FIFO
-        total = int(flags.sum().item())
+        csum = torch.cumsum(flags, 0)
+        total = int(csum[-1].item()) if len(owners) else 0
         if len(mine):
-            gids = self.next_task_id + before[torch.as_tensor(mine, device=self.device)].cpu().numpy().astype(np.uint64)
-            for gid, lid in zip(gids[ok].tolist(), g["task_id"][ok].tolist()):
-                self._g2l[gid] = lid
+            before = (csum - flags)[mine_t]  # grants strictly earlier in the global FIFO
+            gids = np.uint64(self.next_task_id) + before.cpu().numpy().astype(np.uint64)
+            self._gid = np.concatenate([self._gid, gids[ok]])
+            self._lid = np.concatenate([self._lid, g["task_id"][ok]])
+            self._alive = np.concatenate([self._alive, np.ones(int(ok.sum()), dtype=bool)])
             g["task_id"][ok] = gids[ok]
         self.next_task_id += total
         return g
 
+    def _lookup(self, global_ids) -> tuple[np.ndarray, np.ndarray]:
+        """(positions in the map, found mask) for the ids this rank owns and still holds."""
+        ids = np.asarray(global_ids, dtype=np.uint64)
+        pos = np.searchsorted(self._gid, ids)
+        pos_c = np.minimum(pos, max(len(self._gid) - 1, 0))
+        found = (pos < len(self._gid)) & (len(self._gid) > 0)
+        if len(self._gid):
+            found &= (self._gid[pos_c] == ids) & self._alive[pos_c]
+        return pos_c, found
+
     # -- lease maintenance, routed by global id -------------------------------------
     def free_tasks(self, global_ids) -> None:
-        local = [self._g2l.pop(int(i)) for i in global_ids if int(i) in self._g2l]
-        if local:
-            self.local.free_tasks(np.asarray(local, dtype=np.uint64))
+        pos, found = self._lookup(global_ids)
+        if found.any():
+            # np.unique: an id listed twice frees once (FreeTask of an unknown id is a no-op)
+            p = np.unique(pos[found])
+            self.local.free_tasks(self._lid[p])
+            self._alive[p] = False
+            if len(self._alive) > 4096 and self._alive.mean() < 0.5:
+                keep = self._alive
+                self._gid, self._lid, self._alive = self._gid[keep], self._lid[keep], self._alive[keep]
 
     def keep_tasks_alive(self, global_ids, new_expires_in: float, *, now: float = 0.0) -> np.ndarray:
         """Statuses for the ids this rank owns (False for ids owned elsewhere; the caller
         ORs the ranks' answers)."""
-        ids = [int(i) for i in global_ids]
-        out = np.zeros(len(ids), dtype=bool)
-        idx = [k for k, i in enumerate(ids) if i in self._g2l]
-        if idx:
-            st = self.local.keep_tasks_alive(np.asarray([self._g2l[ids[k]] for k in idx], dtype=np.uint64),
-                                             new_expires_in, now=now)
-            out[idx] = st
+        pos, found = self._lookup(global_ids)
+        out = np.zeros(len(pos), dtype=bool)
+        if found.any():
+            out[found] = self.local.keep_tasks_alive(self._lid[pos[found]], new_expires_in, now=now)
         return out
