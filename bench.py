@@ -109,6 +109,28 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.rows), "reasons": sorted(reasons)}
 
 
+def ncu_traffic_bytes() -> tuple[float | None, str]:
+    """DRAM bytes per solve from the committed ncu launch list (profiles/), if present."""
+    p = ROOT / "profiles" / "r1d_launches_summary.csv"
+    try:
+        last = p.read_text().strip().splitlines()[-1]
+        mb = float(last.split("DRAM traffic per solve:")[1].split("MB")[0])
+        return mb * 1e6, "profiles/r1d_launches_summary.csv (sum of dram__bytes_read+write over the solve kernels, cold caches)"
+    except Exception:
+        return None, "no ncu capture"
+
+
+def ncu_traffic_bytes() -> tuple[float | None, str]:
+    """DRAM bytes per solve from the committed ncu launch list (profiles/), if present."""
+    p = ROOT / "profiles" / "r1d_launches_summary.csv"
+    try:
+        last = p.read_text().strip().splitlines()[-1]
+        mb = float(last.split("DRAM traffic per solve:")[1].split("MB")[0])
+        return mb * 1e6, "profiles/r1d_launches_summary.csv (sum of dram__bytes_read+write over the solve kernels, cold caches)"
+    except Exception:
+        return None, "no ncu capture"
+
+
 def measured_hbm_peak() -> tuple[float, str]:
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -317,7 +339,8 @@ def run_ours(args):
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": f"{solver_name} solve pipeline (one CUDA graph, {launches // K} kernels)",
                          "achieved": achieved_model, "peak": peak, "unit": "GB/s", "frac": achieved_model / peak,
-                         "traffic": None, "peak_source": peak_src,
+                         "traffic": ncu_traffic_bytes()[0] if args.workload == "cfg2-mod" else None,
+                         "traffic_source": ncu_traffic_bytes()[1], "peak_source": peak_src,
                          "algorithmic_bytes_per_decision": model_bytes, "kernel_ms_per_step": ms_step,
                          "compulsory": {"bytes_per_step": compulsory,
                                         "achieved": compulsory / (ms_step / 1e3) / 1e9, "unit": "GB/s",
