@@ -174,3 +174,46 @@ def test_many_classes(make_dispatcher, n_classes):
         results.append(d.servant_state()["running_tasks"].copy())
     assert (results[0] == results[2]).all()
     assert (results[1] == results[3]).all()
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_merge_solver_coupled_no_self(make_dispatcher, seed):
+    """Coupled components whose requestors are NOT servants take the merge solver
+    (slots pick the earliest unserved compatible request).  Mixed versions, dedicated
+    servants, low memory, capacity below demand (Timeouts), a digest nobody can serve
+    (EnvironmentNotFound), several independent coupled components, and a component with
+    more than 32 classes (falls back to the sequential solver)."""
+    import numpy as np
+    from yadcc_b200 import Servant, PRIORITY_USER, PRIORITY_DEDICATED
+
+    rng = np.random.default_rng(100 + seed)
+    n_groups = 1 + seed % 3                     # independent coupled components
+    digs = [[f"{g:02x}{i:062x}" for i in range(int(rng.integers(2, 7)))] for g in range(n_groups)]
+    many_versions = seed == 5                   # > 32 (digest, min_version) classes in one component
+    results = []
+    for kind in ("cuda", "port"):
+        d = make_dispatcher(kind)
+        r = np.random.default_rng(200 + seed)
+        k = 0
+        for g in range(n_groups):
+            for _ in range(int(r.integers(30, 400))):
+                envs = [digs[g][j] for j in r.choice(len(digs[g]), size=int(r.integers(1, len(digs[g]) + 1)), replace=False)]
+                nproc = int(r.choice([8, 16, 32]))
+                d.keep_servant_alive(
+                    Servant(f"10.5.{k >> 8}.{k & 255}:8335", None, envs, int(r.choice([6, 7, 8, 9])), nproc,
+                            int(r.integers(0, nproc + 2)), int(r.choice([0, 64 << 30])),
+                            int(r.choice([5 << 30, 40 << 30, 40 << 30])), int(r.integers(0, nproc)),
+                            PRIORITY_DEDICATED if r.random() < 0.15 else PRIORITY_USER), 10.0, now=0.0)
+                k += 1
+        n = int(r.integers(500, 6000))
+        all_d = [x for g in digs for x in g] + ["ee" * 32]
+        mv = r.integers(0, 40, n).astype(np.uint32) if many_versions else r.choice([0, 7, 8, 9], n).astype(np.uint32)
+        reqs = d.make_requests(n, [all_d[j] for j in r.integers(0, len(all_d), n)],
+                               [f"172.20.{j >> 8}.{j & 255}" for j in r.integers(0, 3000, n)], mv)
+        results.append(d.wait_for_starting_new_tasks(reqs, 0.5).copy())
+        # a second batch continues from the state the first one left
+        results.append(d.wait_for_starting_new_tasks(reqs[: n // 2], 0.6).copy())
+        st = d.servant_state()
+        results.append(np.stack([st["running_tasks"], st["ever_assigned_tasks"]], 1))
+    for a, b in zip(results[:3], results[3:]):
+        assert (a == b).all()

@@ -26,7 +26,7 @@ constexpr unsigned long long kClsEmpty = ~0ull;
 struct ClassTable {
   unsigned long long* keys;  // [kClsTableSize] digest id << 32 | min_version, or kClsEmpty
   uint32_t* slot_cls;        // [kClsTableSize] class id of the slot
-  uint32_t* meta;            // [0] number of classes, [1] overflow flag (1: too many classes / table full / list
+  uint32_t* meta;            // [0] number of classes, [2] number of merge-mode components, [1] overflow flag (1: too many classes / table full / list
                              //     too long -> row-scan solver; 2: more classes than cls_bound -> retry with a bigger bound)
   uint32_t cls_bound;        // classes the per-class grids / tables of this solve are sized for (<= kMaxClasses)
   uint32_t* cls_env;         // [kMaxClasses]
@@ -34,8 +34,10 @@ struct ClassTable {
   uint32_t* cls_comp;
   uint32_t* cls_nelig;       // eligible servants (max_tasks != 0, digest, version)
   uint32_t* cls_count;       // requests of the class in this batch
+  uint32_t* cls_lbit;        // index of the class among the classes of its component (merge solver)
   uint32_t* comp_flags;      // [C] bit 0: some request's "self" servant lives in the component
   uint32_t* comp_ncls;       // [C] classes in the component
+  uint32_t* comp_midx;       // [C] merge-mode components: index of their pseudo-class list, else kNone
 };
 
 struct TopoView {  // the parts of the topology the class kernels need
@@ -202,9 +204,39 @@ __global__ void __launch_bounds__(1024) k_cls_finalize(TopoView t, ClassTable ct
     if (tid == 0) ct.cls_nelig[c] = s_sum;
     __syncthreads();
   }
+  // index of each class among the classes of its component
+  for (uint32_t c = tid; c < ncls; c += 1024) {
+    uint32_t lb = 0;
+    const uint32_t comp = ct.cls_comp[c];
+    for (uint32_t o = 0; o < c; ++o) lb += ct.cls_comp[o] == comp ? 1u : 0u;
+    ct.cls_lbit[c] = lb;
+  }
+  // solver mode per component:
+  //   1 = data-parallel (one class, nobody requests from one of its own servants)
+  //   2 = merge solver  (2..32 classes, nobody requests from one of its own servants)
+  //   0 = sequential slot-stream solver
   const bool healthy = ct.meta[1] == 0;
+  __shared__ uint32_t s_nmerge;
+  if (tid == 0) s_nmerge = 0;
+  __syncthreads();
   for (uint32_t c = tid; c < n_comps; c += 1024) {
-    comp_mode[c] = (healthy && ct.comp_ncls[c] == 1 && !(ct.comp_flags[c] & 1u)) ? 1u : 0u;
+    uint32_t mode = 0, midx = kNone;
+    const uint32_t k = ct.comp_ncls[c];
+    if (healthy && !(ct.comp_flags[c] & 1u)) {
+      if (k == 1) mode = 1;
+      else if (k >= 2 && k <= 32) {
+        midx = atomicAdd(&s_nmerge, 1u);
+        if (ncls + midx < ct.cls_bound) mode = 2;
+        else { midx = kNone; atomicMax(&ct.meta[1], 2u); }  // needs a bigger per-class grid: retry
+      }
+    }
+    comp_mode[c] = mode;
+    ct.comp_midx[c] = midx;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    ct.meta[2] = s_nmerge;
+    ct.meta[3] = min(ncls + s_nmerge, ct.cls_bound);  // lists to build: classes + merge pseudo-classes
   }
 }
 
@@ -241,10 +273,21 @@ __global__ void __launch_bounds__(kListTile) k_list_count(const unsigned long lo
   uint32_t pos, r, comp;
   const bool live = decode_slot(d, t, blockIdx.x * kListTile + threadIdx.x, (uint32_t)*m_ptr, pos, r, comp);
   const uint32_t ver = live ? (uint32_t)sv.version[pos] : 0u;
+  uint32_t mask = 0;  // bit cls_lbit[c]: my servant is eligible for class c of its component
   for (uint32_t c = 0; c < ncls; ++c) {
     const bool in = live && comp == ct.cls_comp[c] && ver >= ct.cls_mv[c] && servant_has_env(t, pos, ct.cls_env[c]);
+    if (in) mask |= 1u << (ct.cls_lbit[c] & 31u);
     const int cnt = __syncthreads_count(in);
     if (threadIdx.x == 0) counts[c * n_tiles + blockIdx.x] = (uint32_t)cnt;
+  }
+  // merge-mode components get one list of ALL their slots (pseudo-class ncls + midx)
+  const uint32_t nmerge = min(ct.meta[2], ct.cls_bound - ncls);
+  if (nmerge) {
+    const uint32_t midx = live ? ct.comp_midx[comp] : kNone;
+    for (uint32_t m = 0; m < nmerge; ++m) {
+      const int cnt = __syncthreads_count(live && midx == m && mask != 0);
+      if (threadIdx.x == 0) counts[(ncls + m) * n_tiles + blockIdx.x] = (uint32_t)cnt;
+    }
   }
 }
 
@@ -260,8 +303,19 @@ __global__ void __launch_bounds__(kListTile) k_list_fill(const unsigned long lon
   const bool live = decode_slot(d, t, blockIdx.x * kListTile + tid, (uint32_t)*m_ptr, pos, r, comp);
   const uint32_t ver = live ? (uint32_t)sv.version[pos] : 0u;
   const uint32_t local = live ? t.sv_local[pos] : 0u;
-  for (uint32_t c = 0; c < ncls; ++c) {
-    const bool in = live && comp == ct.cls_comp[c] && ver >= ct.cls_mv[c] && servant_has_env(t, pos, ct.cls_env[c]);
+  const uint32_t nmerge = min(ct.meta[2], ct.cls_bound - ncls);
+  const uint32_t midx = (live && nmerge) ? ct.comp_midx[comp] : kNone;
+  uint32_t mask = 0;
+  for (uint32_t c = 0; c < ncls + nmerge; ++c) {
+    bool in;
+    uint32_t payload = r;
+    if (c < ncls) {
+      in = live && comp == ct.cls_comp[c] && ver >= ct.cls_mv[c] && servant_has_env(t, pos, ct.cls_env[c]);
+      if (in) mask |= 1u << (ct.cls_lbit[c] & 31u);
+    } else {  // pseudo-class: every slot of a merge-mode component, payload = its class mask
+      in = live && midx == c - ncls && mask != 0;
+      payload = mask;
+    }
     const uint32_t bal = __ballot_sync(0xffffffffu, in);
     __syncthreads();  // warp_cnt of the previous class has been consumed
     if (lane == 0) warp_cnt[warp] = __popc(bal);
@@ -270,7 +324,7 @@ __global__ void __launch_bounds__(kListTile) k_list_fill(const unsigned long lon
       uint32_t before = __popc(bal & ((1u << lane) - 1));
       for (uint32_t w = 0; w < warp; ++w) before += warp_cnt[w];
       const uint32_t dst = offs[c * n_tiles + blockIdx.x] + before;
-      if (dst < list_cap) list[dst] = make_uint2(local, r);
+      if (dst < list_cap) list[dst] = make_uint2(local, payload);
       else ct.meta[1] = 1;  // more (class, slot) pairs than provisioned: the host reruns with solver 1
     }
   }

@@ -39,7 +39,7 @@ __global__ void __launch_bounds__(kRankTile) k_rank_count(const yd_task_req* __r
     const uint2 w0 = __ldg(reinterpret_cast<const uint2*>(reqs + q));
     if (w0.x < t.n_envs) {
       const uint32_t comp = t.env_comp[w0.x];
-      if (comp != kNone && comp_mode[comp] == 1) {
+      if (comp != kNone && comp_mode[comp] != 0) {  // data-parallel or merge: both need FIFO ranks
         const uint32_t slot = cls_find(ct.keys, ((unsigned long long)w0.x << 32) | w0.y);
         if (slot != kNone) cls = ct.slot_cls[slot];
       }
@@ -75,13 +75,21 @@ __global__ void __launch_bounds__(256) k_rank_assign(const DynParams* __restrict
                                                      const uint32_t* __restrict__ tile_off,
                                                      const uint32_t* __restrict__ list_off, uint32_t n_list_tiles,
                                                      const uint2* __restrict__ list, ServantArrays sv,
-                                                     uint32_t* __restrict__ res) {
+                                                     const uint32_t* __restrict__ comp_mode,
+                                                     uint32_t* __restrict__ rq, uint32_t* __restrict__ res) {
   const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= dp->n) return;
   const uint32_t c = rcls[q];
   if (c == kNone) return;  // not ours: the sequential solver (or nobody) answers it
   if (ct.cls_nelig[c] == 0) { res[q] = kResEnvNotFound; return; }  // cc:105-108
   const uint32_t rank = tile_off[c * n_tiles + q / kRankTile] - tile_off[c * n_tiles] + rrank[q];
+  if (comp_mode[ct.cls_comp[c]] == 2) {
+    // merge solver: publish the class's FIFO request list (class c owns rq[tile_off[c][0] ...));
+    // the verdict stays Timeout unless a slot picks this request (solve_merge.cuh)
+    rq[tile_off[c * n_tiles] + rank] = q;
+    res[q] = kResTimeout;
+    return;
+  }
   const uint32_t lb = list_off[c * n_list_tiles], le = list_off[(c + 1) * n_list_tiles];
   if (rank >= le - lb) { res[q] = kResTimeout; return; }  // cc:116-118
   const uint2 e = list[lb + rank];  // (servant local index, running_tasks value of the slot)

@@ -28,6 +28,7 @@
 #include "solve_rowscan.cuh"
 #include "solve_stream.cuh"
 #include "parallel.cuh"
+#include "solve_merge.cuh"
 #include "tasks.cuh"
 
 namespace {
@@ -166,7 +167,7 @@ struct yd_sched {
   cudaStream_t st2 = nullptr, st_copy = nullptr;  // class/rank branch; request upload
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_h2d = nullptr;
   uint32_t cls_bound = 16;  // classes the per-class grids are sized for; grows on demand (<= yd::kMaxClasses)
-  DevBuf d_list, d_rcls, d_rrank, d_rank_cnt;
+  DevBuf d_list, d_rcls, d_rrank, d_rank_cnt, d_rq;
   bool stream_attr_set = false;
   size_t res_words = 0;  // u32 words of res[] in d_res (the class-table keys follow)
 
@@ -507,7 +508,7 @@ void yd_destroy(yd_sched* s) {
                     &s->d_t_flags, &s->d_reqs, &s->d_res, &s->d_out, &s->d_blk, &s->d_row_off, &s->d_row_len,
                     &s->d_codes, &s->d_ids, &s->d_ok, &s->d_counters, &s->d_sv_env_off, &s->d_sv_envs,
                     &s->d_comp_mode, &s->d_slot_owner, &s->d_sort_k[0], &s->d_sort_k[1], &s->d_sort_v[0],
-                    &s->d_sort_v[1], &s->d_zero, &s->d_list, &s->d_rcls, &s->d_rrank, &s->d_rank_cnt}) {
+                    &s->d_sort_v[1], &s->d_zero, &s->d_list, &s->d_rcls, &s->d_rrank, &s->d_rank_cnt, &s->d_rq}) {
     b->release();
   }
   for (auto& g : s->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
@@ -593,8 +594,10 @@ yd::ClassTable MakeClassTable(yd_sched* s) {
   ct.cls_comp = u;                       u += yd::kMaxClasses;
   ct.cls_nelig = u;                      u += yd::kMaxClasses;
   ct.cls_count = u;                      u += yd::kMaxClasses;
+  ct.cls_lbit = u;                       u += yd::kMaxClasses;
   ct.comp_flags = u;                     u += s->n_comps;
-  ct.comp_ncls = u;
+  ct.comp_ncls = u;                      u += s->n_comps;
+  ct.comp_midx = u;
   ct.cls_bound = s->cls_bound;
   return ct;
 }
@@ -695,7 +698,7 @@ void PrepareStreamBuffers(yd_sched* s, uint32_t Nb, size_t slot_b) {
   size_t off = 0;
   for (int p = 0; p < passes; ++p) { s->z_hist_off[p] = off; off += size_t(yd::kRsBins) * s->sort_nb * 4; }
   s->z_cls_off = off;
-  off += (yd::kClsTableSize + 8 + 5 * yd::kMaxClasses + 2 * size_t(s->n_comps) + 8) * 4;
+  off += (yd::kClsTableSize + 8 + 6 * yd::kMaxClasses + 3 * size_t(s->n_comps) + 8) * 4;
   const uint32_t n_tiles = (uint32_t)((slot_b + yd::kListTile - 1) / yd::kListTile);
   s->z_listcnt_off = off;
   off += (size_t(s->cls_bound) * n_tiles + 1) * 4;
@@ -703,7 +706,7 @@ void PrepareStreamBuffers(yd_sched* s, uint32_t Nb, size_t slot_b) {
   s->d_zero.ensure(s->z_bytes);
   s->d_list.ensure(slot_b * 8 * 4);
   const uint32_t n_rtiles = (Nb + yd::kRankTile - 1) / yd::kRankTile;
-  s->d_rcls.ensure(size_t(Nb) * 4); s->d_rrank.ensure(size_t(Nb) * 4);
+  s->d_rcls.ensure(size_t(Nb) * 4); s->d_rrank.ensure(size_t(Nb) * 4); s->d_rq.ensure(size_t(Nb) * 4);
   s->d_rank_cnt.ensure((size_t(s->cls_bound) * n_rtiles + 1) * 4);
   if (!s->stream_attr_set) {
     YD_CUDA_CHECK(cudaFuncSetAttribute(yd::k_solve_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, 190 * 1024));
@@ -753,7 +756,7 @@ uint32_t LaunchStream(yd_sched* s, uint32_t N, size_t slot_b, bool capturing) {
   yd::SlotDecode dec{s->d_sort_v[0].as<uint32_t>(), s->d_slot_owner.as<uint32_t>(), s->d_row_off.as<uint32_t>(),
                      s->d_row_len.as<uint32_t>(), s->d_run.as<uint32_t>()};
   yd::k_list_count<<<n_tiles, yd::kListTile, 0, st>>>(m_ptr, dec, t, ct, arr, n_tiles, list_cnt);
-  yd::k_scan_u32<<<1, 1024, 0, st>>>(list_cnt, 0, ct.meta, n_tiles, nullptr);
+  yd::k_scan_u32<<<1, 1024, 0, st>>>(list_cnt, 0, ct.meta + 3, n_tiles, nullptr);
   yd::k_list_fill<<<n_tiles, yd::kListTile, 0, st>>>(m_ptr, dec, t, ct, arr, n_tiles, list_cnt,
                                                      s->d_list.as<uint2>(), (uint32_t)(slot_b * 4));
   launches += 3;
@@ -761,8 +764,21 @@ uint32_t LaunchStream(yd_sched* s, uint32_t N, size_t slot_b, bool capturing) {
   // ---- data-parallel path: single-class components without self-requests ----------------
   yd::k_rank_assign<<<(N + 255) / 256, 256, 0, st>>>(dp, n_rtiles, t, ct, s->d_rcls.as<uint32_t>(),
                                                      s->d_rrank.as<uint32_t>(), s->d_rank_cnt.as<uint32_t>(), list_cnt,
-                                                     n_tiles, s->d_list.as<uint2>(), arr, s->d_res.as<uint32_t>());
+                                                     n_tiles, s->d_list.as<uint2>(), arr, s->d_comp_mode.as<uint32_t>(),
+                                                     s->d_rq.as<uint32_t>(), s->d_res.as<uint32_t>());
   launches += 1;
+
+  // ---- merge solver: coupled components without self-requests ------------------------------
+  {
+    yd::MergeArgs m{};
+    m.t = t; m.ct = ct; m.sv = arr;
+    m.comp_mode = s->d_comp_mode.as<uint32_t>();
+    m.list_off = list_cnt; m.n_list_tiles = n_tiles; m.list = s->d_list.as<uint2>();
+    m.rank_off = s->d_rank_cnt.as<uint32_t>(); m.n_rank_tiles = n_rtiles;
+    m.rq = s->d_rq.as<uint32_t>(); m.res = s->d_res.as<uint32_t>();
+    yd::k_solve_merge<<<s->n_comps, 32, 0, st>>>(m);
+    launches += 1;
+  }
 
   // ---- sequential decisions for everything else ---------------------------------------------
   yd::StreamArgs a{};
