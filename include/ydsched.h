@@ -198,6 +198,43 @@ void yd_keep_task_alive(yd_sched* s, int64_t now_ns, const uint64_t* task_ids, s
  * only skips itself, as in SchedulerServiceImpl::FreeTask, :307-309). */
 void yd_free_tasks(yd_sched* s, const uint64_t* task_ids, size_t n);
 
+/* ---- the caller's request expansion ---------------------------------------- */
+
+/* Status codes of yadcc/api/scheduler.proto:23-35 that WaitForStartingTask can produce. */
+#define YD_RPC_OK 0u
+#define YD_RPC_NO_QUOTA_AVAILABLE 1001u
+#define YD_RPC_INVALID_ARGUMENT 1004u
+#define YD_RPC_ENVIRONMENT_NOT_AVAILABLE 1006u
+
+/* One WaitForStartingTaskRequest (scheduler.proto:181-201) after token verification,
+ * with the peer IP and the digest already interned. */
+typedef struct yd_rpc_wait {
+  uint32_t env_id;               /* env_desc.compiler_digest */
+  uint32_t min_version;
+  uint32_t requestor_ip;         /* EndpointGetIp(controller->GetRemotePeer()) */
+  uint32_t immediate_reqs;
+  uint32_t prefetch_reqs;
+  uint32_t milliseconds_to_wait; /* only range-checked (<= 10 s); waiting is the caller's business */
+  int64_t next_keep_alive_ns;    /* lease of every grant; must be <= 30 s */
+} yd_rpc_wait;
+
+typedef struct yd_rpc_wait_result {
+  uint32_t status;      /* YD_RPC_* */
+  uint32_t n_grants;    /* grants of this RPC ... */
+  uint32_t first_grant; /* ... stored at grants_out[first_grant .. first_grant + n_grants) */
+  uint32_t reserved;
+} yd_rpc_wait_result;
+
+/* n_rpcs SchedulerServiceImpl::WaitForStartingTask bodies (scheduler_service_impl.cc:
+ * 209-271) executed back to back under the zero-wait discipline: each RPC expands to
+ * `immediate_reqs` then `prefetch_reqs` sequential WaitForStartingNewTask calls with the
+ * reference's stop rules (:234-264) and status mapping (:242-246, :266-270; note that an
+ * unknown environment on a prefetch-only RPC yields NO_QUOTA, not ENVIRONMENT_NOT_AVAILABLE).
+ * All RPCs are solved as ONE batch.  Returns the total number of grants written (<= cap;
+ * cap must be >= the sum of immediate_reqs + prefetch_reqs). */
+size_t yd_wait_for_starting_task_rpcs(yd_sched* s, int64_t now_ns, const yd_rpc_wait* rpcs, size_t n_rpcs,
+                                      yd_rpc_wait_result* results, yd_grant* grants_out, size_t cap);
+
 /* ---- introspection ------------------------------------------------------ */
 
 size_t yd_num_servants(yd_sched* s);

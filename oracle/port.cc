@@ -424,3 +424,4 @@ void* yd_alloc_host(size_t bytes) { return std::malloc(bytes ? bytes : 1); }
 void yd_free_host(void* p) { std::free(p); }
 
 }  // extern "C"
+#include "ydsched_rpc_impl.inc"

@@ -281,3 +281,59 @@ void* yd_alloc_host(size_t bytes) { return std::malloc(bytes ? bytes : 1); }
 void yd_free_host(void* p) { std::free(p); }
 
 }  // extern "C"
+
+// SchedulerServiceImpl::WaitForStartingTask's body (scheduler_service_impl.cc:209-271),
+// loop for loop, over the verbatim TaskDispatcher.  This is the oracle for the batched
+// expansion in include/ydsched_rpc_impl.inc.
+extern "C" size_t yd_wait_for_starting_task_rpcs(yd_sched* s, int64_t now_ns, const yd_rpc_wait* rpcs, size_t n_rpcs,
+                                                 yd_rpc_wait_result* results, yd_grant* grants_out, size_t cap) {
+  using namespace std::chrono_literals;
+  SetNow(now_ns);
+  size_t written = 0;
+  std::unordered_map<std::string, std::uint32_t> pos;
+  auto& sv = yd_oracle_access::Servants(*s->d);
+  for (std::uint32_t i = 0; i != sv.size(); ++i) pos.emplace(sv[i]->personality.observed_location, i);
+  for (size_t r = 0; r != n_rpcs; ++r) {
+    const yd_rpc_wait& q = rpcs[r];
+    results[r] = yd_rpc_wait_result{YD_RPC_OK, 0, static_cast<std::uint32_t>(written), 0};
+    auto max_wait = q.milliseconds_to_wait * 1ms;
+    auto next_keep_alive = std::chrono::nanoseconds(q.next_keep_alive_ns);
+    if (max_wait > 10s || next_keep_alive > 30s) {  // :221-226
+      results[r].status = YD_RPC_INVALID_ARGUMENT;
+      continue;
+    }
+    TaskPersonality task;  // :228-231
+    task.requestor_ip = q.requestor_ip < s->ips.size() ? s->ips[q.requestor_ip] : "";
+    task.min_version = q.min_version;
+    task.env_desc.set_compiler_digest(q.env_id < s->envs.size() ? s->envs[q.env_id] : "<unknown env id>");
+    auto now = yd_shim::g_now;
+    std::uint32_t granted = 0;
+    bool failed_env = false;
+    auto emit = [&](const yadcc::scheduler::TaskAllocation& a) {
+      if (written == cap) std::abort();
+      grants_out[written++] = yd_grant{a.task_id, pos.at(a.servant_location), YD_STATUS_GRANTED};
+      ++granted;
+    };
+    for (std::uint32_t i = 0; i != q.immediate_reqs; ++i) {  // :234-252
+      auto result = s->d->WaitForStartingNewTask(task, next_keep_alive, now /* zero-wait */, false);
+      if (!result) {
+        if (result.error() == WaitStatus::EnvironmentNotFound) { failed_env = true; }
+        break;
+      }
+      emit(*result);
+    }
+    if (failed_env) {  // :242-246 SetFailed(STATUS_ENVIRONMENT_NOT_AVAILABLE); return;
+      results[r].status = YD_RPC_ENVIRONMENT_NOT_AVAILABLE;
+      results[r].n_grants = granted;
+      continue;
+    }
+    for (std::uint32_t i = 0; i != q.prefetch_reqs; ++i) {  // :254-264
+      auto result = s->d->WaitForStartingNewTask(task, next_keep_alive, now, true);
+      if (!result) break;
+      emit(*result);
+    }
+    results[r].n_grants = granted;
+    if (granted == 0) results[r].status = YD_RPC_NO_QUOTA_AVAILABLE;  // :266-270
+  }
+  return written;
+}

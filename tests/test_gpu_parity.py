@@ -217,3 +217,16 @@ def test_merge_solver_coupled_no_self(make_dispatcher, seed):
         results.append(np.stack([st["running_tasks"], st["ever_assigned_tasks"]], 1))
     for a, b in zip(results[:3], results[3:]):
         assert (a == b).all()
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_rpc_expansion_cuda_equals_oracle(make_dispatcher, seed):
+    """yd_wait_for_starting_task_rpcs (the caller's request expansion,
+    scheduler_service_impl.cc:209-271) on the CUDA backend against the oracle."""
+    from rpc_cases import run_rpc_stream
+
+    ref = "ref" if REF_LIB.exists() else "port"
+    a = run_rpc_stream(make_dispatcher("cuda"), seed)
+    b = run_rpc_stream(make_dispatcher(ref), seed)
+    for x, y in zip(a, b):
+        assert x.shape == y.shape and (x == y).all()

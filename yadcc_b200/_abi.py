@@ -39,7 +39,21 @@ SERVANT_STATE_DTYPE = np.dtype(
         ("expires_at_ns", "<i8"),
     ]
 )
-assert REQ_DTYPE.itemsize == 24 and GRANT_DTYPE.itemsize == 16
+# struct yd_rpc_wait (32 B) / yd_rpc_wait_result (16 B)
+RPC_WAIT_DTYPE = np.dtype(
+    [
+        ("env_id", "<u4"),
+        ("min_version", "<u4"),
+        ("requestor_ip", "<u4"),
+        ("immediate_reqs", "<u4"),
+        ("prefetch_reqs", "<u4"),
+        ("milliseconds_to_wait", "<u4"),
+        ("next_keep_alive_ns", "<i8"),
+    ]
+)
+RPC_RESULT_DTYPE = np.dtype([("status", "<u4"), ("n_grants", "<u4"), ("first_grant", "<u4"), ("reserved", "<u4")])
+RPC_OK, RPC_NO_QUOTA_AVAILABLE, RPC_INVALID_ARGUMENT, RPC_ENVIRONMENT_NOT_AVAILABLE = 0, 1001, 1004, 1006
+assert REQ_DTYPE.itemsize == 24 and GRANT_DTYPE.itemsize == 16 and RPC_WAIT_DTYPE.itemsize == 32
 
 
 class yd_config(C.Structure):
@@ -114,6 +128,7 @@ PROTOTYPES = [
     ("yd_wait_for_starting_new_tasks", None, [_P, C.c_int64, _P, C.c_size_t, _P]),
     ("yd_keep_task_alive", None, [_P, C.c_int64, _P, C.c_size_t, C.c_int64, _P]),
     ("yd_free_tasks", None, [_P, _P, C.c_size_t]),
+    ("yd_wait_for_starting_task_rpcs", C.c_size_t, [_P, C.c_int64, _P, C.c_size_t, _P, _P, C.c_size_t]),
     ("yd_num_servants", C.c_size_t, [_P]),
     ("yd_servant_location", C.c_char_p, [_P, C.c_uint32]),
     ("yd_get_servant_state", C.c_size_t, [_P, _P, C.c_size_t]),

@@ -1228,3 +1228,4 @@ void yd_free_host(void* p) {
 }
 
 }  // extern "C"
+#include "ydsched_rpc_impl.inc"

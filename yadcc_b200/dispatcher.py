@@ -207,6 +207,21 @@ class TaskDispatcher:
             return TaskAllocation(int(g["task_id"]), self.servant_location(int(g["servant_index"])))
         return WaitStatus(int(g["status"]))
 
+    def wait_for_starting_task_rpcs(self, rpcs: np.ndarray, now: float = 0.0):
+        """A batch of SchedulerServiceImpl::WaitForStartingTask bodies
+        (scheduler_service_impl.cc:209-271): returns (results, grants) where
+        results[i] = (status, n_grants, first_grant) and grants is a GRANT_DTYPE array."""
+        assert rpcs.dtype == _abi.RPC_WAIT_DTYPE and rpcs.flags.c_contiguous
+        n = rpcs.shape[0]
+        cap = int(rpcs["immediate_reqs"].sum() + rpcs["prefetch_reqs"].sum())
+        results = np.zeros(n, dtype=_abi.RPC_RESULT_DTYPE)
+        grants = np.zeros(max(cap, 1), dtype=GRANT_DTYPE)
+        k = self._lib.yd_wait_for_starting_task_rpcs(self._h, _ns(now), rpcs.ctypes.data, n, results.ctypes.data,
+                                                     grants.ctypes.data, cap)
+        if k == (1 << 64) - 1:
+            raise ValueError("grant buffer too small")
+        return results, grants[:k]
+
     def keep_task_alive(self, task_id: int, new_expires_in: float, *, now: float = 0.0) -> bool:
         return bool(self.keep_tasks_alive([task_id], new_expires_in, now=now)[0])
 
