@@ -46,11 +46,9 @@ class ShardedDispatcher:
         self.device = device  # torch device for the collective (cuda:LOCAL_RANK with NCCL, cpu with gloo)
         self.digest_owner = digest_owner
         self.next_task_id = 0  # global id space
-        # global task id -> local task id for the grants this rank owns: two parallel arrays,
-        # sorted by global id (ids only ever grow), dead entries compacted lazily
-        self._gid = np.zeros(0, dtype=np.uint64)
-        self._lid = np.zeros(0, dtype=np.uint64)
-        self._alive = np.zeros(0, dtype=bool)
+        # global task id -> local task id for the grants this rank owns: one chunk per solve
+        # (global ids, local ids, alive flags), chunks ordered by first global id (ids only grow)
+        self._chunks: list[list[np.ndarray]] = []
         self._owners_cache = None  # (owners array object, mine, mine on the collective's device)
         self.collective_bytes = 0
 
@@ -95,7 +93,7 @@ class ShardedDispatcher:
         # the one exchange step: who was granted, over the whole global queue
         flags = torch.zeros(len(owners), dtype=torch.int32, device=self.device)
         if len(mine):
-            flags[mine_t] = torch.as_tensor(ok.astype(np.int32)).to(self.device, non_blocking=True)
+            flags[mine_t] = torch.as_tensor(ok.view(np.uint8)).to(self.device, non_blocking=True).to(torch.int32)
         if self.world > 1:
             dist.all_reduce(flags, op=dist.ReduceOp.SUM, group=self.group)
             self.collective_bytes += flags.numel() * 4
@@ -104,40 +102,41 @@ class ShardedDispatcher:
         if len(mine):
             before = (csum - flags)[mine_t]  # grants strictly earlier in the global FIFO
             gids = np.uint64(self.next_task_id) + before.cpu().numpy().astype(np.uint64)
-            self._gid = np.concatenate([self._gid, gids[ok]])
-            self._lid = np.concatenate([self._lid, g["task_id"][ok]])
-            self._alive = np.concatenate([self._alive, np.ones(int(ok.sum()), dtype=bool)])
+            if ok.any():
+                self._chunks.append([gids[ok], g["task_id"][ok].copy(), np.ones(int(ok.sum()), dtype=bool)])
             g["task_id"][ok] = gids[ok]
         self.next_task_id += total
         return g
 
-    def _lookup(self, global_ids) -> tuple[np.ndarray, np.ndarray]:
-        """(positions in the map, found mask) for the ids this rank owns and still holds."""
+    def _lookup(self, global_ids):
+        """Yields (chunk, positions in the chunk, positions in `global_ids`) for the ids this
+        rank owns and still holds."""
         ids = np.asarray(global_ids, dtype=np.uint64)
-        pos = np.searchsorted(self._gid, ids)
-        pos_c = np.minimum(pos, max(len(self._gid) - 1, 0))
-        found = (pos < len(self._gid)) & (len(self._gid) > 0)
-        if len(self._gid):
-            found &= (self._gid[pos_c] == ids) & self._alive[pos_c]
-        return pos_c, found
+        if not len(ids) or not self._chunks:
+            return
+        firsts = np.asarray([c[0][0] for c in self._chunks], dtype=np.uint64)
+        which = np.searchsorted(firsts, ids, side="right").astype(np.int64) - 1
+        for ci in np.unique(which[which >= 0]):
+            gid, _, alive = self._chunks[ci]
+            sel = np.nonzero(which == ci)[0]
+            pos = np.searchsorted(gid, ids[sel])
+            pos_c = np.minimum(pos, len(gid) - 1)
+            hit = (pos < len(gid)) & (gid[pos_c] == ids[sel]) & alive[pos_c]
+            if hit.any():
+                yield self._chunks[ci], pos_c[hit], sel[hit]
 
     # -- lease maintenance, routed by global id -------------------------------------
     def free_tasks(self, global_ids) -> None:
-        pos, found = self._lookup(global_ids)
-        if found.any():
-            # np.unique: an id listed twice frees once (FreeTask of an unknown id is a no-op)
-            p = np.unique(pos[found])
-            self.local.free_tasks(self._lid[p])
-            self._alive[p] = False
-            if len(self._alive) > 4096 and self._alive.mean() < 0.5:
-                keep = self._alive
-                self._gid, self._lid, self._alive = self._gid[keep], self._lid[keep], self._alive[keep]
+        for chunk, pos, _ in self._lookup(global_ids):
+            p = np.unique(pos)  # an id listed twice frees once (FreeTask of an unknown id is a no-op)
+            self.local.free_tasks(chunk[1][p])
+            chunk[2][p] = False
+        self._chunks = [c for c in self._chunks if c[2].any()]
 
     def keep_tasks_alive(self, global_ids, new_expires_in: float, *, now: float = 0.0) -> np.ndarray:
         """Statuses for the ids this rank owns (False for ids owned elsewhere; the caller
         ORs the ranks' answers)."""
-        pos, found = self._lookup(global_ids)
-        out = np.zeros(len(pos), dtype=bool)
-        if found.any():
-            out[found] = self.local.keep_tasks_alive(self._lid[pos[found]], new_expires_in, now=now)
+        out = np.zeros(len(np.asarray(global_ids)), dtype=bool)
+        for chunk, pos, where in self._lookup(global_ids):
+            out[where] = self.local.keep_tasks_alive(chunk[1][pos], new_expires_in, now=now)
         return out
