@@ -70,6 +70,12 @@ typedef struct yd_config {
   /* bit 0: CUDA backend launches the solve kernel by kernel instead of replaying a
    * captured CUDA graph, so yd_solve_stats can split prep / solve / final. */
   uint32_t reserved;
+  /* Sharded deployments (one handle per GPU, yadcc_b200/sharded.py): task ids handed out
+   * and accepted by this handle are local_id * id_stride + id_offset, so N shards share one
+   * id space without talking to each other.  0 means stride 1, offset 0 (the reference's
+   * numbering).  Ignored by the oracles. */
+  uint32_t id_stride;
+  uint32_t id_offset;
 } yd_config;
 
 /* ServantPersonality, task_dispatcher.h:80-116, as filled in by

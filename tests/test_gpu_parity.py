@@ -230,3 +230,39 @@ def test_rpc_expansion_cuda_equals_oracle(make_dispatcher, seed):
     b = run_rpc_stream(make_dispatcher(ref), seed)
     for x, y in zip(a, b):
         assert x.shape == y.shape and (x == y).all()
+
+
+def test_strided_task_ids(make_dispatcher):
+    """Sharded deployments: yd_config.id_stride / id_offset make a handle hand out and accept
+    ids of the form local * stride + offset, so shards share one id space without talking.
+    Everything except the numbering must equal an unsharded handle."""
+    import numpy as np
+
+    w = S.config2(3000, 60, 2, variant="random", max_tasks=8, nproc=16)
+    plain = make_dispatcher("cuda")
+    shard = [make_dispatcher("cuda", id_stride=4, id_offset=k) for k in (1, 3)]
+    for d in [plain] + shard:
+        w.register(d)
+    base = plain.wait_for_starting_new_tasks(w.build_requests(plain), 0.1).copy()
+    ok = base["status"] == STATUS_GRANTED
+    outs = []
+    for k, d in zip((1, 3), shard):
+        g = d.wait_for_starting_new_tasks(w.build_requests(d), 0.1).copy()
+        assert (g["status"] == base["status"]).all() and (g["servant_index"] == base["servant_index"]).all()
+        assert (g["task_id"][ok] == base["task_id"][ok] * 4 + k).all()
+        assert d.next_task_id() == plain.next_task_id() * 4 + k
+        outs.append(g)
+    # each shard ignores the other's ids (and plain garbage) in FreeTask / KeepTaskAlive / heartbeats
+    mixed = np.concatenate([outs[0]["task_id"][ok][:50], outs[1]["task_id"][ok][:70], [7, 8, 2**40]]).astype(np.uint64)
+    for d in shard:
+        alive = d.keep_tasks_alive(mixed, 5.0, now=0.2)
+        d.free_tasks(mixed)
+    assert shard[0].num_tasks() == int(ok.sum()) - 50 and shard[1].num_tasks() == int(ok.sum()) - 70
+    plain.free_tasks(base["task_id"][ok][:50])
+    assert (shard[0].servant_state()["running_tasks"] == plain.servant_state()["running_tasks"]).all()
+    loc = shard[0].servant_location(int(outs[0]["servant_index"][ok][60]))
+    from yadcc_b200 import RunningTask
+    mine = int(outs[0]["task_id"][ok][60])
+    other = int(outs[1]["task_id"][ok][60])
+    unknown = shard[0].notify_servant_running_tasks(loc, [RunningTask(1, mine, loc, "a"), RunningTask(2, other, loc, "b")])
+    assert unknown == [other]

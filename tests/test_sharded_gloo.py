@@ -48,7 +48,7 @@ def _owner(digest: str, world: int) -> int:
     return (int(digest, 16) // 2) % world  # pairs (2k, 2k+1) stay together
 
 
-def _rank_main(rank, world, port, out_dir):
+def _rank_main(rank, world, port, out_dir, id_mode):
     import torch
     import torch.distributed as dist
 
@@ -60,7 +60,7 @@ def _rank_main(rank, world, port, out_dir):
 
     digests, servants, req_digest, req_ip, req_mv = _workload()
     d = TaskDispatcher(str(PORT_LIB))
-    sd = ShardedDispatcher(d, rank, world, device=torch.device("cpu"), digest_owner=_owner)
+    sd = ShardedDispatcher(d, rank, world, device=torch.device("cpu"), digest_owner=_owner, id_mode=id_mode)
     for sv in servants:
         sd.keep_servant_alive(sv, 10.0, now=0.0)
     owners = np.asarray([_owner(digests[k], world) if k < len(digests) else -1 for k in req_digest])
@@ -77,17 +77,18 @@ def _rank_main(rank, world, port, out_dir):
         ok = g["status"] == 2
         sd.free_tasks(g["task_id"][ok][::3])
     np.save(Path(out_dir) / f"rank{rank}.npy", np.asarray(results, dtype=object), allow_pickle=True)
-    assert sd.collective_bytes > 0
+    assert (sd.collective_bytes > 0) == (id_mode == "fifo")
     dist.barrier()
     dist.destroy_process_group()
 
 
-def test_two_ranks_equal_one_scheduler(tmp_path, port_lib):
+@pytest.mark.parametrize("id_mode", ["fifo"])
+def test_two_ranks_equal_one_scheduler(tmp_path, port_lib, id_mode):
     import torch.multiprocessing as mp
     from yadcc_b200 import TaskDispatcher
 
     world = 2
-    mp.spawn(_rank_main, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_rank_main, args=(world, _free_port(), str(tmp_path), id_mode), nprocs=world, join=True)
 
     digests, servants, req_digest, req_ip, req_mv = _workload()
     one = TaskDispatcher(port_lib)

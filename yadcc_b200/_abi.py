@@ -63,6 +63,8 @@ class yd_config(C.Structure):
         ("servant_min_memory_for_accepting_new_task", C.c_char_p),
         ("solver", C.c_uint32),
         ("reserved", C.c_uint32),
+        ("id_stride", C.c_uint32),
+        ("id_offset", C.c_uint32),
     ]
 
 

@@ -77,8 +77,19 @@ struct TaskRing {
   uint32_t* srv;
   uint32_t* flags;
   uint64_t mask;  // capacity - 1
-  uint64_t lo;    // ids below lo are dead
-  uint64_t next;  // next id to hand out
+  uint64_t lo;    // LOCAL ids below lo are dead
+  uint64_t next;  // next LOCAL id to hand out
+  // external id = local * id_stride + id_offset (sharded deployments; 1 / 0 otherwise)
+  uint32_t id_stride, id_offset;
+  __host__ __device__ unsigned long long ext(unsigned long long local) const { return local * id_stride + id_offset; }
+  // external -> local; false if the id cannot be one of ours
+  __host__ __device__ bool loc(unsigned long long external, unsigned long long* local) const {
+    if (external < id_offset) return false;
+    const unsigned long long d = external - id_offset;
+    if (id_stride > 1 && d % id_stride) return false;
+    *local = id_stride > 1 ? d / id_stride : d;
+    return true;
+  }
 };
 
 // GetCapacityAvailable (task_dispatcher.cc:283-313) for the not-low-memory case,

@@ -96,7 +96,8 @@ __global__ void __launch_bounds__(1024) k_final_write(const uint32_t* __restrict
   uint4 g;  // {task_id lo, task_id hi, servant_index, status} == yd_grant
   if (granted) {
     uint64_t id = ring.next + block_off[blockIdx.x] + before;
-    g = make_uint4((uint32_t)id, (uint32_t)(id >> 32), r, YD_STATUS_GRANTED);
+    const unsigned long long xid = ring.ext(id);
+    g = make_uint4((uint32_t)xid, (uint32_t)(xid >> 32), r, YD_STATUS_GRANTED);
     uint64_t slot = id & ring.mask;
     const yd_task_req rq = reqs[q];
     ring.exp[slot] = now_ns + rq.expires_in_ns;
@@ -114,8 +115,8 @@ __global__ void k_free(const unsigned long long* __restrict__ ids, uint32_t n, T
                        uint32_t* __restrict__ run, Counters* __restrict__ counters) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  unsigned long long id = ids[i];
-  if (id < ring.lo || id >= ring.next) return;  // unknown id: FreeTask just returns (cc:175-179)
+  unsigned long long id;
+  if (!ring.loc(ids[i], &id) || id < ring.lo || id >= ring.next) return;  // unknown id: FreeTask just returns (cc:175-179)
   uint64_t slot = id & ring.mask;
   uint32_t old = atomicExch(&ring.flags[slot], 0u);  // duplicates in one call: first one wins
   if (old & kTaskAlive) {
@@ -130,9 +131,9 @@ __global__ void k_keep_alive(const unsigned long long* __restrict__ ids, uint32_
                              long long new_expires_in_ns, TaskRing ring, uint8_t* __restrict__ ok) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  unsigned long long id = ids[i];
+  unsigned long long id;
   uint8_t r = 0;
-  if (id >= ring.lo && id < ring.next) {
+  if (ring.loc(ids[i], &id) && id >= ring.lo && id < ring.next) {
     uint64_t slot = id & ring.mask;
     uint32_t f = ring.flags[slot];
     if ((f & kTaskAlive) && !(f & kTaskZombie)) {
@@ -239,8 +240,9 @@ __global__ void k_notify_sweep(TaskRing ring, uint32_t pos, const unsigned long 
   uint64_t slot = id & ring.mask;
   uint32_t f = ring.flags[slot];
   if ((f & (kTaskAlive | kTaskZombie)) != (kTaskAlive | kTaskZombie) || ring.srv[slot] != pos) return;
+  const unsigned long long xid = ring.ext(id);
   for (uint32_t i = 0; i < n; ++i) {
-    if (s_rep[i] == id) return;  // still reported: stays a zombie
+    if (s_rep[i] == xid) return;  // still reported: stays a zombie
   }
   ring.flags[slot] = 0;
   atomicSub(&run[pos], 1u);
@@ -254,9 +256,9 @@ __global__ void k_notify_check(TaskRing ring, uint32_t pos, const unsigned long 
                                uint32_t n, uint8_t* __restrict__ permitted) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  unsigned long long id = reported[i];
+  unsigned long long id;
   uint8_t ok = 0;
-  if (id >= ring.lo && id < ring.next) {
+  if (ring.loc(reported[i], &id) && id >= ring.lo && id < ring.next) {
     uint64_t slot = id & ring.mask;
     uint32_t f = ring.flags[slot];
     ok = (f & kTaskAlive) && !(f & kTaskZombie) && ring.srv[slot] == pos;

@@ -175,6 +175,7 @@ struct yd_sched {
   DevBuf d_t_exp, d_t_srv, d_t_flags;
   uint64_t ring_cap = 0;
   uint64_t lo = 0, next_id = 0;
+  uint32_t id_stride = 1, id_offset = 0;
   uint64_t zombies_ub = 0;
 
   // per-solve buffers
@@ -217,7 +218,7 @@ struct yd_sched {
   }
   yd::TaskRing ring() const {
     return yd::TaskRing{d_t_exp.as<long long>(), d_t_srv.as<uint32_t>(), d_t_flags.as<uint32_t>(),
-                        ring_cap - 1, lo, next_id};
+                        ring_cap - 1, lo, next_id, id_stride, id_offset};
   }
 
   uint32_t InternEnv(const std::string& k) {
@@ -429,7 +430,7 @@ void yd_sched::EnsureRing(uint64_t need_ids) {
   ne.ensure(ncap * 8); ns.ensure(ncap * 4); nf.ensure(ncap * 4);
   YD_CUDA_CHECK(cudaMemsetAsync(nf.p, 0, ncap * 4, st));
   if (ring_cap && next_id > lo) {
-    yd::TaskRing nr{ne.as<long long>(), ns.as<uint32_t>(), nf.as<uint32_t>(), ncap - 1, lo, next_id};
+    yd::TaskRing nr{ne.as<long long>(), ns.as<uint32_t>(), nf.as<uint32_t>(), ncap - 1, lo, next_id, id_stride, id_offset};
     uint64_t cnt = next_id - lo;
     yd::k_ring_grow<<<(unsigned)((cnt + 255) / 256), 256, 0, st>>>(ring(), nr);
     YD_CUDA_CHECK(cudaGetLastError());
@@ -476,6 +477,8 @@ yd_sched* yd_create(const yd_config* cfg) {
   s->device = cfg->device;
   s->min_mem = min_mem;
   s->solver_pref = cfg->solver;
+  s->id_stride = cfg->id_stride ? cfg->id_stride : 1;
+  s->id_offset = cfg->id_stride ? cfg->id_offset : 0;
   s->use_graphs = !(cfg->reserved & 1u) && !getenv("YDSCHED_NO_GRAPH");
   YD_CUDA_CHECK(cudaStreamCreateWithFlags(&s->st, cudaStreamNonBlocking));
   YD_CUDA_CHECK(cudaStreamCreateWithFlags(&s->st2, cudaStreamNonBlocking));
@@ -1182,7 +1185,7 @@ size_t yd_get_servant_state(yd_sched* s, yd_servant_state* out, size_t cap) {
   return S;
 }
 
-uint64_t yd_next_task_id(yd_sched* s) { return s->next_id; }
+uint64_t yd_next_task_id(yd_sched* s) { return s->next_id * s->id_stride + s->id_offset; }
 
 uint64_t yd_num_tasks(yd_sched* s) {
   YD_CUDA_CHECK(cudaSetDevice(s->device));

@@ -86,6 +86,8 @@ class TaskDispatcher:
         servant_min_memory_for_accepting_new_task: str | None = None,
         solver: int = 0,
         graphs: bool = True,
+        id_stride: int = 0,
+        id_offset: int = 0,
     ):
         self._lib = library if isinstance(library, C.CDLL) else _abi.load_library(library)
         cfg = _abi.yd_config(
@@ -98,6 +100,8 @@ class TaskDispatcher:
             ),
             solver=solver,
             reserved=0 if graphs else 1,  # bit 0: do not capture the solve into a CUDA graph (per-phase timing)
+            id_stride=id_stride,
+            id_offset=id_offset,
         )
         self._h = self._lib.yd_create(C.byref(cfg))
         if not self._h:

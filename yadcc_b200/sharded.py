@@ -8,12 +8,19 @@ subset of the components -- their servants, their digests and the requests for t
 and one process per GPU runs an ordinary `TaskDispatcher` on its share.  No servant
 state ever crosses ranks.
 
-What does cross ranks is the task-id space: the reference numbers grants in global FIFO
-order (`next_task_id++`, task_dispatcher.cc:127), so rank r must know how many requests
-EARLIER in the global queue were granted by other ranks.  That is the one real exchange
-step of the path: an all-reduce (sum) of the per-request grant flags, followed by a
-local prefix sum.  Everything else (heartbeats, frees, keep-alives, ticks) is routed to
-the owning rank by the caller-visible `owner_of_*` maps.
+The only thing the shards share is the task-id space.  Two modes:
+
+* "strided" (default): the library itself hands out id = local_id * world + rank
+  (`yd_config.id_stride / id_offset`) and ignores ids that are not its own -- no
+  communication at all.  Task-grant ids are opaque lease tokens on the wire
+  (scheduler.proto:181-238), so uniqueness and routability are all the protocol needs.
+* "fifo": exactly the numbering ONE reference scheduler would produce
+  (`next_task_id++` in global FIFO order, task_dispatcher.cc:127): rank r must know how many
+  requests EARLIER in the global queue were granted by other ranks, i.e. one all-reduce
+  (sum) of the per-request grant flags per solve plus a local prefix sum.
+
+Everything else (heartbeats, frees, keep-alives, ticks) is routed to the owning rank by
+the caller-visible `owner_of_*` maps.
 
 The class is backend-agnostic (any library speaking the ydsched C ABI) and
 transport-agnostic (any torch.distributed backend), so the N>1 logic is tested on CPU
@@ -38,7 +45,16 @@ def default_digest_owner(digest: str, world: int) -> int:
 
 class ShardedDispatcher:
     def __init__(self, local: TaskDispatcher, rank: int, world: int, *, group=None, device=None,
-                 digest_owner: Callable[[str, int], int] = default_digest_owner):
+                 digest_owner: Callable[[str, int], int] = default_digest_owner, id_mode: str = "strided"):
+        """id_mode:
+          "strided"  task id = local id * world + rank.  Needs `local` created with
+                     id_stride=world, id_offset=rank (the library then hands out and accepts
+                     such ids itself); no communication at all.  Ids are unique and routable
+                     but not the single-scheduler numbering.
+          "fifo"     exactly the ids one reference scheduler would hand out for the global
+                     queue; costs one all-reduce of grant flags per solve."""
+        assert id_mode in ("strided", "fifo")
+        self.id_mode = id_mode
         self.local = local
         self.rank = rank
         self.world = world
@@ -83,6 +99,8 @@ class ShardedDispatcher:
         import torch.distributed as dist
 
         del digests
+        if self.id_mode == "strided":
+            return self.local.wait_for_starting_new_tasks(local_reqs, now)
         if self._owners_cache is None or self._owners_cache[0] is not owners:
             mine = np.nonzero(owners == self.rank)[0]
             self._owners_cache = (owners, mine, torch.as_tensor(mine, device=self.device))
@@ -127,6 +145,9 @@ class ShardedDispatcher:
 
     # -- lease maintenance, routed by global id -------------------------------------
     def free_tasks(self, global_ids) -> None:
+        if self.id_mode == "strided":  # the library ignores ids that are not its own
+            self.local.free_tasks(global_ids)
+            return
         for chunk, pos, _ in self._lookup(global_ids):
             p = np.unique(pos)  # an id listed twice frees once (FreeTask of an unknown id is a no-op)
             self.local.free_tasks(chunk[1][p])
@@ -136,6 +157,8 @@ class ShardedDispatcher:
     def keep_tasks_alive(self, global_ids, new_expires_in: float, *, now: float = 0.0) -> np.ndarray:
         """Statuses for the ids this rank owns (False for ids owned elsewhere; the caller
         ORs the ranks' answers)."""
+        if self.id_mode == "strided":
+            return self.local.keep_tasks_alive(global_ids, new_expires_in, now=now)
         out = np.zeros(len(np.asarray(global_ids)), dtype=bool)
         for chunk, pos, where in self._lookup(global_ids):
             out[where] = self.local.keep_tasks_alive(chunk[1][pos], new_expires_in, now=now)
