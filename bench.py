@@ -27,9 +27,10 @@ writing a 256 MiB buffer.
 N > 1 (torchrun): ONE logical scheduler whose digest<->servant components are sharded
 over the ranks (the sharding the reference's authors propose at
 task_dispatcher.h:286-288): rank r owns 8 digests / 2 k servants / 100 k requests of
-the global queue.  Decisions need no collective; the global FIFO task-id space needs
-one NCCL all-reduce of the per-request grant flags per solve (yadcc_b200/sharded.py).
-Weak scaling.
+the global queue.  Decisions need no collective.  Task ids are local*world+rank by default
+(opaque lease tokens: unique and routable, no exchange); `--ids fifo` reproduces the
+single-scheduler numbering with one NCCL all-reduce of the per-request grant flags per
+solve (yadcc_b200/sharded.py).  Weak scaling.
 """
 from __future__ import annotations
 
@@ -209,13 +210,16 @@ def run_ours(args):
     # One logical scheduler: rank r owns the components of workload r (its 8 digests, 2 k
     # servants, 100 k requests); global request i*world + r is rank r's i-th request.
     w = build_workload(args.workload, rank)
-    d = TaskDispatcher(device=local, solver=args.solver)
+    fifo_ids = world > 1 and args.ids == "fifo"
+    d = TaskDispatcher(device=local, solver=args.solver, id_stride=0 if (world == 1 or fifo_ids) else world,
+                       id_offset=0 if (world == 1 or fifo_ids) else rank)
     assert d.backend == "cuda-sm100a"
     owner_map = {}
     for r in range(world):
         for dg in build_workload(args.workload, r).digests:
             owner_map[dg] = r
-    sd = ShardedDispatcher(d, rank, world, device=dev, digest_owner=lambda dg, _w: owner_map[dg])
+    sd = ShardedDispatcher(d, rank, world, device=dev, digest_owner=lambda dg, _w: owner_map[dg],
+                           id_mode="fifo" if fifo_ids else "strided")
     for sv in w.servants:
         sd.keep_servant_alive(sv, 3600.0, now=0.0)
     src = w.build_requests(d)
@@ -331,7 +335,8 @@ def run_ours(args):
             "config": {"workload": f"{args.workload}: {w.meta} per GPU", "decisions_per_step_per_gpu": n,
                        "granted_per_step_per_gpu": granted,
                        "parallelism": f"digest<->servant components sharded over {world} rank(s)"
-                                      + ("; one all-reduce of grant flags per solve for global task ids" if world > 1 else ""),
+                                      + ("; task ids = local*world+rank, no collective" if world > 1 and not fifo_ids else "")
+                                      + ("; one all-reduce of grant flags per solve for single-scheduler task ids" if fifo_ids else ""),
                        "l2": "flushed between steps (256 MiB write)", "solver": solver_name,
                        "between_steps_untimed": "FreeTask of the previous grants + OnExpirationTimer tick"},
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": tot_e2e / K,
@@ -375,6 +380,8 @@ def main():
     ap.add_argument("--workload", default="cfg2-mod")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--solver", type=int, default=0, help="0 auto, 1 row-scan, 2 slot-stream")
+    ap.add_argument("--ids", default="strided", choices=["strided", "fifo"],
+                    help="N>1 task-id space: strided (no exchange) or fifo (single-scheduler numbering, one all-reduce per solve)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

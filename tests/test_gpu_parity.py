@@ -238,7 +238,7 @@ def test_strided_task_ids(make_dispatcher):
     Everything except the numbering must equal an unsharded handle."""
     import numpy as np
 
-    w = S.config2(3000, 60, 2, variant="random", max_tasks=8, nproc=16)
+    w = S.config2(3000, 60, 4, variant="random", max_tasks=8, nproc=16)
     plain = make_dispatcher("cuda")
     shard = [make_dispatcher("cuda", id_stride=4, id_offset=k) for k in (1, 3)]
     for d in [plain] + shard:
