@@ -67,6 +67,8 @@ def build_workload(name: str, rank: int):
         return S.config_self(seed=seed)
     if name == "cfg3":
         return S.config3(1_000_000, 4000, 8, seed=seed)
+    if name == "cfg5":  # BASELINE configs[4] shape on ONE GPU: 10 M x 8 k
+        return S.config5(10_000_000, 8000, 8, seed=seed)
     raise SystemExit(f"unknown workload {name}")
 
 

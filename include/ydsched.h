@@ -241,6 +241,30 @@ typedef struct yd_rpc_wait_result {
 size_t yd_wait_for_starting_task_rpcs(yd_sched* s, int64_t now_ns, const yd_rpc_wait* rpcs, size_t n_rpcs,
                                       yd_rpc_wait_result* results, yd_grant* grants_out, size_t cap);
 
+/* ---- compilation-cache bloom pre-filter ------------------- */
+
+/* flare::experimental::SaltedBloomFilter (flare/base/experimental/bloom_filter.h:130,
+ * :178-210, :249-305; hash = XXH64(s, len, 0), bloom_filter.cc:21-23): key k is tested /
+ * added through num_hashes probes h_i = XXH64(le32(i) || key), bit = h_i & (bits - 1),
+ * stored as bytes[bit / 8] & (1 << bit % 8).  yadcc's cache server builds it with
+ * 27 584 639 -> 2^25 bits and 10 hashes (yadcc/cache/bloom_filter_generator.h:65-68) and the
+ * delegate daemon consults it before asking the scheduler for a grant
+ * (yadcc/daemon/local/distributed_cache_reader.cc:70-77).  One filter per handle.
+ *
+ * Keys are passed as n fixed-length records: key i = keys + i * stride, key_len bytes. */
+
+/* BloomFilter(m, k): empty filter of max(8, next_pow2(m)) bits.  Returns 0 on success. */
+int yd_bloom_reset(yd_sched* s, uint64_t size_in_bits, uint32_t num_hashes);
+/* BloomFilter(existing_filter, k): n_bytes * 8 must be a power of two. */
+int yd_bloom_load(yd_sched* s, const uint8_t* bytes, size_t n_bytes, uint32_t num_hashes);
+/* BloomFilter::Add for n keys. */
+void yd_bloom_add(yd_sched* s, const char* keys, size_t n, size_t key_len, size_t stride);
+/* BloomFilter::PossiblyContains for n keys; out[i] = 0 / 1. */
+void yd_bloom_possibly_contains(yd_sched* s, const char* keys, size_t n, size_t key_len, size_t stride,
+                                uint8_t* out);
+/* BloomFilter::GetBytes: returns the filter size in bytes; copies at most cap bytes. */
+size_t yd_bloom_get_bytes(yd_sched* s, uint8_t* out, size_t cap);
+
 /* ---- introspection ------------------------------------------------------ */
 
 size_t yd_num_servants(yd_sched* s);

@@ -425,3 +425,93 @@ void yd_free_host(void* p) { std::free(p); }
 
 }  // extern "C"
 #include "ydsched_rpc_impl.inc"
+
+// ---- bloom pre-filter: restatement of flare's SaltedBloomFilter over XXH64 --------------
+// XXH64 is restated from the published xxHash specification (Cyan4973/xxHash, doc/
+// xxhash_spec.md; the reference vendors xxHash 0.8.0 under thirdparty/xxhash and calls
+// XXH64(data, len, seed = 0) at flare/base/experimental/bloom_filter.cc:21-23).
+namespace {
+constexpr std::uint64_t kP1 = 11400714785074694791ull, kP2 = 14029467366897019727ull,
+                        kP3 = 1609587929392839161ull, kP4 = 9650029242287828579ull,
+                        kP5 = 2870177450012600261ull;
+inline std::uint64_t Rotl(std::uint64_t x, int r) { return (x << r) | (x >> (64 - r)); }
+inline std::uint64_t Rd64(const unsigned char* p) { std::uint64_t v; std::memcpy(&v, p, 8); return v; }
+inline std::uint32_t Rd32(const unsigned char* p) { std::uint32_t v; std::memcpy(&v, p, 4); return v; }
+inline std::uint64_t Round(std::uint64_t acc, std::uint64_t in) { return Rotl(acc + in * kP2, 31) * kP1; }
+inline std::uint64_t Merge(std::uint64_t h, std::uint64_t v) { return (h ^ Round(0, v)) * kP1 + kP4; }
+
+std::uint64_t Xxh64(const unsigned char* p, std::size_t len, std::uint64_t seed) {
+  const unsigned char* end = p + len;
+  std::uint64_t h;
+  if (len >= 32) {
+    std::uint64_t v1 = seed + kP1 + kP2, v2 = seed + kP2, v3 = seed, v4 = seed - kP1;
+    do {
+      v1 = Round(v1, Rd64(p)); v2 = Round(v2, Rd64(p + 8));
+      v3 = Round(v3, Rd64(p + 16)); v4 = Round(v4, Rd64(p + 24));
+      p += 32;
+    } while (p + 32 <= end);
+    h = Rotl(v1, 1) + Rotl(v2, 7) + Rotl(v3, 12) + Rotl(v4, 18);
+    h = Merge(h, v1); h = Merge(h, v2); h = Merge(h, v3); h = Merge(h, v4);
+  } else {
+    h = seed + kP5;
+  }
+  h += len;
+  while (p + 8 <= end) { h = Rotl(h ^ Round(0, Rd64(p)), 27) * kP1 + kP4; p += 8; }
+  if (p + 4 <= end) { h = Rotl(h ^ (std::uint64_t(Rd32(p)) * kP1), 23) * kP2 + kP3; p += 4; }
+  while (p < end) { h = Rotl(h ^ (*p * kP5), 11) * kP1; ++p; }
+  h ^= h >> 33; h *= kP2; h ^= h >> 29; h *= kP3; h ^= h >> 32;
+  return h;
+}
+
+struct Bloom {  // flare/base/experimental/bloom_filter.h:72-128
+  std::uint32_t num_hashes = 0;
+  std::uint64_t mask = 0;
+  std::vector<unsigned char> bytes;
+  // SaltedHashGenerator, :178-210: hash i = XXH64(le32(i) || key)
+  template <class F> bool ForEachHash(const char* key, std::size_t len, F&& f) const {
+    std::vector<unsigned char> buf(len + 4);
+    std::memcpy(buf.data() + 4, key, len);
+    for (std::uint32_t i = 0; i != num_hashes; ++i) {
+      std::memcpy(buf.data(), &i, 4);
+      if (!f(Xxh64(buf.data(), buf.size(), 0))) return false;
+    }
+    return true;
+  }
+};
+std::unordered_map<yd_sched*, Bloom> g_blooms;
+}  // namespace
+
+extern "C" int yd_bloom_reset(yd_sched* s, uint64_t size_in_bits, uint32_t num_hashes) {
+  if (size_in_bits == 0 || size_in_bits > (1ull << 30) || num_hashes == 0) return 1;
+  std::uint64_t bits = 8;  // max(8, GetNextPowerOfTwo(m)), :214-219,:294-297
+  while (bits < size_in_bits) bits <<= 1;
+  Bloom& b = g_blooms[s];
+  b.num_hashes = num_hashes; b.mask = bits - 1; b.bytes.assign(bits / 8, 0);
+  return 0;
+}
+extern "C" int yd_bloom_load(yd_sched* s, const uint8_t* bytes, size_t n_bytes, uint32_t num_hashes) {
+  if (n_bytes == 0 || ((n_bytes * 8) & (n_bytes * 8 - 1)) || num_hashes == 0) return 1;  // :225-235
+  Bloom& b = g_blooms[s];
+  b.num_hashes = num_hashes; b.mask = n_bytes * 8 - 1; b.bytes.assign(bytes, bytes + n_bytes);
+  return 0;
+}
+extern "C" void yd_bloom_add(yd_sched* s, const char* keys, size_t n, size_t key_len, size_t stride) {
+  Bloom& b = g_blooms.at(s);
+  for (size_t i = 0; i != n; ++i) {
+    b.ForEachHash(keys + i * stride, key_len, [&](std::uint64_t h) {  // :249-254, SetBit :299-303
+      std::uint64_t at = h & b.mask; b.bytes[at / 8] |= static_cast<unsigned char>(1u << (at % 8)); return true; });
+  }
+}
+extern "C" void yd_bloom_possibly_contains(yd_sched* s, const char* keys, size_t n, size_t key_len, size_t stride,
+                                           uint8_t* out) {
+  Bloom& b = g_blooms.at(s);
+  for (size_t i = 0; i != n; ++i) {
+    out[i] = b.ForEachHash(keys + i * stride, key_len, [&](std::uint64_t h) {  // :256-261, GetBit :305-309
+      std::uint64_t at = h & b.mask; return (b.bytes[at / 8] & (1u << (at % 8))) != 0; });
+  }
+}
+extern "C" size_t yd_bloom_get_bytes(yd_sched* s, uint8_t* out, size_t cap) {
+  Bloom& b = g_blooms.at(s);
+  if (out) std::memcpy(out, b.bytes.data(), std::min(cap, b.bytes.size()));
+  return b.bytes.size();
+}

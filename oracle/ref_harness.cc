@@ -337,3 +337,36 @@ extern "C" size_t yd_wait_for_starting_task_rpcs(yd_sched* s, int64_t now_ns, co
   }
   return written;
 }
+
+// ---- bloom pre-filter: flare's own SaltedBloomFilter + the vendored xxHash -----------
+#include "flare/base/experimental/bloom_filter.h"
+
+namespace {
+std::unordered_map<yd_sched*, std::unique_ptr<flare::experimental::SaltedBloomFilter>> g_blooms;
+}
+
+extern "C" int yd_bloom_reset(yd_sched* s, uint64_t size_in_bits, uint32_t num_hashes) {
+  if (size_in_bits == 0 || size_in_bits > (1ull << 30) || num_hashes == 0) return 1;
+  g_blooms[s] = std::make_unique<flare::experimental::SaltedBloomFilter>(size_in_bits, num_hashes);
+  return 0;
+}
+extern "C" int yd_bloom_load(yd_sched* s, const uint8_t* bytes, size_t n_bytes, uint32_t num_hashes) {
+  if (n_bytes == 0 || ((n_bytes * 8) & (n_bytes * 8 - 1)) || num_hashes == 0) return 1;  // the ctor FLARE_CHECKs this
+  g_blooms[s] = std::make_unique<flare::experimental::SaltedBloomFilter>(
+      std::string_view(reinterpret_cast<const char*>(bytes), n_bytes), num_hashes);
+  return 0;
+}
+extern "C" void yd_bloom_add(yd_sched* s, const char* keys, size_t n, size_t key_len, size_t stride) {
+  auto& f = *g_blooms.at(s);
+  for (size_t i = 0; i != n; ++i) f.Add(std::string_view(keys + i * stride, key_len));
+}
+extern "C" void yd_bloom_possibly_contains(yd_sched* s, const char* keys, size_t n, size_t key_len, size_t stride,
+                                           uint8_t* out) {
+  auto& f = *g_blooms.at(s);
+  for (size_t i = 0; i != n; ++i) out[i] = f.PossiblyContains(std::string_view(keys + i * stride, key_len));
+}
+extern "C" size_t yd_bloom_get_bytes(yd_sched* s, uint8_t* out, size_t cap) {
+  auto b = g_blooms.at(s)->GetBytes();
+  if (out) std::memcpy(out, b.data(), std::min(cap, b.size()));
+  return b.size();
+}

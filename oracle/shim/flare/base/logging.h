@@ -5,6 +5,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 namespace yd_shim {
 [[noreturn]] inline void CheckFailed(const char* expr, const char* file, int line) {
   std::fprintf(stderr, "FLARE_CHECK failed: %s  (%s:%d)\n", expr, file, line);

@@ -266,3 +266,46 @@ def test_strided_task_ids(make_dispatcher):
     other = int(outs[1]["task_id"][ok][60])
     unknown = shard[0].notify_servant_running_tasks(loc, [RunningTask(1, mine, loc, "a"), RunningTask(2, other, loc, "b")])
     assert unknown == [other]
+
+
+@pytest.mark.parametrize("seed", range(2))
+def test_bloom_prefilter_cuda_equals_oracle(make_dispatcher, seed):
+    """flare's SaltedBloomFilter (10 x XXH64(salt || key), 2^25 bits) on
+    the GPU: identical filter bytes after Add, identical lookups (false positives included),
+    all key lengths, tiny geometries, imported filters."""
+    from bloom_cases import run_bloom_suite
+
+    ref = "ref" if REF_LIB.exists() else "port"
+    a = run_bloom_suite(make_dispatcher("cuda"), seed)
+    b = run_bloom_suite(make_dispatcher(ref), seed)
+    assert len(a) == len(b)
+    for k, (x, y) in enumerate(zip(a, b)):
+        assert x.shape == y.shape and (x == y).all(), k
+
+
+def test_cfg4_trace_with_bloom_prefilter(make_dispatcher):
+    """BASELINE configs[3]: 100 k requests replaying 6124 TU keys, cache bloom filter on.
+    Requests whose cache key may be in the cache are dropped before the solver (the delegate
+    daemon does this, distributed_cache_reader.cc:70-77); the rest is solved as config 2."""
+    import numpy as np
+    from bloom_cases import tu_keys
+
+    keys = tu_keys(6124)
+    rng = np.random.default_rng(4)
+    cached = [k for k, m in zip(keys, rng.random(len(keys)) < 0.3) if m]
+    n = 100_000
+    trace = [keys[i % len(keys)] for i in range(n)]
+    results = []
+    for kind in ("cuda", "port"):
+        d = make_dispatcher(kind)
+        w = S.config2(n, 2000, 8, variant="mod")
+        w.register(d)
+        d.bloom_reset()
+        d.bloom_add(cached)
+        hit = d.bloom_possibly_contains(trace)
+        reqs = w.build_requests(d)[~hit]
+        g = d.wait_for_starting_new_tasks(reqs, 0.5)
+        results.append((hit.copy(), g.copy()))
+    assert (results[0][0] == results[1][0]).all()
+    assert (results[0][1] == results[1][1]).all()
+    assert 0.25 < results[0][0].mean() < 0.35

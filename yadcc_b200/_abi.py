@@ -131,6 +131,11 @@ PROTOTYPES = [
     ("yd_keep_task_alive", None, [_P, C.c_int64, _P, C.c_size_t, C.c_int64, _P]),
     ("yd_free_tasks", None, [_P, _P, C.c_size_t]),
     ("yd_wait_for_starting_task_rpcs", C.c_size_t, [_P, C.c_int64, _P, C.c_size_t, _P, _P, C.c_size_t]),
+    ("yd_bloom_reset", C.c_int, [_P, C.c_uint64, C.c_uint32]),
+    ("yd_bloom_load", C.c_int, [_P, _P, C.c_size_t, C.c_uint32]),
+    ("yd_bloom_add", None, [_P, _P, C.c_size_t, C.c_size_t, C.c_size_t]),
+    ("yd_bloom_possibly_contains", None, [_P, _P, C.c_size_t, C.c_size_t, C.c_size_t, _P]),
+    ("yd_bloom_get_bytes", C.c_size_t, [_P, _P, C.c_size_t]),
     ("yd_num_servants", C.c_size_t, [_P]),
     ("yd_servant_location", C.c_char_p, [_P, C.c_uint32]),
     ("yd_get_servant_state", C.c_size_t, [_P, _P, C.c_size_t]),

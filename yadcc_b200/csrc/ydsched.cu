@@ -29,6 +29,7 @@
 #include "solve_stream.cuh"
 #include "parallel.cuh"
 #include "solve_merge.cuh"
+#include "bloom.cuh"
 #include "tasks.cuh"
 
 namespace {
@@ -206,6 +207,11 @@ struct yd_sched {
   bool use_graphs = true;
   DevBuf d_dyn;
   PinBuf h_dyn, h_meta;
+
+  // compilation-cache bloom pre-filter
+  DevBuf d_bloom, d_bloom_keys, d_bloom_out;
+  uint64_t bloom_bits = 0;
+  uint32_t bloom_hashes = 0;
 
   cudaEvent_t ev[6] = {};
   yd_solve_stats stats{};
@@ -511,7 +517,8 @@ void yd_destroy(yd_sched* s) {
                     &s->d_t_flags, &s->d_reqs, &s->d_res, &s->d_out, &s->d_blk, &s->d_row_off, &s->d_row_len,
                     &s->d_codes, &s->d_ids, &s->d_ok, &s->d_counters, &s->d_sv_env_off, &s->d_sv_envs,
                     &s->d_comp_mode, &s->d_slot_owner, &s->d_sort_k[0], &s->d_sort_k[1], &s->d_sort_v[0],
-                    &s->d_sort_v[1], &s->d_zero, &s->d_list, &s->d_rcls, &s->d_rrank, &s->d_rank_cnt, &s->d_rq}) {
+                    &s->d_sort_v[1], &s->d_zero, &s->d_list, &s->d_rcls, &s->d_rrank, &s->d_rank_cnt, &s->d_rq, &s->d_bloom,
+                    &s->d_bloom_keys, &s->d_bloom_out}) {
     b->release();
   }
   for (auto& g : s->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
@@ -1232,3 +1239,76 @@ void yd_free_host(void* p) {
 
 }  // extern "C"
 #include "ydsched_rpc_impl.inc"
+
+// ---- compilation-cache bloom pre-filter (bloom.cuh) ------------------------------------------
+extern "C" {
+
+int yd_bloom_reset(yd_sched* s, uint64_t size_in_bits, uint32_t num_hashes) {
+  if (size_in_bits == 0 || size_in_bits > (1ull << 30) || num_hashes == 0) return 1;
+  uint64_t bits = 8;  // max(8, next_pow2(m)) (bloom_filter.h:214-219)
+  while (bits < size_in_bits) bits <<= 1;
+  YD_CUDA_CHECK(cudaSetDevice(s->device));
+  const size_t alloc = std::max<size_t>(bits / 8, 4);  // the kernels address the table as le32 words
+  s->d_bloom.ensure(alloc);
+  YD_CUDA_CHECK(cudaMemsetAsync(s->d_bloom.p, 0, alloc, s->st));
+  s->bloom_bits = bits;
+  s->bloom_hashes = num_hashes;
+  return 0;
+}
+
+int yd_bloom_load(yd_sched* s, const uint8_t* bytes, size_t n_bytes, uint32_t num_hashes) {
+  if (n_bytes == 0 || ((n_bytes * 8) & (n_bytes * 8 - 1)) || num_hashes == 0) return 1;
+  YD_CUDA_CHECK(cudaSetDevice(s->device));
+  s->d_bloom.ensure(std::max<size_t>(n_bytes, 4));
+  YD_CUDA_CHECK(cudaMemsetAsync(s->d_bloom.p, 0, 4, s->st));
+  YD_CUDA_CHECK(cudaMemcpyAsync(s->d_bloom.p, bytes, n_bytes, cudaMemcpyHostToDevice, s->st));
+  YD_CUDA_CHECK(cudaStreamSynchronize(s->st));
+  s->bloom_bits = n_bytes * 8;
+  s->bloom_hashes = num_hashes;
+  return 0;
+}
+
+static void BloomRun(yd_sched* s, const char* keys, size_t n, size_t key_len, size_t stride, uint8_t* out) {
+  if (!s->bloom_bits) { fprintf(stderr, "ydsched: bloom filter used before yd_bloom_reset / yd_bloom_load\n"); abort(); }
+  if (key_len > yd::kBloomMaxKey) { fprintf(stderr, "ydsched: bloom keys longer than %d bytes\n", yd::kBloomMaxKey); abort(); }
+  if (n == 0) return;
+  YD_CUDA_CHECK(cudaSetDevice(s->device));
+  const size_t span = (n - 1) * stride + key_len;
+  s->d_bloom_keys.ensure(span ? span : 1);
+  YD_CUDA_CHECK(cudaMemcpyAsync(s->d_bloom_keys.p, keys, span, cudaMemcpyHostToDevice, s->st));
+  const unsigned grid = (unsigned)((n + 127) / 128);
+  if (out) {
+    s->d_bloom_out.ensure(n);
+    yd::k_bloom<false><<<grid, 128, 0, s->st>>>(s->d_bloom_keys.as<unsigned char>(), (uint32_t)n, (uint32_t)key_len, stride,
+                                                s->bloom_hashes, s->bloom_bits - 1, s->d_bloom.as<uint32_t>(),
+                                                s->d_bloom_out.as<uint8_t>());
+    YD_CUDA_CHECK(cudaGetLastError());
+    YD_CUDA_CHECK(cudaMemcpyAsync(out, s->d_bloom_out.p, n, cudaMemcpyDeviceToHost, s->st));
+  } else {
+    yd::k_bloom<true><<<grid, 128, 0, s->st>>>(s->d_bloom_keys.as<unsigned char>(), (uint32_t)n, (uint32_t)key_len, stride,
+                                               s->bloom_hashes, s->bloom_bits - 1, s->d_bloom.as<uint32_t>(), nullptr);
+    YD_CUDA_CHECK(cudaGetLastError());
+  }
+  YD_CUDA_CHECK(cudaStreamSynchronize(s->st));
+}
+
+void yd_bloom_add(yd_sched* s, const char* keys, size_t n, size_t key_len, size_t stride) {
+  BloomRun(s, keys, n, key_len, stride, nullptr);
+}
+
+void yd_bloom_possibly_contains(yd_sched* s, const char* keys, size_t n, size_t key_len, size_t stride, uint8_t* out) {
+  if (!out) return;
+  BloomRun(s, keys, n, key_len, stride, out);
+}
+
+size_t yd_bloom_get_bytes(yd_sched* s, uint8_t* out, size_t cap) {
+  const size_t nbytes = s->bloom_bits / 8;
+  if (out && cap && nbytes) {
+    YD_CUDA_CHECK(cudaSetDevice(s->device));
+    YD_CUDA_CHECK(cudaMemcpyAsync(out, s->d_bloom.p, std::min(cap, nbytes), cudaMemcpyDeviceToHost, s->st));
+    YD_CUDA_CHECK(cudaStreamSynchronize(s->st));
+  }
+  return nbytes;
+}
+
+}  // extern "C"

@@ -292,6 +292,47 @@ class TaskDispatcher:
     def on_expiration_timer(self, *, now: float) -> None:
         self._lib.yd_on_expiration_timer(self._h, _ns(now))
 
+    # -- compilation-cache bloom pre-filter (flare SaltedBloomFilter) ------------
+    @staticmethod
+    def _key_matrix(keys) -> np.ndarray:
+        """Fixed-length keys as an (n, key_len) uint8 matrix."""
+        if isinstance(keys, np.ndarray) and keys.dtype == np.uint8 and keys.ndim == 2:
+            return np.ascontiguousarray(keys)
+        b = [k.encode() if isinstance(k, str) else bytes(k) for k in keys]
+        n = len(b)
+        ln = len(b[0]) if n else 0
+        assert all(len(x) == ln for x in b), "keys of one call must have the same length"
+        return np.frombuffer(b"".join(b), dtype=np.uint8).reshape(n, ln).copy()
+
+    def bloom_reset(self, size_in_bits: int = 27584639, num_hashes: int = 10) -> None:
+        """Defaults: yadcc/cache/bloom_filter_generator.h:65-68."""
+        if self._lib.yd_bloom_reset(self._h, size_in_bits, num_hashes) != 0:
+            raise ValueError("bad bloom filter geometry")
+
+    def bloom_load(self, data: bytes, num_hashes: int = 10) -> None:
+        buf = np.frombuffer(data, dtype=np.uint8)
+        if self._lib.yd_bloom_load(self._h, buf.ctypes.data, len(buf), num_hashes) != 0:
+            raise ValueError("bloom filter size must be a power of two")
+
+    def bloom_add(self, keys) -> None:
+        m = self._key_matrix(keys)
+        if len(m):
+            self._lib.yd_bloom_add(self._h, m.ctypes.data, m.shape[0], m.shape[1], m.strides[0])
+
+    def bloom_possibly_contains(self, keys) -> np.ndarray:
+        m = self._key_matrix(keys)
+        out = np.zeros(m.shape[0], dtype=np.uint8)
+        if len(m):
+            self._lib.yd_bloom_possibly_contains(self._h, m.ctypes.data, m.shape[0], m.shape[1], m.strides[0],
+                                                 out.ctypes.data)
+        return out.astype(bool)
+
+    def bloom_bytes(self) -> bytes:
+        n = self._lib.yd_bloom_get_bytes(self._h, None, 0)
+        out = np.zeros(n, dtype=np.uint8)
+        self._lib.yd_bloom_get_bytes(self._h, out.ctypes.data, n)
+        return out.tobytes()
+
     # -- introspection -----------------------------------------------------
     def num_servants(self) -> int:
         return int(self._lib.yd_num_servants(self._h))
