@@ -266,27 +266,41 @@ __device__ __forceinline__ bool decode_slot(const SlotDecode& d, const TopoView&
   return comp != kNone;
 }
 
+// Block-wide number of threads with `in` set, via the same ballot + per-warp counters the
+// fill kernel ranks with (so the two kernels cannot disagree).  Two barriers per call.
+__device__ __forceinline__ uint32_t list_block_count(bool in, uint32_t* warp_cnt, uint32_t lane, uint32_t warp) {
+  const uint32_t bal = __ballot_sync(0xffffffffu, in);
+  __syncthreads();  // warp_cnt of the previous call has been consumed
+  if (lane == 0) warp_cnt[warp] = __popc(bal);
+  __syncthreads();
+  uint32_t total = 0;
+  if (warp == 0) total = __reduce_add_sync(0xffffffffu, warp_cnt[lane]);
+  return total;  // valid in warp 0
+}
+
 __global__ void __launch_bounds__(kListTile) k_list_count(const unsigned long long* __restrict__ m_ptr, SlotDecode d,
                                                           TopoView t, ClassTable ct, ServantArrays sv,
                                                           uint32_t n_tiles, uint32_t* __restrict__ counts) {
+  __shared__ uint32_t warp_cnt[32];
   const uint32_t ncls = min(ct.meta[0], ct.cls_bound);
+  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   uint32_t pos, r, comp;
-  const bool live = decode_slot(d, t, blockIdx.x * kListTile + threadIdx.x, (uint32_t)*m_ptr, pos, r, comp);
+  const bool live = decode_slot(d, t, blockIdx.x * kListTile + tid, (uint32_t)*m_ptr, pos, r, comp);
   const uint32_t ver = live ? (uint32_t)sv.version[pos] : 0u;
   uint32_t mask = 0;  // bit cls_lbit[c]: my servant is eligible for class c of its component
   for (uint32_t c = 0; c < ncls; ++c) {
     const bool in = live && comp == ct.cls_comp[c] && ver >= ct.cls_mv[c] && servant_has_env(t, pos, ct.cls_env[c]);
     if (in) mask |= 1u << (ct.cls_lbit[c] & 31u);
-    const int cnt = __syncthreads_count(in);
-    if (threadIdx.x == 0) counts[c * n_tiles + blockIdx.x] = (uint32_t)cnt;
+    const uint32_t cnt = list_block_count(in, warp_cnt, lane, warp);
+    if (tid == 0) counts[c * n_tiles + blockIdx.x] = cnt;
   }
   // merge-mode components get one list of ALL their slots (pseudo-class ncls + midx)
   const uint32_t nmerge = min(ct.meta[2], ct.cls_bound - ncls);
   if (nmerge) {
     const uint32_t midx = live ? ct.comp_midx[comp] : kNone;
     for (uint32_t m = 0; m < nmerge; ++m) {
-      const int cnt = __syncthreads_count(live && midx == m && mask != 0);
-      if (threadIdx.x == 0) counts[(ncls + m) * n_tiles + blockIdx.x] = (uint32_t)cnt;
+      const uint32_t cnt = list_block_count(live && midx == m && mask != 0, warp_cnt, lane, warp);
+      if (tid == 0) counts[(ncls + m) * n_tiles + blockIdx.x] = cnt;
     }
   }
 }
@@ -320,6 +334,14 @@ __global__ void __launch_bounds__(kListTile) k_list_fill(const unsigned long lon
     __syncthreads();  // warp_cnt of the previous class has been consumed
     if (lane == 0) warp_cnt[warp] = __popc(bal);
     __syncthreads();
+#ifdef YD_LIST_CHECK
+    if (tid == 0) {
+      uint32_t tot = 0;
+      for (int w = 0; w < 32; ++w) tot += warp_cnt[w];
+      const uint32_t expect = offs[c * n_tiles + blockIdx.x + 1] - offs[c * n_tiles + blockIdx.x];
+      if (tot != expect) printf("LISTCHECK class %u tile %u fill %u count %u\n", c, blockIdx.x, tot, expect);
+    }
+#endif
     if (in) {
       uint32_t before = __popc(bal & ((1u << lane) - 1));
       for (uint32_t w = 0; w < warp; ++w) before += warp_cnt[w];

@@ -60,6 +60,7 @@ __global__ void __launch_bounds__(kRankTile) k_rank_count(const yd_task_req* __r
     }
     tile_cnt[tid * n_tiles + blockIdx.x] = run;
   }
+  if (blockIdx.x == 0 && tid == 0) tile_cnt[ct.cls_bound * n_tiles] = 0;  // the scan's end cell
   __syncthreads();
   if (q < n) {
     rcls[q] = cls;

@@ -21,9 +21,17 @@ __global__ void __launch_bounds__(1024) k_final_count(const uint32_t* __restrict
                                                       const uint32_t* __restrict__ abort_flag) {
   if (abort_flag && *abort_flag) return;
   uint32_t q = blockIdx.x * 1024 + threadIdx.x;
-  int granted = (q < dp->n) && (res[q] < kResTimeout);
-  int c = __syncthreads_count(granted);
-  if (threadIdx.x == 0) block_counts[blockIdx.x] = (uint32_t)c;
+  const bool granted = (q < dp->n) && (res[q] < kResTimeout);
+  // ballot + per-warp counters, the same way k_final_write ranks the grants
+  // (bar.red-based __syncthreads_count under-counted under compute-sanitizer)
+  __shared__ uint32_t warp_cnt[32];
+  const uint32_t bal = __ballot_sync(0xffffffffu, granted);
+  if ((threadIdx.x & 31) == 0) warp_cnt[threadIdx.x >> 5] = __popc(bal);
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    const uint32_t c = __reduce_add_sync(0xffffffffu, warp_cnt[threadIdx.x]);
+    if (threadIdx.x == 0) block_counts[blockIdx.x] = c;
+  }
 }
 
 __global__ void __launch_bounds__(1024) k_final_scan(uint32_t* __restrict__ block_counts, uint32_t nb,

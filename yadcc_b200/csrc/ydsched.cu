@@ -805,6 +805,7 @@ uint32_t LaunchStream(yd_sched* s, uint32_t N, size_t slot_b, bool capturing) {
   a.max_comp_servants = s->max_comp_servants;
   a.comp_mode = s->d_comp_mode.as<uint32_t>();
   a.counters = s->d_counters.as<Counters>();
+  a.debug = getenv("YDSCHED_STREAM_DEBUG") ? (uint32_t)atoi(getenv("YDSCHED_STREAM_DEBUG")) : 0u;
   const size_t dyn = size_t(s->max_comp_servants) * 8;
   yd::k_solve_stream<<<s->n_comps, (yd::kStreamProducers + 1) * 32, dyn, st>>>(a);
   launches += 1;
@@ -865,6 +866,70 @@ uint32_t EnqueueSolve(yd_sched* s, uint32_t Nb, size_t slot_b, uint32_t solver, 
   return launches;
 }
 
+
+// Debug aid (YDSCHED_DUMP=1): hashes of every intermediate of the slot-stream pipeline after a
+// solve, to compare two runs stage by stage.
+void DumpStreamState(yd_sched* s, uint32_t Nb, size_t slot_b) {
+  static int solve_no = 0;
+  ++solve_no;
+  auto fetch = [&](const void* p, size_t bytes) {
+    std::vector<unsigned char> h(bytes);
+    if (bytes) YD_CUDA_CHECK(cudaMemcpy(h.data(), p, bytes, cudaMemcpyDeviceToHost));
+    return h;
+  };
+  auto hash = [&](const char* name, const std::vector<unsigned char>& h) {
+    unsigned long long x = 1469598103934665603ull;
+    for (unsigned char c : h) { x ^= c; x *= 1099511628211ull; }
+    fprintf(stderr, "YDDUMP %d %-12s %8zu %016llx\n", solve_no, name, h.size(), x);
+  };
+  Counters c;
+  YD_CUDA_CHECK(cudaMemcpy(&c, s->d_counters.p, sizeof c, cudaMemcpyDeviceToHost));
+  const size_t m = (size_t)c.slots, ksz = s->wide ? 8 : 4;
+  const uint32_t S = (uint32_t)s->sv.size();
+  fprintf(stderr, "YDDUMP %d slots %zu Nb %u slot_b %zu cls_bound %u\n", solve_no, m, Nb, slot_b, s->cls_bound);
+  hash("row_off", fetch(s->d_row_off.p, size_t(S + 1) * 4));
+  hash("row_len", fetch(s->d_row_len.p, size_t(S) * 4));
+  hash("codes", fetch(s->d_codes.p, m * ksz));
+  hash("owner", fetch(s->d_slot_owner.p, m * 4));
+  hash("sorted_k", fetch(s->d_sort_k[0].p, m * ksz));
+  hash("sorted_v", fetch(s->d_sort_v[0].p, m * 4));
+  yd::ClassTable ct = MakeClassTable(s);
+  auto meta = fetch(ct.meta, 32);
+  const uint32_t* mt = reinterpret_cast<const uint32_t*>(meta.data());
+  fprintf(stderr, "YDDUMP %d meta %u %u %u %u\n", solve_no, mt[0], mt[1], mt[2], mt[3]);
+  const uint32_t ncls = std::min(mt[0], yd::kMaxClasses);
+  hash("cls_env", fetch(ct.cls_env, ncls * 4));
+  hash("cls_mv", fetch(ct.cls_mv, ncls * 4));
+  hash("cls_nelig", fetch(ct.cls_nelig, ncls * 4));
+  hash("comp_mode", fetch(s->d_comp_mode.p, size_t(s->n_comps) * 4));
+  const uint32_t n_tiles = (uint32_t)((slot_b + yd::kListTile - 1) / yd::kListTile);
+  auto lo = fetch(static_cast<char*>(s->d_zero.p) + s->z_listcnt_off, (size_t(mt[3]) * n_tiles + 1) * 4);
+  hash("list_off", lo);
+  const uint32_t total = reinterpret_cast<const uint32_t*>(lo.data())[size_t(mt[3]) * n_tiles];
+  fprintf(stderr, "YDDUMP %d list_total %u\n", solve_no, total);
+  hash("list", fetch(s->d_list.p, size_t(total) * 8));
+  hash("res", fetch(s->d_res.p, size_t(s->h_dyn.as<yd::DynParams>()->n) * 4));
+  hash("run_after", fetch(s->d_run.p, size_t(S) * 4));
+  if (const char* dir = getenv("YDSCHED_DUMP_DIR")) {
+    auto save = [&](const char* name, const std::vector<unsigned char>& h) {
+      char path[512];
+      snprintf(path, sizeof path, "%s/s%d_%s.bin", dir, solve_no, name);
+      if (FILE* f = fopen(path, "wb")) { fwrite(h.data(), 1, h.size(), f); fclose(f); }
+    };
+    save("sorted_k", fetch(s->d_sort_k[0].p, m * ksz));
+    save("sorted_v", fetch(s->d_sort_v[0].p, m * 4));
+    save("owner", fetch(s->d_slot_owner.p, m * 4));
+    save("row_off", fetch(s->d_row_off.p, size_t(S + 1) * 4));
+    save("row_len", fetch(s->d_row_len.p, size_t(S) * 4));
+    save("list_off", lo);
+    save("list", fetch(s->d_list.p, size_t(total) * 8));
+    save("cls_env", fetch(ct.cls_env, ncls * 4));
+    save("cls_mv", fetch(ct.cls_mv, ncls * 4));
+    save("res", fetch(s->d_res.p, size_t(s->h_dyn.as<yd::DynParams>()->n) * 4));
+    save("run_after", fetch(s->d_run.p, size_t(S) * 4));
+    save("reqs", fetch(s->d_reqs.p, size_t(s->h_dyn.as<yd::DynParams>()->n) * sizeof(yd_task_req)));
+  }
+}
 }  // namespace
 }  // extern "C++"
 
@@ -963,6 +1028,7 @@ void yd_wait_for_starting_new_tasks(yd_sched* s, int64_t now_ns, const yd_task_r
     YD_CUDA_CHECK(cudaMemcpyAsync(out, s->d_out.p, size_t(N) * sizeof(yd_grant), cudaMemcpyDeviceToHost, st));
     YD_CUDA_CHECK(cudaEventRecord(s->ev[5], st));
     YD_CUDA_CHECK(cudaStreamSynchronize(st));
+    if (getenv("YDSCHED_DUMP") && solver == 2 && S && s->n_comps) DumpStreamState(s, Nb, slot_b);
     if (solver == 2 && S && s->n_comps && s->h_meta.as<uint32_t>()[1] != 0) {
       // Nothing was decided (the stream solver and the final kernels all stood down).
       const uint32_t flag = s->h_meta.as<uint32_t>()[1], ncls = s->h_meta.as<uint32_t>()[0];
