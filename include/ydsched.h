@@ -265,6 +265,35 @@ void yd_bloom_possibly_contains(yd_sched* s, const char* keys, size_t n, size_t 
 /* BloomFilter::GetBytes: returns the filter size in bytes; copies at most cap bytes. */
 size_t yd_bloom_get_bytes(yd_sched* s, uint8_t* out, size_t cap);
 
+/* ---- in-flight task index ------------------------------ */
+
+/* The delegate daemon's RunningTaskKeeper (yadcc/daemon/local/running_task_keeper.cc:40-75):
+ * once a second it replaces its map  task_digest -> {servant_location, servant_task_id}  with the
+ * scheduler's GetRunningTasks answer (a later entry with the same digest overwrites an earlier
+ * one, cc:56-60) and, before asking for a grant, looks the new task's digest up
+ * (TryFindTask, cc:67-75; caller distributed_task_dispatcher.cc:257) so that a translation
+ * unit already being compiled somewhere is joined instead of compiled twice.  Here the map is
+ * built from the handle's own running-task bookkeeping and probed for a whole queue at once. */
+typedef struct yd_running_hit {
+  uint64_t servant_task_id; /* TaskDesc::servant_task_id (running_task_keeper.h:39), 0 if not found */
+  uint32_t snapshot_index;  /* position of the winning entry in the refreshed snapshot (the order
+                             * yd_get_running_tasks returned at refresh time), YD_NO_SERVANT if not found */
+  uint32_t found;           /* TryFindTask(...).has_value() */
+} yd_running_hit;
+
+/* RunningTaskKeeper::Refresh (cc:40-65) against this handle: snapshot = what
+ * yd_get_running_tasks returns now.  Returns the number of entries in the snapshot. */
+size_t yd_running_index_refresh(yd_sched* s);
+/* Number of distinct digests in the index (running_tasks_.size()). */
+size_t yd_running_index_size(yd_sched* s);
+/* TryFindTask x n.  Keys are n fixed-length records like the bloom calls:
+ * key i = keys + i * stride, key_len bytes. */
+void yd_running_index_find(yd_sched* s, const char* keys, size_t n, size_t key_len, size_t stride,
+                           yd_running_hit* out);
+/* Entry `snapshot_index` of the refreshed snapshot; returns 0 if out of range.  The strings
+ * stay valid until the next yd_running_index_refresh. */
+int yd_running_index_entry(yd_sched* s, uint32_t snapshot_index, yd_running_task* out);
+
 /* ---- introspection ------------------------------------------------------ */
 
 size_t yd_num_servants(yd_sched* s);

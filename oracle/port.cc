@@ -104,6 +104,10 @@ struct yd_sched {
   std::vector<std::string> envs, ips;
   std::unordered_map<std::string, std::uint32_t> env_ids, ip_ids;
   std::vector<RunningTaskRec> running_cache;
+  struct Keeper {  // RunningTaskKeeper state (in-flight task index)
+    std::vector<RunningTaskRec> snapshot;
+    std::unordered_map<std::string, uint32_t> by_digest;  // digest -> winning snapshot index
+  } keeper;
   yd_solve_stats stats{};
   bool have_stats = false;
 
@@ -514,4 +518,38 @@ extern "C" size_t yd_bloom_get_bytes(yd_sched* s, uint8_t* out, size_t cap) {
   Bloom& b = g_blooms.at(s);
   if (out) std::memcpy(out, b.bytes.data(), std::min(cap, b.bytes.size()));
   return b.bytes.size();
+}
+
+// ---- in-flight task index: restatement of RunningTaskKeeper ---------------------------------
+// yadcc/daemon/local/running_task_keeper.cc:40-65 (Refresh: tmp[digest] = desc over the
+// GetRunningTasks answer, in order, so the LAST entry of a digest wins) and :67-75 (TryFindTask).
+
+extern "C" size_t yd_running_index_refresh(yd_sched* s) {
+  auto& k = s->keeper;
+  k.snapshot.clear();
+  for (auto&& [loc, v] : s->running_tasks) k.snapshot.insert(k.snapshot.begin(), v.begin(), v.end());  // bookkeeper.cc:36-43
+  k.by_digest.clear();
+  for (uint32_t i = 0; i < k.snapshot.size(); ++i) k.by_digest[k.snapshot[i].task_digest] = i;
+  return k.snapshot.size();
+}
+
+extern "C" size_t yd_running_index_size(yd_sched* s) { return s->keeper.by_digest.size(); }
+
+extern "C" void yd_running_index_find(yd_sched* s, const char* keys, size_t n, size_t key_len, size_t stride,
+                                      yd_running_hit* out) {
+  if (!out) return;
+  auto& k = s->keeper;
+  for (size_t i = 0; i < n; ++i) {
+    auto it = k.by_digest.find(std::string(keys + i * stride, key_len));
+    if (it == k.by_digest.end()) out[i] = yd_running_hit{0, YD_NO_SERVANT, 0};
+    else out[i] = yd_running_hit{k.snapshot[it->second].servant_task_id, it->second, 1};
+  }
+}
+
+extern "C" int yd_running_index_entry(yd_sched* s, uint32_t i, yd_running_task* out) {
+  auto& k = s->keeper;
+  if (i >= k.snapshot.size()) return 0;
+  auto&& t = k.snapshot[i];
+  if (out) *out = yd_running_task{t.servant_task_id, t.task_grant_id, t.servant_location.c_str(), t.task_digest.c_str()};
+  return 1;
 }

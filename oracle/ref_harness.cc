@@ -58,6 +58,11 @@ struct yd_sched {
   std::vector<std::string> ips;  // ip id -> text (id 0 = "")
   std::unordered_map<std::string, std::uint32_t> ip_ids;
   std::vector<RunningTask> running_cache;  // backing store for yd_get_running_tasks
+  struct KeeperState {  // RunningTaskKeeper state (in-flight task index)
+    std::vector<RunningTask> snapshot;
+    struct TaskDesc { std::string servant_location; std::uint64_t servant_task_id; std::uint32_t index; };
+    std::unordered_map<std::string, TaskDesc> running_tasks;
+  } keeper;
   std::string location_cache;
   yd_solve_stats stats{};
   bool have_stats = false;
@@ -369,4 +374,43 @@ extern "C" size_t yd_bloom_get_bytes(yd_sched* s, uint8_t* out, size_t cap) {
   auto b = g_blooms.at(s)->GetBytes();
   if (out) std::memcpy(out, b.data(), std::min(cap, b.size()));
   return b.size();
+}
+
+// ---- in-flight task index: RunningTaskKeeper's two loops, literally ----------------------------
+// running_task_keeper.cc itself needs flare's RPC client (scheduler_stub_), so it cannot be
+// compiled here; what it does with the GetRunningTasks answer is restated line by line on top
+// of the verbatim TaskDispatcher::GetRunningTasks (Refresh cc:56-64, TryFindTask cc:67-75).
+
+extern "C" size_t yd_running_index_refresh(yd_sched* s) {
+  auto& k = s->keeper;
+  k.snapshot = s->d->GetRunningTasks();
+  std::unordered_map<std::string, yd_sched::KeeperState::TaskDesc> tmp_running_tasks;
+  std::uint32_t i = 0;
+  for (auto&& running_task : k.snapshot) {
+    yd_sched::KeeperState::TaskDesc task_desc = {running_task.servant_location(), running_task.servant_task_id(), i++};
+    tmp_running_tasks[running_task.task_digest()] = std::move(task_desc);
+  }
+  k.running_tasks.swap(tmp_running_tasks);
+  return k.snapshot.size();
+}
+
+extern "C" size_t yd_running_index_size(yd_sched* s) { return s->keeper.running_tasks.size(); }
+
+extern "C" void yd_running_index_find(yd_sched* s, const char* keys, size_t n, size_t key_len, size_t stride,
+                                      yd_running_hit* out) {
+  if (!out) return;
+  auto& k = s->keeper;
+  for (size_t i = 0; i < n; ++i) {
+    auto result = k.running_tasks.find(std::string(keys + i * stride, key_len));
+    if (result != k.running_tasks.end()) out[i] = yd_running_hit{result->second.servant_task_id, result->second.index, 1};
+    else out[i] = yd_running_hit{0, YD_NO_SERVANT, 0};
+  }
+}
+
+extern "C" int yd_running_index_entry(yd_sched* s, uint32_t i, yd_running_task* out) {
+  auto& k = s->keeper;
+  if (i >= k.snapshot.size()) return 0;
+  auto&& t = k.snapshot[i];
+  if (out) *out = yd_running_task{t.servant_task_id(), t.task_grant_id(), t.servant_location().c_str(), t.task_digest().c_str()};
+  return 1;
 }

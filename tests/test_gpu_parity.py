@@ -286,15 +286,22 @@ def test_bloom_prefilter_cuda_equals_oracle(make_dispatcher, seed):
 def test_cfg4_trace_with_bloom_prefilter(make_dispatcher):
     """BASELINE configs[3]: 100 k requests replaying 6124 TU keys, cache bloom filter on.
     Requests whose cache key may be in the cache are dropped before the solver (the delegate
-    daemon does this, distributed_cache_reader.cc:70-77); the rest is solved as config 2."""
+    daemon does this, distributed_cache_reader.cc:70-77), requests whose task digest is
+    already being compiled somewhere join that task instead (running_task_keeper.cc:67-75,
+    distributed_task_dispatcher.cc:257); the rest is solved as config 2."""
     import numpy as np
     from bloom_cases import tu_keys
+    from running_index_cases import task_digests
+    from yadcc_b200 import RunningTask
 
     keys = tu_keys(6124)
+    digests = task_digests(6124, 11)  # the task digest of TU i (task_digest.cc:25-31)
     rng = np.random.default_rng(4)
     cached = [k for k, m in zip(keys, rng.random(len(keys)) < 0.3) if m]
     n = 100_000
-    trace = [keys[i % len(keys)] for i in range(n)]
+    tu = np.arange(n) % len(keys)
+    trace = [keys[i] for i in tu]
+    trace_digests = [digests[i] for i in tu]
     results = []
     for kind in ("cuda", "port"):
         d = make_dispatcher(kind)
@@ -302,10 +309,62 @@ def test_cfg4_trace_with_bloom_prefilter(make_dispatcher):
         w.register(d)
         d.bloom_reset()
         d.bloom_add(cached)
+        # an earlier wave is still compiling: its servants list those tasks in their heartbeats
+        all_reqs = w.build_requests(d)
+        early = d.wait_for_starting_new_tasks(all_reqs[:1500].copy(), 0.25)
+        locs = [d.servant_location(i) for i in range(2000)]
+        by_servant = {}
+        for j, gr in enumerate(early):
+            assert gr["status"] == 2
+            by_servant.setdefault(int(gr["servant_index"]), []).append(
+                RunningTask(j + 1, int(gr["task_id"]), locs[int(gr["servant_index"])], digests[5000 - j]))
+        for si, tasks in by_servant.items():
+            d.notify_servant_running_tasks(locs[si], tasks)
+        d.running_index_refresh()
         hit = d.bloom_possibly_contains(trace)
-        reqs = w.build_requests(d)[~hit]
-        g = d.wait_for_starting_new_tasks(reqs, 0.5)
-        results.append((hit.copy(), g.copy()))
+        joined = d.find_running_tasks(trace_digests)
+        keep = ~hit & (joined["found"] == 0)
+        g = d.wait_for_starting_new_tasks(all_reqs[keep], 0.5)
+        results.append((hit.copy(), joined.copy(), g.copy()))
     assert (results[0][0] == results[1][0]).all()
     assert (results[0][1] == results[1][1]).all()
+    assert (results[0][2] == results[1][2]).all()
     assert 0.25 < results[0][0].mean() < 0.35
+    assert 0.15 < results[0][1]["found"].mean() < 0.35
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", range(3))
+def test_running_index_matches_oracle(make_dispatcher, seed):
+    """In-flight task index (RunningTaskKeeper): device hash table vs the CPU restatement."""
+    from running_index_cases import run_suite
+
+    a = run_suite(make_dispatcher("cuda"), seed)
+    b = run_suite(make_dispatcher("port"), seed)
+    assert len(a) == len(b)
+    for k, (x, y) in enumerate(zip(a, b)):
+        assert x.shape == y.shape and (x == y).all(), k
+
+
+@pytest.mark.gpu
+def test_running_index_reference_test_and_scale(make_dispatcher):
+    """running_task_keeper_test.cc's own scenario, then a 2000-servant cluster with ~30 k
+    in-flight tasks (many duplicate digests) probed by a 100 k-entry queue."""
+    import numpy as np
+    from running_index_cases import populate, reference_test_case, task_digests
+
+    first, second = reference_test_case(make_dispatcher("cuda"))
+    assert first["found"].all() and list(first["servant_task_id"]) == [0, 1, 2]
+    assert not second["found"].any()
+
+    pool = task_digests(12000, 3)
+    queue = [pool[i % len(pool)] for i in range(60_000)] + task_digests(40_000, 4)
+    res = []
+    for kind in ("cuda", "port"):
+        d = make_dispatcher(kind)
+        populate(d, 2000, 8, pool, seed=1)  # 2000 servants, 8000 grants
+        n = d.running_index_refresh()
+        res.append((n, d.running_index_size(), d.find_running_tasks(queue)))
+    assert res[0][0] == res[1][0] > 7000 and res[0][1] == res[1][1]
+    assert (res[0][2] == res[1][2]).all()
+    assert 0.1 < res[0][2]["found"].mean() < 0.6

@@ -51,6 +51,7 @@ RPC_WAIT_DTYPE = np.dtype(
         ("next_keep_alive_ns", "<i8"),
     ]
 )
+RUNNING_HIT_DTYPE = np.dtype([("servant_task_id", "<u8"), ("snapshot_index", "<u4"), ("found", "<u4")])
 RPC_RESULT_DTYPE = np.dtype([("status", "<u4"), ("n_grants", "<u4"), ("first_grant", "<u4"), ("reserved", "<u4")])
 RPC_OK, RPC_NO_QUOTA_AVAILABLE, RPC_INVALID_ARGUMENT, RPC_ENVIRONMENT_NOT_AVAILABLE = 0, 1001, 1004, 1006
 assert REQ_DTYPE.itemsize == 24 and GRANT_DTYPE.itemsize == 16 and RPC_WAIT_DTYPE.itemsize == 32
@@ -136,6 +137,10 @@ PROTOTYPES = [
     ("yd_bloom_add", None, [_P, _P, C.c_size_t, C.c_size_t, C.c_size_t]),
     ("yd_bloom_possibly_contains", None, [_P, _P, C.c_size_t, C.c_size_t, C.c_size_t, _P]),
     ("yd_bloom_get_bytes", C.c_size_t, [_P, _P, C.c_size_t]),
+    ("yd_running_index_refresh", C.c_size_t, [_P]),
+    ("yd_running_index_size", C.c_size_t, [_P]),
+    ("yd_running_index_find", None, [_P, _P, C.c_size_t, C.c_size_t, C.c_size_t, _P]),
+    ("yd_running_index_entry", C.c_int, [_P, C.c_uint32, _P]),
     ("yd_num_servants", C.c_size_t, [_P]),
     ("yd_servant_location", C.c_char_p, [_P, C.c_uint32]),
     ("yd_get_servant_state", C.c_size_t, [_P, _P, C.c_size_t]),

@@ -30,6 +30,7 @@
 #include "parallel.cuh"
 #include "solve_merge.cuh"
 #include "bloom.cuh"
+#include "running_index.cuh"
 #include "tasks.cuh"
 
 namespace {
@@ -212,6 +213,12 @@ struct yd_sched {
   DevBuf d_bloom, d_bloom_keys, d_bloom_out;
   uint64_t bloom_bits = 0;
   uint32_t bloom_hashes = 0;
+
+  // in-flight task index (running_index.cuh)
+  std::vector<RunningRec> rt_snapshot;
+  DevBuf d_rt_bytes, d_rt_off, d_rt_len, d_rt_ids, d_rt_slots, d_rt_keys, d_rt_out;
+  uint32_t rt_mask = 0;
+  size_t rt_distinct = 0;
 
   cudaEvent_t ev[6] = {};
   yd_solve_stats stats{};
@@ -518,7 +525,8 @@ void yd_destroy(yd_sched* s) {
                     &s->d_codes, &s->d_ids, &s->d_ok, &s->d_counters, &s->d_sv_env_off, &s->d_sv_envs,
                     &s->d_comp_mode, &s->d_slot_owner, &s->d_sort_k[0], &s->d_sort_k[1], &s->d_sort_v[0],
                     &s->d_sort_v[1], &s->d_zero, &s->d_list, &s->d_rcls, &s->d_rrank, &s->d_rank_cnt, &s->d_rq, &s->d_bloom,
-                    &s->d_bloom_keys, &s->d_bloom_out}) {
+                    &s->d_bloom_keys, &s->d_bloom_out, &s->d_rt_bytes, &s->d_rt_off, &s->d_rt_len, &s->d_rt_ids,
+                    &s->d_rt_slots, &s->d_rt_keys, &s->d_rt_out}) {
     b->release();
   }
   for (auto& g : s->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
@@ -1377,4 +1385,99 @@ size_t yd_bloom_get_bytes(yd_sched* s, uint8_t* out, size_t cap) {
   return nbytes;
 }
 
+// ---- in-flight task index (running_index.cuh) ---------------------------------------------------
+
+static yd::RtIndex MakeRtIndex(yd_sched* s) {
+  yd::RtIndex ix{};
+  ix.bytes = s->d_rt_bytes.as<unsigned char>();
+  ix.off = s->d_rt_off.as<uint32_t>();
+  ix.len = s->d_rt_len.as<uint32_t>();
+  ix.slots = s->rt_snapshot.empty() ? nullptr : s->d_rt_slots.as<uint32_t>();
+  ix.mask = s->rt_mask;
+  return ix;
+}
+
+// RunningTaskKeeper::Refresh, running_task_keeper.cc:40-65.
+size_t yd_running_index_refresh(yd_sched* s) {
+  // the snapshot: what GetRunningTasks answers now (running_task_bookkeeper.cc:36-43)
+  // (each servant's list goes to the FRONT there: same order, built back to front in O(n))
+  s->rt_snapshot.clear();
+  {
+    std::vector<const std::vector<RunningRec>*> groups;
+    for (auto&& [k, v] : s->running) groups.push_back(&v);
+    for (auto it = groups.rbegin(); it != groups.rend(); ++it) {
+      s->rt_snapshot.insert(s->rt_snapshot.end(), (*it)->begin(), (*it)->end());
+    }
+  }
+  const size_t n = s->rt_snapshot.size();
+  s->rt_distinct = 0;
+  if (n == 0) return 0;
+  if (n > 0x7fffffffull) { fprintf(stderr, "ydsched: running-task snapshot too large\n"); abort(); }
+  YD_CUDA_CHECK(cudaSetDevice(s->device));
+  // digests packed on 8-byte boundaries so the kernels can use word loads
+  std::vector<uint32_t> off(n), len(n);
+  std::vector<unsigned long long> ids(n);
+  size_t total = 0;
+  for (size_t i = 0; i < n; ++i) {
+    off[i] = (uint32_t)total;
+    len[i] = (uint32_t)s->rt_snapshot[i].task_digest.size();
+    ids[i] = s->rt_snapshot[i].servant_task_id;
+    total += (len[i] + 7) & ~size_t(7);
+    if (total > 0xfffffff0ull) { fprintf(stderr, "ydsched: running-task digests exceed 4 GiB\n"); abort(); }
+  }
+  std::vector<unsigned char> bytes(total ? total : 8, 0);
+  for (size_t i = 0; i < n; ++i) memcpy(bytes.data() + off[i], s->rt_snapshot[i].task_digest.data(), len[i]);
+  uint64_t cap = 1024;
+  while (cap < 2 * n) cap <<= 1;  // load factor <= 0.5
+  s->rt_mask = (uint32_t)(cap - 1);
+  s->d_rt_bytes.ensure(bytes.size());
+  s->d_rt_off.ensure(n * 4);
+  s->d_rt_len.ensure(n * 4);
+  s->d_rt_ids.ensure(n * 8);
+  s->d_rt_slots.ensure(cap * 4 + 4);  // + the distinct-digest counter
+  cudaStream_t st = s->st;
+  YD_CUDA_CHECK(cudaMemcpyAsync(s->d_rt_bytes.p, bytes.data(), bytes.size(), cudaMemcpyHostToDevice, st));
+  YD_CUDA_CHECK(cudaMemcpyAsync(s->d_rt_off.p, off.data(), n * 4, cudaMemcpyHostToDevice, st));
+  YD_CUDA_CHECK(cudaMemcpyAsync(s->d_rt_len.p, len.data(), n * 4, cudaMemcpyHostToDevice, st));
+  YD_CUDA_CHECK(cudaMemcpyAsync(s->d_rt_ids.p, ids.data(), n * 8, cudaMemcpyHostToDevice, st));
+  YD_CUDA_CHECK(cudaMemsetAsync(s->d_rt_slots.p, 0, cap * 4 + 4, st));
+  uint32_t* distinct = s->d_rt_slots.as<uint32_t>() + cap;
+  yd::k_rt_build<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(MakeRtIndex(s), (uint32_t)n, distinct);
+  YD_CUDA_CHECK(cudaGetLastError());
+  uint32_t h_distinct = 0;
+  YD_CUDA_CHECK(cudaMemcpyAsync(&h_distinct, distinct, 4, cudaMemcpyDeviceToHost, st));
+  YD_CUDA_CHECK(cudaStreamSynchronize(st));  // also keeps the pageable staging vectors alive long enough
+  s->rt_distinct = h_distinct;
+  return n;
+}
+
+size_t yd_running_index_size(yd_sched* s) { return s->rt_distinct; }
+
+// RunningTaskKeeper::TryFindTask x n, running_task_keeper.cc:67-75.
+void yd_running_index_find(yd_sched* s, const char* keys, size_t n, size_t key_len, size_t stride,
+                           yd_running_hit* out) {
+  if (n == 0 || !out) return;
+  if (n > 0x7fffffffull || key_len > 0x7fffffffull) { fprintf(stderr, "ydsched: running-index query too large\n"); abort(); }
+  YD_CUDA_CHECK(cudaSetDevice(s->device));
+  cudaStream_t st = s->st;
+  const size_t span = (n - 1) * stride + key_len;
+  s->d_rt_keys.ensure(span ? span : 1);
+  s->d_rt_out.ensure(n * sizeof(yd_running_hit));
+  YD_CUDA_CHECK(cudaMemcpyAsync(s->d_rt_keys.p, keys, span, cudaMemcpyHostToDevice, st));
+  yd::k_rt_find<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(MakeRtIndex(s), s->d_rt_keys.as<unsigned char>(), (uint32_t)n,
+                                                              (uint32_t)key_len, stride,
+                                                              s->d_rt_ids.as<unsigned long long>(), s->d_rt_out.as<uint4>());
+  YD_CUDA_CHECK(cudaGetLastError());
+  YD_CUDA_CHECK(cudaMemcpyAsync(out, s->d_rt_out.p, n * sizeof(yd_running_hit), cudaMemcpyDeviceToHost, st));
+  YD_CUDA_CHECK(cudaStreamSynchronize(st));
+}
+
+int yd_running_index_entry(yd_sched* s, uint32_t i, yd_running_task* out) {
+  if (i >= s->rt_snapshot.size()) return 0;
+  auto&& t = s->rt_snapshot[i];
+  if (out) *out = yd_running_task{t.servant_task_id, t.task_grant_id, t.servant_location.c_str(), t.task_digest.c_str()};
+  return 1;
+}
+
 }  // extern "C"
+

@@ -333,6 +333,34 @@ class TaskDispatcher:
         self._lib.yd_bloom_get_bytes(self._h, out.ctypes.data, n)
         return out.tobytes()
 
+    # -- in-flight task index (RunningTaskKeeper, running_task_keeper.cc:40-75) ----
+    def running_index_refresh(self) -> int:
+        """Refresh(): rebuild digest -> running task from the current bookkeeping.
+        Returns the snapshot length."""
+        return int(self._lib.yd_running_index_refresh(self._h))
+
+    def running_index_size(self) -> int:
+        return int(self._lib.yd_running_index_size(self._h))
+
+    def find_running_tasks(self, digests) -> np.ndarray:
+        """TryFindTask for a whole queue of (equal-length) task digests.  Returns a
+        RUNNING_HIT array: found, snapshot_index, servant_task_id."""
+        m = self._key_matrix(digests)
+        out = np.zeros(m.shape[0], dtype=_abi.RUNNING_HIT_DTYPE)
+        if len(m):
+            self._lib.yd_running_index_find(self._h, m.ctypes.data, m.shape[0], m.shape[1], m.strides[0],
+                                            out.ctypes.data)
+        return out
+
+    def running_index_entry(self, snapshot_index: int) -> RunningTask | None:
+        t = _abi.yd_running_task()
+        import ctypes as C
+
+        if not self._lib.yd_running_index_entry(self._h, int(snapshot_index), C.byref(t)):
+            return None
+        return RunningTask(int(t.servant_task_id), int(t.task_grant_id), (t.servant_location or b"").decode(),
+                           (t.task_digest or b"").decode())
+
     # -- introspection -----------------------------------------------------
     def num_servants(self) -> int:
         return int(self._lib.yd_num_servants(self._h))
