@@ -302,6 +302,10 @@ size_t yd_num_servants(yd_sched* s);
 const char* yd_servant_location(yd_sched* s, uint32_t servant_index);
 /* Fills up to `cap` entries in registry order; returns the servant count. */
 size_t yd_get_servant_state(yd_sched* s, yd_servant_state* out, size_t cap);
+/* ServantPersonality of registry position `servant_index` as last reported (h:80-116).
+ * Strings and the digest array stay valid until the next call on the handle.  Returns 0 if
+ * out of range. */
+int yd_get_servant_personality(yd_sched* s, uint32_t servant_index, yd_servant* out);
 /* Next task id that would be handed out (TaskRegistry::next_task_id, h:218). */
 uint64_t yd_next_task_id(yd_sched* s);
 /* Number of live (granted, not freed/swept) task leases, zombies included. */

@@ -104,6 +104,7 @@ struct yd_sched {
   std::vector<std::string> envs, ips;
   std::unordered_map<std::string, std::uint32_t> env_ids, ip_ids;
   std::vector<RunningTaskRec> running_cache;
+  std::vector<const char*> personality_envs;
   struct Keeper {  // RunningTaskKeeper state (in-flight task index)
     std::vector<RunningTaskRec> snapshot;
     std::unordered_map<std::string, uint32_t> by_digest;  // digest -> winning snapshot index
@@ -394,6 +395,19 @@ size_t yd_get_servant_state(yd_sched* s, yd_servant_state* out, size_t cap) {
   return s->servants.size();
 }
 
+int yd_get_servant_personality(yd_sched* s, uint32_t idx, yd_servant* out) {
+  if (idx >= s->servants.size()) return 0;
+  const ServantRec& v = *s->servants[idx];
+  s->personality_envs.clear();
+  for (auto&& e : v.environments) s->personality_envs.push_back(e.c_str());
+  if (out) {
+    *out = yd_servant{v.version, v.priority, v.reason, (uint32_t)v.environments.size(), v.observed_location.c_str(),
+                      v.reported_location.c_str(), s->personality_envs.data(), (uint32_t)v.num_processors,
+                      (uint32_t)v.current_load, (uint32_t)v.max_tasks, 0, v.total_memory, v.memory_available};
+  }
+  return 1;
+}
+
 uint64_t yd_next_task_id(yd_sched* s) { return s->next_task_id; }
 uint64_t yd_num_tasks(yd_sched* s) { return s->tasks.size(); }
 
@@ -429,6 +443,7 @@ void yd_free_host(void* p) { std::free(p); }
 
 }  // extern "C"
 #include "ydsched_rpc_impl.inc"
+#include "ydservice_impl.inc"
 
 // ---- bloom pre-filter: restatement of flare's SaltedBloomFilter over XXH64 --------------
 // XXH64 is restated from the published xxHash specification (Cyan4973/xxHash, doc/

@@ -58,6 +58,7 @@ struct yd_sched {
   std::vector<std::string> ips;  // ip id -> text (id 0 = "")
   std::unordered_map<std::string, std::uint32_t> ip_ids;
   std::vector<RunningTask> running_cache;  // backing store for yd_get_running_tasks
+  std::vector<const char*> personality_envs;
   struct KeeperState {  // RunningTaskKeeper state (in-flight task index)
     std::vector<RunningTask> snapshot;
     struct TaskDesc { std::string servant_location; std::uint64_t servant_task_id; std::uint32_t index; };
@@ -255,6 +256,21 @@ size_t yd_get_servant_state(yd_sched* s, yd_servant_state* out, size_t cap) {
   return sv.size();
 }
 
+int yd_get_servant_personality(yd_sched* s, uint32_t idx, yd_servant* out) {
+  auto& sv = yd_oracle_access::Servants(*s->d);
+  if (idx >= sv.size()) return 0;
+  const ServantPersonality& p = sv[idx]->personality;
+  s->personality_envs.clear();
+  for (auto&& e : p.environments) s->personality_envs.push_back(e.compiler_digest().c_str());
+  if (out) {
+    *out = yd_servant{p.version, (int32_t)p.priority, (int32_t)p.not_accepting_task_reason,
+                      (uint32_t)p.environments.size(), p.observed_location.c_str(), p.reported_location.c_str(),
+                      s->personality_envs.data(), (uint32_t)p.num_processors, (uint32_t)p.current_load,
+                      (uint32_t)p.max_tasks, 0, p.total_memory_in_bytes, p.memory_available_in_bytes};
+  }
+  return 1;
+}
+
 uint64_t yd_next_task_id(yd_sched* s) { return yd_oracle_access::NextTaskId(*s->d); }
 uint64_t yd_num_tasks(yd_sched* s) { return yd_oracle_access::Tasks(*s->d).size(); }
 
@@ -414,3 +430,7 @@ extern "C" int yd_running_index_entry(yd_sched* s, uint32_t i, yd_running_task* 
   if (out) *out = yd_running_task{t.servant_task_id(), t.task_grant_id(), t.servant_location().c_str(), t.task_digest().c_str()};
   return 1;
 }
+
+// SchedulerServiceImpl's other handlers: host logic over the ABI above (the handlers themselves need
+// flare's RPC controller and protobuf, so scheduler_service_impl.cc cannot be compiled here).
+#include "ydservice_impl.inc"

@@ -11,14 +11,15 @@ from conftest import CUDA_LIB, PORT_LIB, REF_LIB, ROOT, have_gpu
 from yadcc_b200 import _abi
 
 
-def header_symbols():
-    text = (ROOT / "include" / "ydsched.h").read_text()
+def header_symbols(header="ydsched.h"):
+    text = (ROOT / "include" / header).read_text()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
     return sorted(set(re.findall(r"\b(yd_[a-z_]+)\s*\(", text)))
 
 
 def test_prototypes_cover_header():
     assert header_symbols() == sorted(name for name, _, _ in _abi.PROTOTYPES)
+    assert header_symbols("ydservice.h") == sorted(name for name, _, _ in _abi.SERVICE_PROTOTYPES)
 
 
 @pytest.mark.parametrize("lib", [CUDA_LIB, PORT_LIB, REF_LIB], ids=["cuda", "port", "ref"])
@@ -28,7 +29,7 @@ def test_library_exports_every_symbol(lib, port_lib):
             pytest.skip("reference build not present")
         pytest.fail(f"{lib} missing: run make / __graft_entry__.build()")
     h = ctypes.CDLL(str(lib))
-    for name in header_symbols():
+    for name in header_symbols() + header_symbols("ydservice.h"):
         assert hasattr(h, name), f"{lib} does not export {name}"
 
 

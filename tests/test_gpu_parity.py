@@ -368,3 +368,14 @@ def test_running_index_reference_test_and_scale(make_dispatcher):
     assert res[0][0] == res[1][0] > 7000 and res[0][1] == res[1][1]
     assert (res[0][2] == res[1][2]).all()
     assert 0.1 < res[0][2]["found"].mean() < 0.6
+
+
+@pytest.mark.gpu
+def test_service_layer_over_cuda_backend(make_dispatcher):
+    """SchedulerServiceImpl's handlers (include/ydservice.h) over the CUDA dispatcher give the
+    same answers as over the CPU restatement, for every case of tests/service_cases.py."""
+    import service_cases as SC
+    from test_service import CASES, _same
+
+    for case in CASES:
+        assert _same(case(make_dispatcher("cuda")), case(make_dispatcher("port"))), case.__name__

@@ -96,6 +96,46 @@ class yd_running_task(C.Structure):
     ]
 
 
+class yd_service_config(C.Structure):
+    _fields_ = [
+        ("acceptable_user_tokens", C.c_char_p),
+        ("acceptable_servant_tokens", C.c_char_p),
+        ("min_daemon_version", C.c_int32),
+        ("serving_daemon_token_rollout_interval_s", C.c_int32),
+        ("token_seed", C.c_uint64),
+    ]
+
+
+class yd_heartbeat_request(C.Structure):
+    _fields_ = [
+        ("token", C.c_char_p),
+        ("location", C.c_char_p),
+        ("remote_ip", C.c_char_p),
+        ("remote_is_ipv6", C.c_uint32),
+        ("next_heartbeat_in_ms", C.c_uint32),
+        ("version", C.c_uint32),
+        ("num_processors", C.c_uint32),
+        ("current_load", C.c_uint32),
+        ("servant_priority", C.c_uint32),
+        ("not_accepting_task_reason", C.c_uint32),
+        ("capacity", C.c_uint32),
+        ("n_env_digests", C.c_uint32),
+        ("total_memory_in_bytes", C.c_uint64),
+        ("memory_available_in_bytes", C.c_uint64),
+        ("env_digests", C.POINTER(C.c_char_p)),
+        ("running_tasks", C.POINTER(yd_running_task)),
+        ("n_running_tasks", C.c_size_t),
+    ]
+
+
+class yd_heartbeat_response(C.Structure):
+    _fields_ = [
+        ("acceptable_tokens", C.c_char_p * 3),
+        ("expired_tasks", C.POINTER(C.c_uint64)),
+        ("n_expired_tasks", C.c_size_t),
+    ]
+
+
 class yd_solve_stats(C.Structure):
     _fields_ = [
         ("total_ms", C.c_double),
@@ -137,6 +177,7 @@ PROTOTYPES = [
     ("yd_bloom_add", None, [_P, _P, C.c_size_t, C.c_size_t, C.c_size_t]),
     ("yd_bloom_possibly_contains", None, [_P, _P, C.c_size_t, C.c_size_t, C.c_size_t, _P]),
     ("yd_bloom_get_bytes", C.c_size_t, [_P, _P, C.c_size_t]),
+    ("yd_get_servant_personality", C.c_int, [_P, C.c_uint32, C.POINTER(yd_servant)]),
     ("yd_running_index_refresh", C.c_size_t, [_P]),
     ("yd_running_index_size", C.c_size_t, [_P]),
     ("yd_running_index_find", None, [_P, _P, C.c_size_t, C.c_size_t, C.c_size_t, _P]),
@@ -173,9 +214,23 @@ def load_library(path: os.PathLike | str | None = None) -> C.CDLL:
             "yadcc_b200 has no CPU fallback."
         )
     lib = C.CDLL(str(p), mode=C.RTLD_LOCAL)
-    for name, restype, argtypes in PROTOTYPES:
+    for name, restype, argtypes in PROTOTYPES + SERVICE_PROTOTYPES:
         fn = getattr(lib, name)  # AttributeError if the symbol is missing
         fn.restype = restype
         fn.argtypes = argtypes
     lib._yd_path = str(p)
     return lib
+
+
+# Every symbol include/ydservice.h declares.
+SERVICE_PROTOTYPES = [
+    ("yd_service_create", _P, [_P, C.c_int64, C.POINTER(yd_service_config)]),
+    ("yd_service_destroy", None, [_P]),
+    ("yd_service_heartbeat", C.c_int, [_P, C.c_int64, C.POINTER(yd_heartbeat_request), C.POINTER(yd_heartbeat_response)]),
+    ("yd_service_get_config", C.c_int, [_P, C.c_int64, C.c_char_p, C.POINTER(C.c_char_p)]),
+    ("yd_service_wait_for_starting_tasks", C.c_size_t,
+     [_P, C.c_int64, C.POINTER(C.c_char_p), _P, C.c_size_t, _P, _P, C.c_size_t]),
+    ("yd_service_keep_task_alive", C.c_int, [_P, C.c_int64, C.c_char_p, C.c_uint32, _P, C.c_size_t, _P]),
+    ("yd_service_free_task", C.c_int, [_P, C.c_char_p, _P, C.c_size_t]),
+    ("yd_service_get_running_tasks", C.c_size_t, [_P, C.POINTER(yd_running_task), C.c_size_t]),
+]

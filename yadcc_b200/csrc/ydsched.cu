@@ -189,6 +189,7 @@ struct yd_sched {
   // operation sequence as the reference, hence the same iteration order.
   std::unordered_map<std::string, std::vector<RunningRec>> running;
   std::vector<RunningRec> running_cache;
+  std::vector<const char*> personality_envs;  // backing store for yd_get_servant_personality
 
   // captured solve graphs, keyed by size class
   struct GraphKey {
@@ -1266,6 +1267,18 @@ size_t yd_get_servant_state(yd_sched* s, yd_servant_state* out, size_t cap) {
   return S;
 }
 
+int yd_get_servant_personality(yd_sched* s, uint32_t idx, yd_servant* out) {
+  if (idx >= s->sv.size()) return 0;
+  const ServantHost& v = s->sv[idx];
+  s->personality_envs.clear();
+  for (uint32_t e : v.envs) s->personality_envs.push_back(s->envs[e].c_str());
+  if (out) {
+    *out = yd_servant{v.version, v.priority, v.reason, (uint32_t)v.envs.size(), v.observed.c_str(), v.reported.c_str(),
+                      s->personality_envs.data(), v.nproc, v.load, v.max_tasks, 0, v.total_mem, v.avail_mem};
+  }
+  return 1;
+}
+
 uint64_t yd_next_task_id(yd_sched* s) { return s->next_id * s->id_stride + s->id_offset; }
 
 uint64_t yd_num_tasks(yd_sched* s) {
@@ -1313,6 +1326,7 @@ void yd_free_host(void* p) {
 
 }  // extern "C"
 #include "ydsched_rpc_impl.inc"
+#include "ydservice_impl.inc"
 
 // ---- compilation-cache bloom pre-filter (bloom.cuh) ------------------------------------------
 extern "C" {

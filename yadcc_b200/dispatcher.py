@@ -365,6 +365,19 @@ class TaskDispatcher:
     def num_servants(self) -> int:
         return int(self._lib.yd_num_servants(self._h))
 
+    def servant_personality(self, index: int) -> Servant | None:
+        """ServantPersonality of registry position `index` as last reported."""
+        sv = _abi.yd_servant()
+        if not self._lib.yd_get_servant_personality(self._h, int(index), C.byref(sv)):
+            return None
+        return Servant(
+            observed_location=(sv.observed_location or b"").decode(),
+            reported_location=(sv.reported_location or b"").decode(),
+            environments=[sv.env_digests[i].decode() for i in range(sv.num_envs)],
+            version=sv.version, num_processors=sv.num_processors, current_load=sv.current_load,
+            total_memory_in_bytes=sv.total_memory_in_bytes, memory_available_in_bytes=sv.memory_available_in_bytes,
+            max_tasks=sv.max_tasks, priority=sv.priority, not_accepting_task_reason=sv.not_accepting_task_reason)
+
     def servant_location(self, index: int) -> str | None:
         v = self._lib.yd_servant_location(self._h, index)
         return v.decode() if v is not None else None
