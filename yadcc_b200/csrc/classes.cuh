@@ -260,48 +260,62 @@ __device__ __forceinline__ bool decode_slot(const SlotDecode& d, const TopoView&
   const uint32_t orig = d.sorted_orig[i];
   pos = d.slot_owner[orig];
   const uint32_t k = orig - d.row_off[pos];
-  if (k >= d.row_len[pos]) return false;  // the row's sentinel is nobody's slot
+  if (k >= d.row_len[pos]) return false;  // (defensive: the stream path's rows carry no sentinel)
   r = d.run[pos] + k;
   comp = t.sv_comp[pos];
   return comp != kNone;
 }
 
-// Block-wide number of threads with `in` set, via the same ballot + per-warp counters the
-// fill kernel ranks with (so the two kernels cannot disagree).  Two barriers per call.
-__device__ __forceinline__ uint32_t list_block_count(bool in, uint32_t* warp_cnt, uint32_t lane, uint32_t warp) {
-  const uint32_t bal = __ballot_sync(0xffffffffu, in);
-  __syncthreads();  // warp_cnt of the previous call has been consumed
-  if (lane == 0) warp_cnt[warp] = __popc(bal);
-  __syncthreads();
-  uint32_t total = 0;
-  if (warp == 0) total = __reduce_add_sync(0xffffffffu, warp_cnt[lane]);
-  return total;  // valid in warp 0
+// Both list kernels evaluate "slot i belongs to list c" the same way and exchange it through
+// shared-memory ballots, one 32-bit word per (list, warp): the count kernel pop-counts them, the
+// fill kernel turns them into in-tile ranks.  Lists are processed in chunks of kListChunk so
+// the ballots of a chunk cost one barrier, whatever the number of classes.
+constexpr uint32_t kListChunk = 64;
+
+struct ListMembership {  // per-thread view of one sorted slot
+  bool live;
+  uint32_t pos, r, comp, ver, midx;
+  uint32_t mask;  // bit cls_lbit[c]: my servant is eligible for class c of its component (merge payload)
+};
+
+// Ballots for lists [c0, c1) into bal[c - c0][warp]; lists < ncls are classes, the rest are the
+// merge-mode components' pseudo-classes (every slot of the component, once all class bits are known).
+__device__ __forceinline__ void list_ballots(ListMembership& me, const TopoView& t, const ClassTable& ct, uint32_t ncls,
+                                             uint32_t c0, uint32_t c1, uint32_t (*bal)[32], uint32_t lane,
+                                             uint32_t warp) {
+  for (uint32_t c = c0; c < c1; ++c) {
+    bool in;
+    if (c < ncls) {
+      in = me.live && me.comp == ct.cls_comp[c] && me.ver >= ct.cls_mv[c] && servant_has_env(t, me.pos, ct.cls_env[c]);
+      if (in) me.mask |= 1u << (ct.cls_lbit[c] & 31u);
+    } else {
+      in = me.live && me.midx == c - ncls && me.mask != 0;
+    }
+    const uint32_t b = __ballot_sync(0xffffffffu, in);
+    if (lane == 0) bal[c - c0][warp] = b;
+  }
 }
 
 __global__ void __launch_bounds__(kListTile) k_list_count(const unsigned long long* __restrict__ m_ptr, SlotDecode d,
                                                           TopoView t, ClassTable ct, ServantArrays sv,
                                                           uint32_t n_tiles, uint32_t* __restrict__ counts) {
-  __shared__ uint32_t warp_cnt[32];
+  __shared__ uint32_t bal[kListChunk][32];
   const uint32_t ncls = min(ct.meta[0], ct.cls_bound);
-  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  uint32_t pos, r, comp;
-  const bool live = decode_slot(d, t, blockIdx.x * kListTile + tid, (uint32_t)*m_ptr, pos, r, comp);
-  const uint32_t ver = live ? (uint32_t)sv.version[pos] : 0u;
-  uint32_t mask = 0;  // bit cls_lbit[c]: my servant is eligible for class c of its component
-  for (uint32_t c = 0; c < ncls; ++c) {
-    const bool in = live && comp == ct.cls_comp[c] && ver >= ct.cls_mv[c] && servant_has_env(t, pos, ct.cls_env[c]);
-    if (in) mask |= 1u << (ct.cls_lbit[c] & 31u);
-    const uint32_t cnt = list_block_count(in, warp_cnt, lane, warp);
-    if (tid == 0) counts[c * n_tiles + blockIdx.x] = cnt;
-  }
-  // merge-mode components get one list of ALL their slots (pseudo-class ncls + midx)
   const uint32_t nmerge = min(ct.meta[2], ct.cls_bound - ncls);
-  if (nmerge) {
-    const uint32_t midx = live ? ct.comp_midx[comp] : kNone;
-    for (uint32_t m = 0; m < nmerge; ++m) {
-      const uint32_t cnt = list_block_count(live && midx == m && mask != 0, warp_cnt, lane, warp);
-      if (tid == 0) counts[(ncls + m) * n_tiles + blockIdx.x] = cnt;
+  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  ListMembership me{};
+  me.live = decode_slot(d, t, blockIdx.x * kListTile + tid, (uint32_t)*m_ptr, me.pos, me.r, me.comp);
+  me.ver = me.live ? (uint32_t)sv.version[me.pos] : 0u;
+  me.midx = (me.live && nmerge) ? ct.comp_midx[me.comp] : kNone;
+  for (uint32_t c0 = 0; c0 < ncls + nmerge; c0 += kListChunk) {
+    const uint32_t c1 = min(c0 + kListChunk, ncls + nmerge);
+    list_ballots(me, t, ct, ncls, c0, c1, bal, lane, warp);
+    __syncthreads();
+    for (uint32_t c = c0 + warp; c < c1; c += 32) {
+      const uint32_t cnt = __reduce_add_sync(0xffffffffu, (uint32_t)__popc(bal[c - c0][lane]));
+      if (lane == 0) counts[c * n_tiles + blockIdx.x] = cnt;
     }
+    __syncthreads();  // the ballots have been consumed
   }
 }
 
@@ -310,45 +324,41 @@ __global__ void __launch_bounds__(kListTile) k_list_fill(const unsigned long lon
                                                          TopoView t, ClassTable ct, ServantArrays sv, uint32_t n_tiles,
                                                          const uint32_t* __restrict__ offs,
                                                          uint2* __restrict__ list, uint32_t list_cap) {
-  __shared__ uint32_t warp_cnt[32];
+  __shared__ uint32_t bal[kListChunk][32];
+  __shared__ uint16_t pre[kListChunk][32];  // slots of the list in lower warps of this tile
   const uint32_t ncls = min(ct.meta[0], ct.cls_bound);
-  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  uint32_t pos, r, comp;
-  const bool live = decode_slot(d, t, blockIdx.x * kListTile + tid, (uint32_t)*m_ptr, pos, r, comp);
-  const uint32_t ver = live ? (uint32_t)sv.version[pos] : 0u;
-  const uint32_t local = live ? t.sv_local[pos] : 0u;
   const uint32_t nmerge = min(ct.meta[2], ct.cls_bound - ncls);
-  const uint32_t midx = (live && nmerge) ? ct.comp_midx[comp] : kNone;
-  uint32_t mask = 0;
-  for (uint32_t c = 0; c < ncls + nmerge; ++c) {
-    bool in;
-    uint32_t payload = r;
-    if (c < ncls) {
-      in = live && comp == ct.cls_comp[c] && ver >= ct.cls_mv[c] && servant_has_env(t, pos, ct.cls_env[c]);
-      if (in) mask |= 1u << (ct.cls_lbit[c] & 31u);
-    } else {  // pseudo-class: every slot of a merge-mode component, payload = its class mask
-      in = live && midx == c - ncls && mask != 0;
-      payload = mask;
-    }
-    const uint32_t bal = __ballot_sync(0xffffffffu, in);
-    __syncthreads();  // warp_cnt of the previous class has been consumed
-    if (lane == 0) warp_cnt[warp] = __popc(bal);
+  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  ListMembership me{};
+  me.live = decode_slot(d, t, blockIdx.x * kListTile + tid, (uint32_t)*m_ptr, me.pos, me.r, me.comp);
+  me.ver = me.live ? (uint32_t)sv.version[me.pos] : 0u;
+  me.midx = (me.live && nmerge) ? ct.comp_midx[me.comp] : kNone;
+  const uint32_t local = me.live ? t.sv_local[me.pos] : 0u;
+  for (uint32_t c0 = 0; c0 < ncls + nmerge; c0 += kListChunk) {
+    const uint32_t c1 = min(c0 + kListChunk, ncls + nmerge);
+    list_ballots(me, t, ct, ncls, c0, c1, bal, lane, warp);
     __syncthreads();
-#ifdef YD_LIST_CHECK
-    if (tid == 0) {
-      uint32_t tot = 0;
-      for (int w = 0; w < 32; ++w) tot += warp_cnt[w];
-      const uint32_t expect = offs[c * n_tiles + blockIdx.x + 1] - offs[c * n_tiles + blockIdx.x];
-      if (tot != expect) printf("LISTCHECK class %u tile %u fill %u count %u\n", c, blockIdx.x, tot, expect);
+    for (uint32_t c = c0 + warp; c < c1; c += 32) {  // exclusive prefix over the warps, per list
+      const uint32_t v = __popc(bal[c - c0][lane]);
+      uint32_t x = v;
+#pragma unroll
+      for (int s = 1; s < 32; s <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xffffffffu, x, s);
+        if (lane >= s) x += y;
+      }
+      pre[c - c0][lane] = (uint16_t)(x - v);
     }
-#endif
-    if (in) {
-      uint32_t before = __popc(bal & ((1u << lane) - 1));
-      for (uint32_t w = 0; w < warp; ++w) before += warp_cnt[w];
-      const uint32_t dst = offs[c * n_tiles + blockIdx.x] + before;
-      if (dst < list_cap) list[dst] = make_uint2(local, payload);
-      else ct.meta[1] = 1;  // more (class, slot) pairs than provisioned: the host reruns with solver 1
+    __syncthreads();
+    for (uint32_t c = c0; c < c1; ++c) {
+      const uint32_t word = bal[c - c0][warp];
+      if ((word >> lane) & 1u) {
+        const uint32_t dst = offs[c * n_tiles + blockIdx.x] + pre[c - c0][warp] + __popc(word & ((1u << lane) - 1));
+        // class list: (servant, running_tasks value of the slot); pseudo-class: (servant, class mask)
+        if (dst < list_cap) list[dst] = make_uint2(local, c < ncls ? me.r : me.mask);
+        else ct.meta[1] = 1;  // more (class, slot) pairs than provisioned: the host reruns with solver 1
+      }
     }
+    __syncthreads();  // bal / pre are reused by the next chunk
   }
 }
 

@@ -5,13 +5,17 @@
 // order (tier, utilisation, registry position): ties on the code are broken by
 // position exactly like `first minimum wins` (task_dispatcher.cc:444).
 //
-// One pass = two kernels: per-tile digit histogram (shared-memory atomics), then a stable
-// scatter in which every block derives its own global bases from the raw tile histograms
-// (so there is no separate scan kernel on the critical path).  Stability inside a tile:
+// One kernel up front counts the digits of ALL passes at once (the multiset of keys, hence
+// every digit histogram, is the same before and after each permutation); then one kernel
+// per pass: a block takes the next tile (ticket counter), counts its digits, publishes them,
+// waits for the LOWER tiles' counts only (they are already running, so this cannot deadlock)
+// and scatters.  base(digit, tile) = sum of all smaller digits (global histogram) + counts of
+// that digit in lower tiles.  Stability inside a tile:
 // warp w owns a contiguous chunk of the tile and walks it 32 elements at a time;
 // __match_any_sync ranks equal digits inside a group, per-warp digit counters in
 // shared memory carry the rank across groups, and a prefix over the warps' counts
-// orders the warps.  Algorithmic bytes per pass: read 2 x (key + payload), write 1 x.
+// orders the warps.  Algorithmic bytes: keys read once by the histogram kernel; per pass
+// keys read twice (count, scatter; the second read hits L1/L2) + payload once, both written once.
 #pragma once
 #include "common.cuh"
 
@@ -27,23 +31,6 @@ constexpr int kRsTile = kRsWarps * kRsItemsPerWarp;     // 2048 elements per blo
 template <typename KeyT>
 __device__ __forceinline__ uint32_t rs_digit(KeyT k, int shift) {
   return (uint32_t)(k >> shift) & (kRsBins - 1);
-}
-
-template <typename KeyT>
-__global__ void __launch_bounds__(kRsThreads) k_rs_hist(const KeyT* __restrict__ keys,
-                                                        const unsigned long long* __restrict__ n_ptr, int shift,
-                                                        uint32_t nb, uint32_t* __restrict__ hist) {
-  __shared__ uint32_t h[kRsBins];
-  const uint32_t n = (uint32_t)*n_ptr;  // exact element count (the host sized the grid from a bound)
-  for (int i = threadIdx.x; i < kRsBins; i += kRsThreads) h[i] = 0;
-  __syncthreads();
-  const uint32_t base = blockIdx.x * kRsTile;
-  for (uint32_t i = threadIdx.x; i < kRsTile; i += kRsThreads) {
-    uint32_t g = base + i;
-    if (g < n) atomicAdd(&h[rs_digit(keys[g], shift)], 1u);
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < kRsBins; i += kRsThreads) hist[i * nb + blockIdx.x] = h[i];
 }
 
 // Generic one-block exclusive scan (in place).  Each thread owns 8 consecutive
@@ -100,40 +87,138 @@ __global__ void __launch_bounds__(1024) k_scan_u32(uint32_t* __restrict__ data, 
   if (tid == 0 && total_out) *total_out = carry_s;
 }
 
+// ---- onesweep-style passes -----------------------------------------------------------------
+
+constexpr int kRsMaxPasses = 9;  // 63 key bits / 7
+
+// Scratch of one pass inside the zero-initialised region (32-bit words).
+struct RsPassScratch {
+  uint32_t* tile_hist;  // [nb][kRsBins] digit counts per tile, stored as count + 1 (0 = not published yet)
+  uint32_t* ticket;     // [1]  next tile to hand out
+  uint32_t* ghist;      // [kRsBins] digit counts over all keys (k_rs_ghist)
+};
+__host__ __device__ inline size_t rs_pass_words(uint32_t nb) {
+  return ((size_t(kRsBins) * nb + kRsBins + 1) + 3) & ~size_t(3);
+}
+__host__ __device__ inline RsPassScratch rs_pass_scratch(uint32_t* base, uint32_t nb) {
+  RsPassScratch r;
+  r.tile_hist = base;                      // 16-byte aligned: region sizes are multiples of 4 words
+  r.ghist = base + size_t(kRsBins) * nb;
+  r.ticket = r.ghist + kRsBins;
+  return r;
+}
+
+// Digit histograms of every pass in one read of the keys.
 template <typename KeyT>
-__global__ void __launch_bounds__(kRsThreads) k_rs_scatter(const KeyT* __restrict__ keys_in,
-                                                           const uint32_t* __restrict__ vals_in,
-                                                           const unsigned long long* __restrict__ n_ptr,
-                                                           int shift, uint32_t nb,
-                                                           const uint32_t* __restrict__ hist /* raw [bin][tile] */,
-                                                           KeyT* __restrict__ keys_out,
-                                                           uint32_t* __restrict__ vals_out) {
+__global__ void __launch_bounds__(kRsThreads) k_rs_ghist(const KeyT* __restrict__ keys,
+                                                         const unsigned long long* __restrict__ n_ptr, int first_bit,
+                                                         int passes, uint32_t nb, uint32_t* __restrict__ zbase) {
+  __shared__ uint32_t h[kRsMaxPasses][kRsBins];
+  const uint32_t n = (uint32_t)*n_ptr;
+  for (int i = threadIdx.x; i < passes * kRsBins; i += kRsThreads) (&h[0][0])[i] = 0;
+  __syncthreads();
+  const uint32_t base = blockIdx.x * kRsTile;
+  for (uint32_t i = threadIdx.x; i < kRsTile; i += kRsThreads) {
+    const uint32_t g = base + i;
+    if (g < n) {
+      const KeyT k = keys[g];
+      for (int p = 0; p < passes; ++p) atomicAdd(&h[p][rs_digit(k, first_bit + p * kRsBits)], 1u);
+    }
+  }
+  __syncthreads();
+  const size_t stride = rs_pass_words(nb);
+  for (int i = threadIdx.x; i < passes * kRsBins; i += kRsThreads) {
+    const uint32_t c = (&h[0][0])[i];
+    if (c) atomicAdd(rs_pass_scratch(zbase + (i / kRsBins) * stride, nb).ghist + (i % kRsBins), c);
+  }
+}
+
+// 16-byte load that always goes to L2 (the words are written by other SMs during this kernel).
+__device__ __forceinline__ uint4 rs_ld_volatile_v4(const uint32_t* p) {
+  uint4 v;
+  asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+  return v;
+}
+
+template <typename KeyT>
+__global__ void __launch_bounds__(kRsThreads) k_rs_pass(const KeyT* __restrict__ keys_in,
+                                                        const uint32_t* __restrict__ vals_in,
+                                                        const unsigned long long* __restrict__ n_ptr, int shift,
+                                                        uint32_t nb, RsPassScratch sc, KeyT* __restrict__ keys_out,
+                                                        uint32_t* __restrict__ vals_out) {
   __shared__ uint32_t wcnt[kRsWarps][kRsBins];  // per-warp digit counts, then running offsets
   __shared__ uint32_t dig_base[kRsBins];        // global base of (digit, this tile)
   __shared__ uint32_t wsum[kRsThreads / 32];
+  __shared__ uint32_t part[kRsWarps][kRsBins];  // look-back partial sums per warp
+  __shared__ uint32_t s_tile;
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t n = (uint32_t)*n_ptr;
+  // A pass in which every key has the same digit is the identity permutation (the sort is
+  // stable): just move the tile to the output buffer.  Typical for the low fraction bits when
+  // capacities are powers of two.  All blocks see the same histogram, so all take this branch.
+  if (n != 0 && sc.ghist[rs_digit(keys_in[0], shift)] == n) {
+    const uint32_t base = blockIdx.x * kRsTile;
+    for (uint32_t i = tid; i < kRsTile; i += kRsThreads) {
+      const uint32_t idx = base + i;
+      if (idx < n) {
+        keys_out[idx] = keys_in[idx];
+        vals_out[idx] = vals_in ? vals_in[idx] : idx;
+      }
+    }
+    return;
+  }
+  if (tid == 0) s_tile = atomicAdd(sc.ticket, 1u);  // tiles are handed out in start order
   for (int i = tid; i < kRsWarps * kRsBins; i += kRsThreads) (&wcnt[0][0])[i] = 0;
   __syncthreads();
-  const uint32_t wbase = blockIdx.x * kRsTile + warp * kRsItemsPerWarp;
+  const uint32_t tile = s_tile;
+  const uint32_t wbase = tile * kRsTile + warp * kRsItemsPerWarp;
   // pass 1: count digits of my chunk
   for (int g = 0; g < kRsItemsPerWarp; g += 32) {
     uint32_t idx = wbase + g + lane;
     if (idx < n) atomicAdd(&wcnt[warp][rs_digit(keys_in[idx], shift)], 1u);
   }
   __syncthreads();
-  // This tile's global base per digit, straight from the raw tile histograms (no separate
-  // scan kernel): base(d) = sum of all tiles' counts of smaller digits
-  //                        + counts of digit d in earlier tiles.
+  // Publish this tile's digit counts as count + 1: every word validates itself (0 = not there
+  // yet), so no flag and no fence are needed.
+  if (tid < kRsBins) {
+    uint32_t c = 0;
+#pragma unroll
+    for (int w = 0; w < kRsWarps; ++w) c += wcnt[w][tid];
+    __stcg(sc.tile_hist + size_t(tile) * kRsBins + tid, c + 1);
+  }
+  // Look back: counts of every digit in the LOWER tiles (all of them are running: they drew their
+  // ticket before us).  Warp w takes tiles w, w + 8, ...; a lane owns four digits (one 16-byte
+  // load per tile); four tiles are in flight per round.
+  {
+    uint4 acc = make_uint4(0, 0, 0, 0);
+    static_assert(kRsBins == 128, "a lane owns kRsBins / 32 = 4 digits");
+    for (uint32_t b0 = warp; b0 < tile; b0 += kRsWarps * 4) {
+      uint4 v[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t b = b0 + j * kRsWarps;
+        v[j] = b < tile ? rs_ld_volatile_v4(sc.tile_hist + size_t(b) * kRsBins + lane * 4) : make_uint4(1, 1, 1, 1);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t b = b0 + j * kRsWarps;
+        while (v[j].x == 0 || v[j].y == 0 || v[j].z == 0 || v[j].w == 0) {
+          v[j] = rs_ld_volatile_v4(sc.tile_hist + size_t(b) * kRsBins + lane * 4);
+        }
+        acc.x += v[j].x - 1; acc.y += v[j].y - 1; acc.z += v[j].z - 1; acc.w += v[j].w - 1;
+      }
+    }
+    part[warp][lane * 4 + 0] = acc.x; part[warp][lane * 4 + 1] = acc.y;
+    part[warp][lane * 4 + 2] = acc.z; part[warp][lane * 4 + 3] = acc.w;
+  }
+  __syncthreads();
   {
     uint32_t total = 0, before = 0;
     if (tid < kRsBins) {
-      const uint32_t* row = hist + tid * nb;
-      for (uint32_t b = 0; b < nb; ++b) {
-        const uint32_t c = row[b];
-        before += b < blockIdx.x ? c : 0u;
-        total += c;
-      }
+      total = sc.ghist[tid];
+#pragma unroll
+      for (int w = 0; w < kRsWarps; ++w) before += part[w][tid];
     }
     // exclusive scan of `total` over the digits (kRsBins <= kRsThreads)
     uint32_t x = total;

@@ -14,8 +14,8 @@
 // or, for larger capacities, a 64-bit word holding the reference's own double
 // r/cap (see the kWide branch below).
 //
-// Row s of the table holds the codes for r = run[s] .. run[s]+len-1 followed by
-// a kFull sentinel, so the solver advances a servant by bumping one index.
+// Row s of the table holds the codes for r = run[s] .. run[s]+len-1, followed (row-scan
+// solver only) by a kFull sentinel, so that solver advances a servant by bumping one index.
 // Algorithmic bytes: 4 B written per slot; facts read once (20 B per servant).
 #pragma once
 #include "common.cuh"
@@ -24,10 +24,12 @@ namespace yd {
 
 // Single CTA: row lengths + exclusive scan -> row offsets.  S is a few thousand,
 // so one 1024-thread block with a running carry is launch-latency bound anyway.
+// `sentinel` = 1 appends the kFull end marker to every row (row-scan solver); the slot-stream
+// solver sorts the table and wants slots only.
 __global__ void __launch_bounds__(1024) k_slot_rows(uint32_t S, const DynParams* __restrict__ dp,
                                                     ServantArrays sv, uint32_t* __restrict__ row_off,
                                                     uint32_t* __restrict__ row_len,
-                                                    Counters* __restrict__ counters) {
+                                                    Counters* __restrict__ counters, uint32_t sentinel) {
   __shared__ uint32_t warp_sums[32];
   __shared__ uint32_t carry_s;
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -44,7 +46,7 @@ __global__ void __launch_bounds__(1024) k_slot_rows(uint32_t S, const DynParams*
       if (len > n_requests) len = n_requests;  // a servant cannot win more than n times
       row_len[s] = len;
     }
-    uint32_t v = len + 1;  // + sentinel
+    uint32_t v = len + sentinel;
     if (s >= S) v = 0;
     // inclusive warp scan
     uint32_t x = v;
@@ -88,14 +90,14 @@ __global__ void __launch_bounds__(256) k_slot_fill(uint32_t S, ServantArrays sv,
                                                    const uint32_t* __restrict__ row_len,
                                                    uint32_t* __restrict__ codes,
                                                    unsigned long long* __restrict__ codes_wide,
-                                                   uint32_t* __restrict__ slot_owner) {
+                                                   uint32_t* __restrict__ slot_owner, uint32_t sentinel) {
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t s = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (s >= S) return;
   const uint32_t len = row_len[s], off = row_off[s];
   const uint32_t M = sv.max_tasks[s], P = sv.nproc[s], L = sv.load[s], fl = sv.flags[s];
   const uint32_t r0 = sv.run[s];
-  for (uint32_t i = lane; i <= len; i += 32) {
+  for (uint32_t i = lane; i < len + sentinel; i += 32) {
     if (slot_owner) slot_owner[off + i] = s;  // slot-stream solver: slot -> registry position
     if (i == len) {
       if (kWide) codes_wide[off + i] = ~0ull; else codes[off + i] = kFull;

@@ -627,17 +627,18 @@ uint32_t LaunchSlotTable(yd_sched* s, bool for_stream) {
   const uint32_t S = (uint32_t)s->sv.size();
   cudaStream_t st = s->st;
   yd::ServantArrays arr = s->arrays();
+  const uint32_t sentinel = for_stream ? 0u : 1u;
   yd::k_slot_rows<<<1, 1024, 0, st>>>(S, s->d_dyn.as<yd::DynParams>(), arr, s->d_row_off.as<uint32_t>(),
-                                      s->d_row_len.as<uint32_t>(), s->d_counters.as<Counters>());
+                                      s->d_row_len.as<uint32_t>(), s->d_counters.as<Counters>(), sentinel);
   uint32_t* owner = for_stream ? s->d_slot_owner.as<uint32_t>() : nullptr;
   if (s->wide) {
     yd::k_slot_fill<true><<<(S + 7) / 8, 256, 0, st>>>(S, arr, s->d_row_off.as<uint32_t>(),
                                                        s->d_row_len.as<uint32_t>(), nullptr,
-                                                       s->d_codes.as<unsigned long long>(), owner);
+                                                       s->d_codes.as<unsigned long long>(), owner, sentinel);
   } else {
     yd::k_slot_fill<false><<<(S + 7) / 8, 256, 0, st>>>(S, arr, s->d_row_off.as<uint32_t>(),
                                                         s->d_row_len.as<uint32_t>(), s->d_codes.as<uint32_t>(),
-                                                        nullptr, owner);
+                                                        nullptr, owner, sentinel);
   }
   return 2;
 }
@@ -684,17 +685,21 @@ uint32_t LaunchSort(yd_sched* s, int first_bit, int last_bit) {
   cudaStream_t st = s->st;
   const uint32_t nb = s->sort_nb;
   const unsigned long long* n_ptr = &s->d_counters.as<Counters>()->slots;
-  auto hist = [&](int pass) { return reinterpret_cast<uint32_t*>(static_cast<char*>(s->d_zero.p) + s->z_hist_off[pass]); };
+  uint32_t* zbase = reinterpret_cast<uint32_t*>(static_cast<char*>(s->d_zero.p) + s->z_hist_off[0]);
+  const size_t stride = yd::rs_pass_words(nb);
+  const int passes = (last_bit - first_bit) / yd::kRsBits + 1;
   const KeyT* kin = s->d_codes.as<KeyT>();
   const uint32_t* vin = nullptr;
-  int cur = 0, pass = 0;
-  uint32_t launches = 0;
-  for (int shift = first_bit; shift <= last_bit; shift += yd::kRsBits, ++pass) {
+  int cur = 0;
+  // digit histograms of all passes in one read, then one kernel per pass
+  yd::k_rs_ghist<KeyT><<<nb, yd::kRsThreads, 0, st>>>(kin, n_ptr, first_bit, passes, nb, zbase);
+  uint32_t launches = 1;
+  for (int pass = 0; pass < passes; ++pass) {
     KeyT* kout = s->d_sort_k[cur].as<KeyT>();
     uint32_t* vout = s->d_sort_v[cur].as<uint32_t>();
-    yd::k_rs_hist<KeyT><<<nb, yd::kRsThreads, 0, st>>>(kin, n_ptr, shift, nb, hist(pass));
-    yd::k_rs_scatter<KeyT><<<nb, yd::kRsThreads, 0, st>>>(kin, vin, n_ptr, shift, nb, hist(pass), kout, vout);
-    launches += 2;
+    yd::k_rs_pass<KeyT><<<nb, yd::kRsThreads, 0, st>>>(kin, vin, n_ptr, first_bit + pass * yd::kRsBits, nb,
+                                                       yd::rs_pass_scratch(zbase + pass * stride, nb), kout, vout);
+    launches += 1;
     kin = kout;
     vin = vout;
     cur ^= 1;
@@ -715,7 +720,7 @@ void PrepareStreamBuffers(yd_sched* s, uint32_t Nb, size_t slot_b) {
   s->sort_nb = (uint32_t)((slot_b + yd::kRsTile - 1) / yd::kRsTile);
   const int passes = s->wide ? 9 : 4;
   size_t off = 0;
-  for (int p = 0; p < passes; ++p) { s->z_hist_off[p] = off; off += size_t(yd::kRsBins) * s->sort_nb * 4; }
+  for (int p = 0; p < passes; ++p) { s->z_hist_off[p] = off; off += yd::rs_pass_words(s->sort_nb) * 4; }
   s->z_cls_off = off;
   off += (yd::kClsTableSize + 8 + 6 * yd::kMaxClasses + 3 * size_t(s->n_comps) + 8) * 4;
   const uint32_t n_tiles = (uint32_t)((slot_b + yd::kListTile - 1) / yd::kListTile);
