@@ -197,6 +197,15 @@ void yd_on_expiration_timer(yd_sched* s, int64_t now_ns);
  * returned had the calls been issued one after another. */
 void yd_wait_for_starting_new_tasks(yd_sched* s, int64_t now_ns, const yd_task_req* reqs,
                                     size_t n, yd_grant* out);
+
+/* The same call with the queue already in HBM.  A front end that receives requests over a
+ * window of time can stage them as they arrive and start the solve when the batch closes:
+ * yd_stage_requests copies reqs[0..n) into the handle's device-side queue (synchronously: the
+ * array may be reused at once); yd_wait_for_staged_tasks decides the first n staged requests
+ * exactly like yd_wait_for_starting_new_tasks would.  Staged requests stay valid until the
+ * next yd_stage_requests / yd_wait_for_starting_new_tasks(reqs != NULL) call. */
+void yd_stage_requests(yd_sched* s, const yd_task_req* reqs, size_t n);
+void yd_wait_for_staged_tasks(yd_sched* s, int64_t now_ns, size_t n, yd_grant* out);
 /* n TaskDispatcher::KeepTaskAlive calls (cc:142-165); ok_out[i] is the bool. */
 void yd_keep_task_alive(yd_sched* s, int64_t now_ns, const uint64_t* task_ids, size_t n,
                         int64_t new_expires_in_ns, uint8_t* ok_out);

@@ -568,3 +568,14 @@ extern "C" int yd_running_index_entry(yd_sched* s, uint32_t i, yd_running_task* 
   if (out) *out = yd_running_task{t.servant_task_id, t.task_grant_id, t.servant_location.c_str(), t.task_digest.c_str()};
   return 1;
 }
+
+// ---- staged queue (yd_stage_requests / yd_wait_for_staged_tasks): host-side copy ----------
+namespace { std::unordered_map<yd_sched*, std::vector<yd_task_req>> g_staged; }
+extern "C" void yd_stage_requests(yd_sched* s, const yd_task_req* reqs, size_t n) {
+  g_staged[s].assign(reqs, reqs + n);
+}
+extern "C" void yd_wait_for_staged_tasks(yd_sched* s, int64_t now_ns, size_t n, yd_grant* out) {
+  auto& q = g_staged[s];
+  if (n > q.size()) { std::fprintf(stderr, "ydsched: %zu requests asked for, %zu staged\n", n, q.size()); std::abort(); }
+  yd_wait_for_starting_new_tasks(s, now_ns, q.data(), n, out);
+}

@@ -434,3 +434,14 @@ extern "C" int yd_running_index_entry(yd_sched* s, uint32_t i, yd_running_task* 
 // SchedulerServiceImpl's other handlers: host logic over the ABI above (the handlers themselves need
 // flare's RPC controller and protobuf, so scheduler_service_impl.cc cannot be compiled here).
 #include "ydservice_impl.inc"
+
+// ---- staged queue (yd_stage_requests / yd_wait_for_staged_tasks): host-side copy ----------
+namespace { std::unordered_map<yd_sched*, std::vector<yd_task_req>> g_staged; }
+extern "C" void yd_stage_requests(yd_sched* s, const yd_task_req* reqs, size_t n) {
+  g_staged[s].assign(reqs, reqs + n);
+}
+extern "C" void yd_wait_for_staged_tasks(yd_sched* s, int64_t now_ns, size_t n, yd_grant* out) {
+  auto& q = g_staged[s];
+  if (n > q.size()) { std::fprintf(stderr, "ydsched: %zu requests asked for, %zu staged\n", n, q.size()); std::abort(); }
+  yd_wait_for_starting_new_tasks(s, now_ns, q.data(), n, out);
+}

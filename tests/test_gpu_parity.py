@@ -379,3 +379,31 @@ def test_service_layer_over_cuda_backend(make_dispatcher):
 
     for case in CASES:
         assert _same(case(make_dispatcher("cuda")), case(make_dispatcher("port"))), case.__name__
+
+
+@pytest.mark.gpu
+def test_staged_queue_equals_direct_call(make_dispatcher):
+    """yd_stage_requests + yd_wait_for_staged_tasks == yd_wait_for_starting_new_tasks, also for a
+    prefix of the staged queue and after an un-staged call in between."""
+    import numpy as np
+
+    w = S.config2(30_000, 600, 8, variant="random")
+    outs = []
+    for mode in ("direct", "staged"):
+        d = make_dispatcher("cuda")
+        w.register(d)
+        reqs = w.build_requests(d)
+        res = []
+        if mode == "direct":
+            res.append(d.wait_for_starting_new_tasks(reqs[:20_000].copy(), 0.5).copy())
+            res.append(d.wait_for_starting_new_tasks(reqs[20_000:].copy(), 0.6).copy())
+            res.append(d.wait_for_starting_new_tasks(reqs[:5_000].copy(), 0.7).copy())
+        else:
+            d.stage_requests(reqs)
+            res.append(d.wait_for_staged_tasks(20_000, 0.5).copy())          # a prefix of the staged queue
+            res.append(d.wait_for_starting_new_tasks(reqs[20_000:].copy(), 0.6).copy())  # un-staged call in between
+            d.stage_requests(reqs[:5_000].copy())
+            res.append(d.wait_for_staged_tasks(5_000, 0.7).copy())
+        outs.append(res)
+    for a, b in zip(*outs):
+        assert (a == b).all()

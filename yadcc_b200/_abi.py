@@ -169,6 +169,8 @@ PROTOTYPES = [
     ("yd_get_running_tasks", C.c_size_t, [_P, C.POINTER(yd_running_task), C.c_size_t]),
     ("yd_on_expiration_timer", None, [_P, C.c_int64]),
     ("yd_wait_for_starting_new_tasks", None, [_P, C.c_int64, _P, C.c_size_t, _P]),
+    ("yd_stage_requests", None, [_P, _P, C.c_size_t]),
+    ("yd_wait_for_staged_tasks", None, [_P, C.c_int64, C.c_size_t, _P]),
     ("yd_keep_task_alive", None, [_P, C.c_int64, _P, C.c_size_t, C.c_int64, _P]),
     ("yd_free_tasks", None, [_P, _P, C.c_size_t]),
     ("yd_wait_for_starting_task_rpcs", C.c_size_t, [_P, C.c_int64, _P, C.c_size_t, _P, _P, C.c_size_t]),

@@ -172,6 +172,7 @@ struct yd_sched {
   DevBuf d_list, d_rcls, d_rrank, d_rank_cnt, d_rq;
   bool stream_attr_set = false;
   size_t res_words = 0;  // u32 words of res[] in d_res (the class-table keys follow)
+  size_t staged_n = 0;   // requests placed in d_reqs by yd_stage_requests
 
   // lease ring
   DevBuf d_t_exp, d_t_srv, d_t_flags;
@@ -948,9 +949,30 @@ void DumpStreamState(yd_sched* s, uint32_t Nb, size_t slot_b) {
 }  // extern "C++"
 
 // THE HOT PATH: n sequential WaitForStartingNewTask decisions (cc:93-140).
+// Queue staging: a front end can move the pending queue into HBM while RPCs are still
+// arriving and start the solve when the batch closes.
+void yd_stage_requests(yd_sched* s, const yd_task_req* reqs, size_t n) {
+  if (n > 0x40000000ull) { fprintf(stderr, "ydsched: batch too large\n"); abort(); }
+  YD_CUDA_CHECK(cudaSetDevice(s->device));
+  s->staged_n = 0;
+  if (n == 0) return;
+  s->d_reqs.ensure(size_t(NextPow2(n, 1024)) * sizeof(yd_task_req));
+  YD_CUDA_CHECK(cudaMemcpyAsync(s->d_reqs.p, reqs, n * sizeof(yd_task_req), cudaMemcpyHostToDevice, s->st_copy));
+  YD_CUDA_CHECK(cudaStreamSynchronize(s->st_copy));  // `reqs` may be reused by the caller right away
+  s->staged_n = n;
+}
+
+void yd_wait_for_staged_tasks(yd_sched* s, int64_t now_ns, size_t n, yd_grant* out) {
+  if (n == 0) return;
+  if (n > s->staged_n) { fprintf(stderr, "ydsched: %zu requests asked for, %zu staged\n", n, s->staged_n); abort(); }
+  yd_wait_for_starting_new_tasks(s, now_ns, nullptr, n, out);
+}
+
+// `reqs` == NULL: the first n staged requests (yd_stage_requests) are already in HBM.
 void yd_wait_for_starting_new_tasks(yd_sched* s, int64_t now_ns, const yd_task_req* reqs, size_t n,
                                     yd_grant* out) {
   if (n == 0) return;
+  if (!reqs && n > s->staged_n) { fprintf(stderr, "ydsched: NULL request array and nothing staged\n"); abort(); }
   if (n > 0x40000000ull) { fprintf(stderr, "ydsched: batch too large\n"); abort(); }
   YD_CUDA_CHECK(cudaSetDevice(s->device));
   cudaStream_t st = s->st;
@@ -998,8 +1020,11 @@ void yd_wait_for_starting_new_tasks(yd_sched* s, int64_t now_ns, const yd_task_r
   YD_CUDA_CHECK(cudaEventRecord(s->ev[0], st));
   // The request upload runs on its own stream so that the slot table and its sort (which
   // do not read the requests) overlap it; consumers wait on ev_h2d.
-  YD_CUDA_CHECK(cudaMemcpyAsync(s->d_reqs.p, reqs, size_t(N) * sizeof(yd_task_req), cudaMemcpyHostToDevice,
-                                s->st_copy));
+  if (reqs) {
+    YD_CUDA_CHECK(cudaMemcpyAsync(s->d_reqs.p, reqs, size_t(N) * sizeof(yd_task_req), cudaMemcpyHostToDevice,
+                                  s->st_copy));
+    s->staged_n = 0;  // the staging area now holds this batch
+  }
   YD_CUDA_CHECK(cudaEventRecord(s->ev_h2d, s->st_copy));
   bool graphed = false;
   for (int attempt = 0;; ++attempt) {
@@ -1078,7 +1103,7 @@ void yd_wait_for_starting_new_tasks(yd_sched* s, int64_t now_ns, const yd_task_r
   stt.granted = c->granted;
   stt.kernel_launches = launches;
   stt.solver = solver;
-  stt.h2d_bytes = size_t(N) * sizeof(yd_task_req) + sizeof(yd::DynParams);
+  stt.h2d_bytes = (reqs ? size_t(N) * sizeof(yd_task_req) : 0) + sizeof(yd::DynParams);
   stt.d2h_bytes = size_t(N) * sizeof(yd_grant) + sizeof(Counters) + 8;
   s->have_stats = true;
   if (getenv("YDSCHED_DEBUG")) {

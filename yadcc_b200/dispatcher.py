@@ -211,6 +211,19 @@ class TaskDispatcher:
             return TaskAllocation(int(g["task_id"]), self.servant_location(int(g["servant_index"])))
         return WaitStatus(int(g["status"]))
 
+    def stage_requests(self, reqs: np.ndarray) -> None:
+        """Copy the pending queue into HBM ahead of the solve (yd_stage_requests)."""
+        assert reqs.dtype == REQ_DTYPE and reqs.flags.c_contiguous
+        self._lib.yd_stage_requests(self._h, reqs.ctypes.data, reqs.shape[0])
+
+    def wait_for_staged_tasks(self, n: int, now: float = 0.0, out: np.ndarray | None = None) -> np.ndarray:
+        """Decide the first n staged requests (queue already resident in HBM)."""
+        if out is None:
+            out = np.zeros(n, dtype=GRANT_DTYPE)
+        assert out.dtype == GRANT_DTYPE and out.flags.c_contiguous and out.shape[0] >= n
+        self._lib.yd_wait_for_staged_tasks(self._h, _ns(now), n, out.ctypes.data)
+        return out[:n]
+
     def wait_for_starting_task_rpcs(self, rpcs: np.ndarray, now: float = 0.0):
         """A batch of SchedulerServiceImpl::WaitForStartingTask bodies
         (scheduler_service_impl.cc:209-271): returns (results, grants) where
