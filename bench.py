@@ -115,25 +115,16 @@ class ClockSampler(threading.Thread):
 
 
 def ncu_traffic_bytes() -> tuple[float | None, str]:
-    """DRAM bytes per solve from the committed ncu launch list (profiles/), if present."""
-    p = ROOT / "profiles" / "r1d_launches_summary.csv"
-    try:
-        last = p.read_text().strip().splitlines()[-1]
-        mb = float(last.split("DRAM traffic per solve:")[1].split("MB")[0])
-        return mb * 1e6, "profiles/r1d_launches_summary.csv (sum of dram__bytes_read+write over the solve kernels, cold caches)"
-    except Exception:
-        return None, "no ncu capture"
-
-
-def ncu_traffic_bytes() -> tuple[float | None, str]:
-    """DRAM bytes per solve from the committed ncu launch list (profiles/), if present."""
-    p = ROOT / "profiles" / "r1d_launches_summary.csv"
-    try:
-        last = p.read_text().strip().splitlines()[-1]
-        mb = float(last.split("DRAM traffic per solve:")[1].split("MB")[0])
-        return mb * 1e6, "profiles/r1d_launches_summary.csv (sum of dram__bytes_read+write over the solve kernels, cold caches)"
-    except Exception:
-        return None, "no ncu capture"
+    """DRAM bytes per solve from the newest committed ncu launch list (profiles/), if present."""
+    for name in ("r1h_launches_summary.csv", "r1d_launches_summary.csv"):
+        p = ROOT / "profiles" / name
+        try:
+            last = p.read_text().strip().splitlines()[-1]
+            mb = float(last.split("DRAM traffic per solve:")[1].split("MB")[0])
+            return mb * 1e6, f"profiles/{name} (sum of dram__bytes_read+write over the solve kernels, cold caches)"
+        except Exception:
+            continue
+    return None, "no ncu capture"
 
 
 def measured_hbm_peak() -> tuple[float, str]:
