@@ -407,3 +407,39 @@ def test_staged_queue_equals_direct_call(make_dispatcher):
         outs.append(res)
     for a, b in zip(*outs):
         assert (a == b).all()
+
+
+@pytest.mark.gpu
+def test_late_class_bound_overflow_leaves_no_trace(make_dispatcher):
+    """16 classes fit the initial class bound, but three merge-mode components need three more
+    list slots: the overflow is only noticed after the single-class components were marked
+    data-parallel.  The aborted attempt must not count anything (running_tasks, task ids):
+    the retry with a bigger bound has to give the reference's answers and state."""
+    import numpy as np
+    from yadcc_b200 import Servant
+
+    digests = [f"{i:064x}" for i in range(16)]
+    results = []
+    for kind in ("cuda", "port"):
+        d = make_dispatcher(kind)
+        k = 0
+        for c in range(10):  # ten single-digest components
+            for _ in range(6):
+                d.keep_servant_alive(Servant(f"10.5.{k >> 8}.{k & 255}:8335", None, [digests[c]], 8, 16, 0, 0, 64 << 30, 8),
+                                     10.0, now=0.0)
+                k += 1
+        for c in range(3):  # three components coupling two digests each
+            for j in range(8):
+                envs = [digests[10 + 2 * c], digests[11 + 2 * c]] if j % 2 else [digests[10 + 2 * c + j // 4 % 2]]
+                d.keep_servant_alive(Servant(f"10.5.{k >> 8}.{k & 255}:8335", None, envs, 8, 16, 0, 0, 64 << 30, 8),
+                                     10.0, now=0.0)
+                k += 1
+        rng = np.random.default_rng(3)
+        n = 4000
+        for rnd in range(2):
+            reqs = d.make_requests(n, [digests[j] for j in rng.integers(0, 16, n)], "172.16.0.9", 8)
+            results.append(d.wait_for_starting_new_tasks(reqs, 0.5 + rnd).copy())
+            results.append(d.servant_state()["running_tasks"].copy())
+    h = len(results) // 2
+    for a, b in zip(results[:h], results[h:]):
+        assert (a == b).all()

@@ -266,50 +266,40 @@ __device__ __forceinline__ bool decode_slot(const SlotDecode& d, const TopoView&
   return comp != kNone;
 }
 
-// Both list kernels evaluate "slot i belongs to list c" the same way and exchange it through
-// shared-memory ballots, one 32-bit word per (list, warp): the count kernel pop-counts them, the
-// fill kernel turns them into in-tile ranks.  Lists are processed in chunks of kListChunk so
-// the ballots of a chunk cost one barrier, whatever the number of classes.
+// "Slot i belongs to list c" is evaluated ONCE, by the count kernel, as ballots: one 32-bit
+// word per (tile, list, warp), kept in HBM (`balg`, row stride cls_bound lists).  The count
+// kernel pop-counts them; the fill kernel turns the very same words into in-tile ranks, so the
+// two can never disagree about a slot.  Lists are processed in chunks of kListChunk: one or two
+// barriers per chunk, whatever the number of classes.
 constexpr uint32_t kListChunk = 64;
-
-struct ListMembership {  // per-thread view of one sorted slot
-  bool live;
-  uint32_t pos, r, comp, ver, midx;
-  uint32_t mask;  // bit cls_lbit[c]: my servant is eligible for class c of its component (merge payload)
-};
-
-// Ballots for lists [c0, c1) into bal[c - c0][warp]; lists < ncls are classes, the rest are the
-// merge-mode components' pseudo-classes (every slot of the component, once all class bits are known).
-__device__ __forceinline__ void list_ballots(ListMembership& me, const TopoView& t, const ClassTable& ct, uint32_t ncls,
-                                             uint32_t c0, uint32_t c1, uint32_t (*bal)[32], uint32_t lane,
-                                             uint32_t warp) {
-  for (uint32_t c = c0; c < c1; ++c) {
-    bool in;
-    if (c < ncls) {
-      in = me.live && me.comp == ct.cls_comp[c] && me.ver >= ct.cls_mv[c] && servant_has_env(t, me.pos, ct.cls_env[c]);
-      if (in) me.mask |= 1u << (ct.cls_lbit[c] & 31u);
-    } else {
-      in = me.live && me.midx == c - ncls && me.mask != 0;
-    }
-    const uint32_t b = __ballot_sync(0xffffffffu, in);
-    if (lane == 0) bal[c - c0][warp] = b;
-  }
-}
 
 __global__ void __launch_bounds__(kListTile) k_list_count(const unsigned long long* __restrict__ m_ptr, SlotDecode d,
                                                           TopoView t, ClassTable ct, ServantArrays sv,
-                                                          uint32_t n_tiles, uint32_t* __restrict__ counts) {
+                                                          uint32_t n_tiles, uint32_t* __restrict__ counts,
+                                                          uint32_t* __restrict__ balg) {
   __shared__ uint32_t bal[kListChunk][32];
   const uint32_t ncls = min(ct.meta[0], ct.cls_bound);
   const uint32_t nmerge = min(ct.meta[2], ct.cls_bound - ncls);
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  ListMembership me{};
-  me.live = decode_slot(d, t, blockIdx.x * kListTile + tid, (uint32_t)*m_ptr, me.pos, me.r, me.comp);
-  me.ver = me.live ? (uint32_t)sv.version[me.pos] : 0u;
-  me.midx = (me.live && nmerge) ? ct.comp_midx[me.comp] : kNone;
+  uint32_t pos, r, comp;
+  const bool live = decode_slot(d, t, blockIdx.x * kListTile + tid, (uint32_t)*m_ptr, pos, r, comp);
+  const uint32_t ver = live ? (uint32_t)sv.version[pos] : 0u;
+  const uint32_t midx = (live && nmerge) ? ct.comp_midx[comp] : kNone;
+  uint32_t* my_row = balg + size_t(blockIdx.x) * ct.cls_bound * 32;
+  bool any = false;  // my servant is eligible for some class of its component
   for (uint32_t c0 = 0; c0 < ncls + nmerge; c0 += kListChunk) {
     const uint32_t c1 = min(c0 + kListChunk, ncls + nmerge);
-    list_ballots(me, t, ct, ncls, c0, c1, bal, lane, warp);
+    for (uint32_t c = c0; c < c1; ++c) {
+      bool in;
+      if (c < ncls) {  // class list: eligibility (cc:316-344)
+        in = live && comp == ct.cls_comp[c] && ver >= ct.cls_mv[c] && servant_has_env(t, pos, ct.cls_env[c]);
+        any |= in;
+      } else {         // pseudo-class of a merge-mode component: every slot some class can use
+        in = live && midx == c - ncls && any;
+      }
+      const uint32_t b = __ballot_sync(0xffffffffu, in);
+      if (lane == 0) { bal[c - c0][warp] = b; my_row[c * 32 + warp] = b; }
+    }
     __syncthreads();
     for (uint32_t c = c0 + warp; c < c1; c += 32) {
       const uint32_t cnt = __reduce_add_sync(0xffffffffu, (uint32_t)__popc(bal[c - c0][lane]));
@@ -321,22 +311,23 @@ __global__ void __launch_bounds__(kListTile) k_list_count(const unsigned long lo
 
 // counts[] has been exclusive-scanned over (class-major, tile-minor).
 __global__ void __launch_bounds__(kListTile) k_list_fill(const unsigned long long* __restrict__ m_ptr, SlotDecode d,
-                                                         TopoView t, ClassTable ct, ServantArrays sv, uint32_t n_tiles,
+                                                         TopoView t, ClassTable ct, uint32_t n_tiles,
                                                          const uint32_t* __restrict__ offs,
+                                                         const uint32_t* __restrict__ balg,
                                                          uint2* __restrict__ list, uint32_t list_cap) {
   __shared__ uint32_t bal[kListChunk][32];
   __shared__ uint16_t pre[kListChunk][32];  // slots of the list in lower warps of this tile
   const uint32_t ncls = min(ct.meta[0], ct.cls_bound);
   const uint32_t nmerge = min(ct.meta[2], ct.cls_bound - ncls);
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  ListMembership me{};
-  me.live = decode_slot(d, t, blockIdx.x * kListTile + tid, (uint32_t)*m_ptr, me.pos, me.r, me.comp);
-  me.ver = me.live ? (uint32_t)sv.version[me.pos] : 0u;
-  me.midx = (me.live && nmerge) ? ct.comp_midx[me.comp] : kNone;
-  const uint32_t local = me.live ? t.sv_local[me.pos] : 0u;
+  uint32_t pos, r, comp;
+  const bool live = decode_slot(d, t, blockIdx.x * kListTile + tid, (uint32_t)*m_ptr, pos, r, comp);
+  const uint32_t local = live ? t.sv_local[pos] : 0u;
+  const uint32_t* my_row = balg + size_t(blockIdx.x) * ct.cls_bound * 32;
+  uint32_t mask = 0;  // bit cls_lbit[c]: my servant is eligible for class c of its component (merge payload)
   for (uint32_t c0 = 0; c0 < ncls + nmerge; c0 += kListChunk) {
     const uint32_t c1 = min(c0 + kListChunk, ncls + nmerge);
-    list_ballots(me, t, ct, ncls, c0, c1, bal, lane, warp);
+    for (uint32_t i = tid; i < (c1 - c0) * 32; i += kListTile) (&bal[0][0])[i] = my_row[c0 * 32 + i];
     __syncthreads();
     for (uint32_t c = c0 + warp; c < c1; c += 32) {  // exclusive prefix over the warps, per list
       const uint32_t v = __popc(bal[c - c0][lane]);
@@ -352,9 +343,10 @@ __global__ void __launch_bounds__(kListTile) k_list_fill(const unsigned long lon
     for (uint32_t c = c0; c < c1; ++c) {
       const uint32_t word = bal[c - c0][warp];
       if ((word >> lane) & 1u) {
+        if (c < ncls) mask |= 1u << (ct.cls_lbit[c] & 31u);
         const uint32_t dst = offs[c * n_tiles + blockIdx.x] + pre[c - c0][warp] + __popc(word & ((1u << lane) - 1));
         // class list: (servant, running_tasks value of the slot); pseudo-class: (servant, class mask)
-        if (dst < list_cap) list[dst] = make_uint2(local, c < ncls ? me.r : me.mask);
+        if (dst < list_cap) list[dst] = make_uint2(local, c < ncls ? r : mask);
         else ct.meta[1] = 1;  // more (class, slot) pairs than provisioned: the host reruns with solver 1
       }
     }

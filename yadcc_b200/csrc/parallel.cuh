@@ -80,6 +80,9 @@ __global__ void __launch_bounds__(256) k_rank_assign(const DynParams* __restrict
                                                      uint32_t* __restrict__ rq, uint32_t* __restrict__ res) {
   const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= dp->n) return;
+  // Overflow flagged by the class table or the list builder: the host reruns this batch (bigger
+  // class bound or the row-scan solver), so nothing may be decided -- or counted -- now.
+  if (ct.meta[1]) return;
   const uint32_t c = rcls[q];
   if (c == kNone) return;  // not ours: the sequential solver (or nobody) answers it
   if (ct.cls_nelig[c] == 0) { res[q] = kResEnvNotFound; return; }  // cc:105-108

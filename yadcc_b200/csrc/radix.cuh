@@ -35,16 +35,16 @@ __device__ __forceinline__ uint32_t rs_digit(KeyT k, int shift) {
 
 // Generic one-block exclusive scan (in place).  Each thread owns 8 consecutive
 // values (two 16-byte loads), so 8192 values need one block-wide round.  The length
-// is n_static, or (*n_dyn) * per_dyn + 1 when n_dyn != nullptr (sizes that only the
-// device knows, e.g. number of classes x tiles).
+// is n_static, or min(*n_dyn, dyn_cap) * per_dyn + 1 when n_dyn != nullptr (sizes that only
+// the device knows, e.g. number of classes x tiles; dyn_cap = what the buffer was sized for).
 constexpr int kScanItems = 8;
 __global__ void __launch_bounds__(1024) k_scan_u32(uint32_t* __restrict__ data, uint32_t n_static,
                                                    const uint32_t* __restrict__ n_dyn, uint32_t per_dyn,
-                                                   uint32_t* __restrict__ total_out) {
+                                                   uint32_t* __restrict__ total_out, uint32_t dyn_cap) {
   __shared__ uint32_t warp_sums[32];
   __shared__ uint32_t carry_s;
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const uint32_t n = n_dyn ? (*n_dyn) * per_dyn + 1 : n_static;
+  const uint32_t n = n_dyn ? min(*n_dyn, dyn_cap) * per_dyn + 1 : n_static;  // never past what the host sized
   if (tid == 0) carry_s = 0;
   __syncthreads();
   for (uint32_t base = 0; base < n; base += 1024 * kScanItems) {

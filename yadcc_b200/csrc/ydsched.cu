@@ -169,7 +169,7 @@ struct yd_sched {
   cudaStream_t st2 = nullptr, st_copy = nullptr;  // class/rank branch; request upload
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_h2d = nullptr;
   uint32_t cls_bound = 16;  // classes the per-class grids are sized for; grows on demand (<= yd::kMaxClasses)
-  DevBuf d_list, d_rcls, d_rrank, d_rank_cnt, d_rq;
+  DevBuf d_list, d_list_bal, d_rcls, d_rrank, d_rank_cnt, d_rq;
   bool stream_attr_set = false;
   size_t res_words = 0;  // u32 words of res[] in d_res (the class-table keys follow)
   size_t staged_n = 0;   // requests placed in d_reqs by yd_stage_requests
@@ -526,7 +526,7 @@ void yd_destroy(yd_sched* s) {
                     &s->d_t_flags, &s->d_reqs, &s->d_res, &s->d_out, &s->d_blk, &s->d_row_off, &s->d_row_len,
                     &s->d_codes, &s->d_ids, &s->d_ok, &s->d_counters, &s->d_sv_env_off, &s->d_sv_envs,
                     &s->d_comp_mode, &s->d_slot_owner, &s->d_sort_k[0], &s->d_sort_k[1], &s->d_sort_v[0],
-                    &s->d_sort_v[1], &s->d_zero, &s->d_list, &s->d_rcls, &s->d_rrank, &s->d_rank_cnt, &s->d_rq, &s->d_bloom,
+                    &s->d_sort_v[1], &s->d_zero, &s->d_list, &s->d_list_bal, &s->d_rcls, &s->d_rrank, &s->d_rank_cnt, &s->d_rq, &s->d_bloom,
                     &s->d_bloom_keys, &s->d_bloom_out, &s->d_rt_bytes, &s->d_rt_off, &s->d_rt_len, &s->d_rt_ids,
                     &s->d_rt_slots, &s->d_rt_keys, &s->d_rt_out}) {
     b->release();
@@ -730,6 +730,7 @@ void PrepareStreamBuffers(yd_sched* s, uint32_t Nb, size_t slot_b) {
   s->z_bytes = (off + 255) & ~size_t(255);
   s->d_zero.ensure(s->z_bytes);
   s->d_list.ensure(slot_b * 8 * 4);
+  s->d_list_bal.ensure(size_t(n_tiles) * s->cls_bound * 32 * 4);  // membership ballots: (tile, list, warp)
   const uint32_t n_rtiles = (Nb + yd::kRankTile - 1) / yd::kRankTile;
   s->d_rcls.ensure(size_t(Nb) * 4); s->d_rrank.ensure(size_t(Nb) * 4); s->d_rq.ensure(size_t(Nb) * 4);
   s->d_rank_cnt.ensure((size_t(s->cls_bound) * n_rtiles + 1) * 4);
@@ -766,7 +767,7 @@ uint32_t LaunchStream(yd_sched* s, uint32_t N, size_t slot_b, bool capturing) {
                                                          s->d_comp_mode.as<uint32_t>(), n_rtiles,
                                                          s->d_rcls.as<uint32_t>(), s->d_rrank.as<uint32_t>(),
                                                          s->d_rank_cnt.as<uint32_t>());
-  yd::k_scan_u32<<<1, 1024, 0, st2>>>(s->d_rank_cnt.as<uint32_t>(), 0, ct.meta, n_rtiles, nullptr);
+  yd::k_scan_u32<<<1, 1024, 0, st2>>>(s->d_rank_cnt.as<uint32_t>(), 0, ct.meta, n_rtiles, nullptr, ct.cls_bound);
   YD_CUDA_CHECK(cudaEventRecord(s->ev_join, st2));
   launches += 4;
   // branch A: slot table and its sort
@@ -780,9 +781,10 @@ uint32_t LaunchStream(yd_sched* s, uint32_t N, size_t slot_b, bool capturing) {
   const unsigned long long* m_ptr = &s->d_counters.as<Counters>()->slots;
   yd::SlotDecode dec{s->d_sort_v[0].as<uint32_t>(), s->d_slot_owner.as<uint32_t>(), s->d_row_off.as<uint32_t>(),
                      s->d_row_len.as<uint32_t>(), s->d_run.as<uint32_t>()};
-  yd::k_list_count<<<n_tiles, yd::kListTile, 0, st>>>(m_ptr, dec, t, ct, arr, n_tiles, list_cnt);
-  yd::k_scan_u32<<<1, 1024, 0, st>>>(list_cnt, 0, ct.meta + 3, n_tiles, nullptr);
-  yd::k_list_fill<<<n_tiles, yd::kListTile, 0, st>>>(m_ptr, dec, t, ct, arr, n_tiles, list_cnt,
+  yd::k_list_count<<<n_tiles, yd::kListTile, 0, st>>>(m_ptr, dec, t, ct, arr, n_tiles, list_cnt,
+                                                      s->d_list_bal.as<uint32_t>());
+  yd::k_scan_u32<<<1, 1024, 0, st>>>(list_cnt, 0, ct.meta + 3, n_tiles, nullptr, ct.cls_bound);
+  yd::k_list_fill<<<n_tiles, yd::kListTile, 0, st>>>(m_ptr, dec, t, ct, n_tiles, list_cnt, s->d_list_bal.as<uint32_t>(),
                                                      s->d_list.as<uint2>(), (uint32_t)(slot_b * 4));
   launches += 3;
 
