@@ -444,6 +444,7 @@ void yd_free_host(void* p) { std::free(p); }
 }  // extern "C"
 #include "ydsched_rpc_impl.inc"
 #include "ydservice_impl.inc"
+#include "ydwire_impl.inc"
 
 // ---- bloom pre-filter: restatement of flare's SaltedBloomFilter over XXH64 --------------
 // XXH64 is restated from the published xxHash specification (Cyan4973/xxHash, doc/

@@ -434,6 +434,7 @@ extern "C" int yd_running_index_entry(yd_sched* s, uint32_t i, yd_running_task* 
 // SchedulerServiceImpl's other handlers: host logic over the ABI above (the handlers themselves need
 // flare's RPC controller and protobuf, so scheduler_service_impl.cc cannot be compiled here).
 #include "ydservice_impl.inc"
+#include "ydwire_impl.inc"
 
 // ---- staged queue (yd_stage_requests / yd_wait_for_staged_tasks): host-side copy ----------
 namespace { std::unordered_map<yd_sched*, std::vector<yd_task_req>> g_staged; }

@@ -20,6 +20,7 @@ def header_symbols(header="ydsched.h"):
 def test_prototypes_cover_header():
     assert header_symbols() == sorted(name for name, _, _ in _abi.PROTOTYPES)
     assert header_symbols("ydservice.h") == sorted(name for name, _, _ in _abi.SERVICE_PROTOTYPES)
+    assert header_symbols("ydwire.h") == sorted(name for name, _, _ in _abi.WIRE_PROTOTYPES)
 
 
 @pytest.mark.parametrize("lib", [CUDA_LIB, PORT_LIB, REF_LIB], ids=["cuda", "port", "ref"])
@@ -29,7 +30,7 @@ def test_library_exports_every_symbol(lib, port_lib):
             pytest.skip("reference build not present")
         pytest.fail(f"{lib} missing: run make / __graft_entry__.build()")
     h = ctypes.CDLL(str(lib))
-    for name in header_symbols() + header_symbols("ydservice.h"):
+    for name in header_symbols() + header_symbols("ydservice.h") + header_symbols("ydwire.h"):
         assert hasattr(h, name), f"{lib} does not export {name}"
 
 

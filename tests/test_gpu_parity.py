@@ -443,3 +443,13 @@ def test_late_class_bound_overflow_leaves_no_trace(make_dispatcher):
     h = len(results) // 2
     for a, b in zip(results[:h], results[h:]):
         assert (a == b).all()
+
+
+@pytest.mark.gpu
+def test_wire_front_end_over_cuda_backend(make_dispatcher):
+    """FlareStd frames in, frames out (include/ydwire.h) over the CUDA dispatcher: every response
+    frame equals, byte for byte, the one produced over the CPU restatement."""
+    pytest.importorskip("google.protobuf")
+    from wire_cases import run_wire_scenario
+
+    assert run_wire_scenario(make_dispatcher, "cuda") == run_wire_scenario(make_dispatcher, "port")

@@ -136,6 +136,16 @@ class yd_heartbeat_response(C.Structure):
     ]
 
 
+class yd_wire_in(C.Structure):
+    _fields_ = [("data", C.c_void_p), ("len", C.c_size_t), ("remote_ip", C.c_char_p), ("remote_is_ipv6", C.c_uint32),
+                ("reserved", C.c_uint32)]
+
+
+class yd_wire_out(C.Structure):
+    _fields_ = [("consumed", C.c_size_t), ("offset", C.c_size_t), ("len", C.c_size_t), ("verdict", C.c_int32),
+                ("status", C.c_int32)]
+
+
 class yd_solve_stats(C.Structure):
     _fields_ = [
         ("total_ms", C.c_double),
@@ -216,7 +226,7 @@ def load_library(path: os.PathLike | str | None = None) -> C.CDLL:
             "yadcc_b200 has no CPU fallback."
         )
     lib = C.CDLL(str(p), mode=C.RTLD_LOCAL)
-    for name, restype, argtypes in PROTOTYPES + SERVICE_PROTOTYPES:
+    for name, restype, argtypes in PROTOTYPES + SERVICE_PROTOTYPES + WIRE_PROTOTYPES:
         fn = getattr(lib, name)  # AttributeError if the symbol is missing
         fn.restype = restype
         fn.argtypes = argtypes
@@ -235,4 +245,13 @@ SERVICE_PROTOTYPES = [
     ("yd_service_keep_task_alive", C.c_int, [_P, C.c_int64, C.c_char_p, C.c_uint32, _P, C.c_size_t, _P]),
     ("yd_service_free_task", C.c_int, [_P, C.c_char_p, _P, C.c_size_t]),
     ("yd_service_get_running_tasks", C.c_size_t, [_P, C.POINTER(yd_running_task), C.c_size_t]),
+]
+
+# Every symbol include/ydwire.h declares.
+WIRE_PROTOTYPES = [
+    ("yd_wire_handle_frames", C.c_size_t,
+     [_P, C.c_int64, C.POINTER(yd_wire_in), C.c_size_t, _P, C.c_size_t, C.POINTER(yd_wire_out)]),
+    ("yd_wire_call", C.c_int,
+     [_P, C.c_int64, C.c_char_p, C.c_char_p, C.c_uint32, _P, C.c_size_t, _P, C.c_size_t, C.POINTER(C.c_size_t),
+      C.POINTER(C.c_char_p)]),
 ]

@@ -1359,6 +1359,7 @@ void yd_free_host(void* p) {
 }  // extern "C"
 #include "ydsched_rpc_impl.inc"
 #include "ydservice_impl.inc"
+#include "ydwire_impl.inc"
 
 // ---- compilation-cache bloom pre-filter (bloom.cuh) ------------------------------------------
 extern "C" {

@@ -133,3 +133,36 @@ class SchedulerService:
         return [RunningTask(int(arr[i].servant_task_id), int(arr[i].task_grant_id),
                             (arr[i].servant_location or b"").decode(), (arr[i].task_digest or b"").decode())
                 for i in range(n)]
+
+    # -- FlareStd wire front end (include/ydwire.h) ---------------------------------
+    def handle_frames(self, frames, *, now: float = 0.0, out_cap: int | None = None):
+        """frames: [(bytes, remote_ip[, is_ipv6])], the first frame of each is handled, in order
+        (consecutive WaitForStartingTask frames as one batched solve).  Returns a list of
+        (verdict, consumed, status, response_bytes)."""
+        n = len(frames)
+        ins = (_abi.yd_wire_in * max(n, 1))()
+        keep = []
+        for i, f in enumerate(frames):
+            data, ip = f[0], f[1]
+            buf = C.create_string_buffer(bytes(data), len(data))
+            ipb = ip.encode()
+            keep.append((buf, ipb))
+            ins[i] = _abi.yd_wire_in(C.cast(buf, C.c_void_p), len(data), ipb, int(f[2]) if len(f) > 2 else 0, 0)
+        cap = out_cap if out_cap is not None else 65536 * max(n, 1)
+        out = C.create_string_buffer(cap)
+        outs = (_abi.yd_wire_out * max(n, 1))()
+        total = self._lib.yd_wire_handle_frames(self._h, _ns(now), ins, n, C.cast(out, C.c_void_p), cap, outs)
+        if total == (1 << 64) - 1:
+            raise ValueError("response buffer too small")
+        return [(outs[i].verdict, outs[i].consumed, outs[i].status, out.raw[outs[i].offset:outs[i].offset + outs[i].len])
+                for i in range(n)]
+
+    def call(self, method: str, body: bytes, remote_ip: str, *, now: float = 0.0, remote_is_ipv6: bool = False):
+        """One call at message-body level (yd_wire_call): returns (status, description, response bytes)."""
+        cap = 1 << 20
+        out = C.create_string_buffer(cap)
+        n = C.c_size_t(0)
+        desc = C.c_char_p()
+        st = self._lib.yd_wire_call(self._h, _ns(now), method.encode(), remote_ip.encode(), int(remote_is_ipv6), body,
+                                    len(body), C.cast(out, C.c_void_p), cap, C.byref(n), C.byref(desc))
+        return st, (desc.value or b"").decode(), out.raw[:n.value]
