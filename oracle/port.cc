@@ -97,6 +97,7 @@ struct yd_sched {
   std::vector<std::shared_ptr<ServantRec>> servants;  // discovery order == tie-break order
   std::unordered_map<std::uint64_t, TaskRec> tasks;
   std::uint64_t next_task_id = 0;  // task_dispatcher.h:218
+  std::uint64_t id_stride = 1, id_offset = 0;
   // RunningTaskBookkeeper, running_task_bookkeeper.h:41-42.  Same container and
   // same operation sequence as the reference, so iteration order matches too.
   std::unordered_map<std::string, std::vector<RunningTaskRec>> running_tasks;
@@ -177,7 +178,9 @@ struct yd_sched {
     auto& s = servants[pick];
     ++s->running_tasks;  // :123-124
     ++s->ever_assigned_tasks;
-    std::uint64_t id = next_task_id++;  // :127
+    // :127; sharded deployments hand out local * stride + offset (yd_config.id_stride / id_offset):
+    // the registry is keyed by the external id, so other shards' ids are simply unknown here
+    std::uint64_t id = (next_task_id++) * id_stride + id_offset;
     TaskRec& t = tasks[id];
     t.servant = s;
     t.started_at = now;
@@ -208,6 +211,11 @@ yd_sched* yd_create(const yd_config* cfg) {
   }
   s->ips.emplace_back();  // id 0 == YD_IP_NONE == ""
   s->ip_ids.emplace("", 0);
+  if (cfg->id_stride > 1) {
+    if (cfg->id_offset >= cfg->id_stride) { delete s; return nullptr; }
+    s->id_stride = cfg->id_stride;
+    s->id_offset = cfg->id_offset;
+  }
   return s;
 }
 
@@ -408,7 +416,7 @@ int yd_get_servant_personality(yd_sched* s, uint32_t idx, yd_servant* out) {
   return 1;
 }
 
-uint64_t yd_next_task_id(yd_sched* s) { return s->next_task_id; }
+uint64_t yd_next_task_id(yd_sched* s) { return s->next_task_id * s->id_stride + s->id_offset; }
 uint64_t yd_num_tasks(yd_sched* s) { return s->tasks.size(); }
 
 // DumpInternals summary, task_dispatcher.cc:540-547,581-584,603-612.

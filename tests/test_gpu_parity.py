@@ -266,6 +266,15 @@ def test_strided_task_ids(make_dispatcher):
     other = int(outs[1]["task_id"][ok][60])
     unknown = shard[0].notify_servant_running_tasks(loc, [RunningTask(1, mine, loc, "a"), RunningTask(2, other, loc, "b")])
     assert unknown == [other]
+    # the CPU restatement implements the same option: identical ids, answers and state
+    twin = make_dispatcher("port", id_stride=4, id_offset=1)
+    w.register(twin)
+    g = twin.wait_for_starting_new_tasks(w.build_requests(twin), 0.1)
+    assert (g == outs[0]).all()
+    assert (twin.keep_tasks_alive(mixed, 5.0, now=0.2) == np.concatenate([np.ones(50, bool), np.zeros(73, bool)])).all()
+    twin.free_tasks(mixed)
+    assert twin.notify_servant_running_tasks(loc, [RunningTask(1, mine, loc, "a"), RunningTask(2, other, loc, "b")]) == [other]
+    assert (twin.servant_state() == shard[0].servant_state()).all() and twin.next_task_id() == shard[0].next_task_id()
 
 
 @pytest.mark.parametrize("seed", range(2))

@@ -59,7 +59,8 @@ def _rank_main(rank, world, port, out_dir, id_mode):
     from yadcc_b200.sharded import ShardedDispatcher
 
     digests, servants, req_digest, req_ip, req_mv = _workload()
-    d = TaskDispatcher(str(PORT_LIB))
+    strided = id_mode == "strided"
+    d = TaskDispatcher(str(PORT_LIB), id_stride=world if strided else 0, id_offset=rank if strided else 0)
     sd = ShardedDispatcher(d, rank, world, device=torch.device("cpu"), digest_owner=_owner, id_mode=id_mode)
     for sv in servants:
         sd.keep_servant_alive(sv, 10.0, now=0.0)
@@ -76,13 +77,18 @@ def _rank_main(rank, world, port, out_dir, id_mode):
         # free every third grant through the GLOBAL ids, then renew the rest
         ok = g["status"] == 2
         sd.free_tasks(g["task_id"][ok][::3])
+        if strided:  # ids of the other shard are ignored, not mistaken for local ones
+            foreign = g["task_id"][ok][1::3] - np.uint64(rank) + np.uint64((rank + 1) % world)
+            assert not sd.keep_tasks_alive(foreign, 5.0, now=0.6 + rnd).any()
+            sd.free_tasks(foreign)
+            assert sd.keep_tasks_alive(g["task_id"][ok][1::3], 5.0, now=0.6 + rnd).all()
     np.save(Path(out_dir) / f"rank{rank}.npy", np.asarray(results, dtype=object), allow_pickle=True)
     assert (sd.collective_bytes > 0) == (id_mode == "fifo")
     dist.barrier()
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("id_mode", ["fifo"])
+@pytest.mark.parametrize("id_mode", ["fifo", "strided"])
 def test_two_ranks_equal_one_scheduler(tmp_path, port_lib, id_mode):
     import torch.multiprocessing as mp
     from yadcc_b200 import TaskDispatcher
@@ -110,12 +116,21 @@ def test_two_ranks_equal_one_scheduler(tmp_path, port_lib, id_mode):
             seen[mine] = True
             assert (status == g["status"][mine]).all()
             ok = status == 2
-            assert (task_id[ok] == g["task_id"][mine][ok]).all(), "global task ids"
+            if id_mode == "fifo":
+                assert (task_id[ok] == g["task_id"][mine][ok]).all(), "global task ids"
+            else:  # local FIFO number * world + rank: unique, routable, in the shard's own grant order
+                assert (task_id[ok] % world == r).all()
+                local = task_id[ok] // world
+                assert (np.diff(local.astype(np.int64)) == 1).all() and (rnd > 0 or local[0] == 0)
             assert (rloc[ok] == loc[mine][ok]).all()
         # requests nobody owns are exactly the unknown-digest ones: EnvironmentNotFound
         assert (g["status"][~seen] == 0).all()
         # mirror the per-rank "free every third of MY grants"
         for r in range(world):
             mine, status, task_id, _ = ranks[r][rnd]
+            mine = np.asarray(mine, dtype=np.int64)
             status, task_id = np.asarray(status, dtype=np.uint32), np.asarray(task_id, dtype=np.uint64)
-            one.free_tasks(task_id[status == 2][::3])
+            if id_mode == "fifo":
+                one.free_tasks(task_id[status == 2][::3])
+            else:  # the same requests' grants in the single scheduler's numbering
+                one.free_tasks(g["task_id"][mine][status == 2][::3])
