@@ -2,6 +2,7 @@
 the committed golden vectors generated from the reference.  Bit-exact: statuses,
 task ids, servant indices, per-servant bookkeeping, unknown-id lists."""
 import json
+import os
 from pathlib import Path
 
 import numpy as np
@@ -53,6 +54,15 @@ def test_fuzz_large_components(make_dispatcher, seed, solver):
     _parity(make_dispatcher,
             lambda d: S.fuzz_stream(d, seed, n_servants=300 + 150 * (seed % 4), n_events=40, max_batch=600),
             solver=solver)
+
+
+@pytest.mark.parametrize("seed", range(2000, 2000 + int(os.environ.get("YD_SOAK_SEEDS", "0"))))
+def test_fuzz_soak(make_dispatcher, seed):
+    """Opt-in soak (YD_SOAK_SEEDS=n): more large-component / many-class streams through the
+    slot-stream solver than the default suite runs."""
+    _parity(make_dispatcher,
+            lambda d: S.fuzz_stream(d, seed, n_servants=40 + 97 * (seed % 9), n_events=50, max_batch=200 + 300 * (seed % 4),
+                                    wide=(seed % 7 == 0)), solver=2)
 
 
 @pytest.mark.parametrize("solver", [1, 2], ids=SOLVERS.get)
