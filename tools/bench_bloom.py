@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """Throughput of the GPU bloom pre-filter next to flare's own
-SaltedBloomFilter on the host (oracle/_ref, or the restatement if that build is absent).
+SaltedBloomFilter on the host when --cpu-library names a CPU build of the same C ABI (the
+test oracle; this script never picks one up by itself).
 Host buffers, copies included (yd_bloom_possibly_contains is synchronous)."""
 import json
 import sys
@@ -32,12 +33,17 @@ def run(lib, n, reps):
 
 
 if __name__ == "__main__":
-    n = int(sys.argv[1]) if len(sys.argv) > 1 else 1_000_000
-    ref = ROOT / "oracle" / "_ref" / "libydref.so"
-    if not ref.exists():
-        ref = ROOT / "oracle" / "libydoracle.so"
+    import argparse
+
+    ap = argparse.ArgumentParser()
+    ap.add_argument("keys", nargs="?", type=int, default=1_000_000)
+    ap.add_argument("--cpu-library", default=None, help="CPU library speaking the same C ABI, timed beside the GPU")
+    args = ap.parse_args()
+    n = args.keys
     gpu, hit, klen = run(None, n, 10)
-    cpu, _, _ = run(str(ref), min(n, 200_000), 3)
-    print(json.dumps({"metric": "bloom_lookups_per_sec", "keys": n, "key_bytes": klen, "hashes": 10, "bits": 1 << 25,
-                      "gpu_e2e_keys_per_s": gpu, "gpu_e2e_GBps_of_keys": gpu * klen / 1e9, "hit_rate": hit,
-                      "cpu_reference_keys_per_s": cpu, "cpu_impl": ref.name}))
+    line = {"metric": "bloom_lookups_per_sec", "keys": n, "key_bytes": klen, "hashes": 10, "bits": 1 << 25,
+            "gpu_e2e_keys_per_s": gpu, "gpu_e2e_GBps_of_keys": gpu * klen / 1e9, "hit_rate": hit}
+    if args.cpu_library:
+        cpu, _, _ = run(args.cpu_library, min(n, 200_000), 3)
+        line.update({"cpu_reference_keys_per_s": cpu, "cpu_impl": Path(args.cpu_library).name})
+    print(json.dumps(line))

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Throughput of the GPU in-flight task index next to the
-RunningTaskKeeper loops on the host (oracle/_ref, or the restatement if that build is
-absent): Refresh() of a cluster-wide snapshot and TryFindTask for a pending queue.
+RunningTaskKeeper loops on the host when --cpu-library names a CPU build of the same C ABI (the
+test oracle; this script never picks one up by itself): Refresh() of a cluster-wide snapshot and TryFindTask for a pending queue.
 Host buffers, copies included (both calls are synchronous)."""
 import json
 import sys
@@ -34,13 +34,18 @@ def run(lib, n_queries, reps):
 
 
 if __name__ == "__main__":
-    nq = int(sys.argv[1]) if len(sys.argv) > 1 else 1_000_000
-    ref = ROOT / "oracle" / "_ref" / "libydref.so"
-    if not ref.exists():
-        ref = ROOT / "oracle" / "libydoracle.so"
+    import argparse
+
+    ap = argparse.ArgumentParser()
+    ap.add_argument("queries", nargs="?", type=int, default=1_000_000)
+    ap.add_argument("--cpu-library", default=None, help="CPU library speaking the same C ABI, timed beside the GPU")
+    args = ap.parse_args()
+    nq = args.queries
     n, distinct, g_refresh, g_find, hit = run(None, nq, 8)
-    _, _, c_refresh, c_find, _ = run(str(ref), min(nq, 200_000), 3)
-    print(json.dumps({"metric": "running_index", "snapshot_entries": n, "distinct_digests": distinct, "queries": nq,
-                      "key_bytes": 64, "hit_rate": hit, "gpu_refresh_entries_per_s": g_refresh,
-                      "gpu_find_keys_per_s": g_find, "cpu_reference_refresh_entries_per_s": c_refresh,
-                      "cpu_reference_find_keys_per_s": c_find, "cpu_impl": ref.name}))
+    line = {"metric": "running_index", "snapshot_entries": n, "distinct_digests": distinct, "queries": nq, "key_bytes": 64,
+            "hit_rate": hit, "gpu_refresh_entries_per_s": g_refresh, "gpu_find_keys_per_s": g_find}
+    if args.cpu_library:
+        _, _, c_refresh, c_find, _ = run(args.cpu_library, min(nq, 200_000), 3)
+        line.update({"cpu_reference_refresh_entries_per_s": c_refresh, "cpu_reference_find_keys_per_s": c_find,
+                     "cpu_impl": Path(args.cpu_library).name})
+    print(json.dumps(line))

@@ -1,8 +1,9 @@
 #!/usr/bin/env python
 """Dispatch latency (request enqueue -> grant available to the caller) as a function of the batch
 size, through the C-ABI call with pinned host buffers on BASELINE configs[1]'s cluster
-(2 000 servants, 8 digests).  One line of JSON; the reference's latency per decision on the same
-host is printed beside it (single thread: it serialises on allocation_lock_)."""
+(2 000 servants, 8 digests).  One line of JSON.  With --cpu-library (a CPU build of the same C ABI,
+i.e. the test oracle -- never picked up implicitly) the reference's latency on the same host is
+printed beside it (single thread: it serialises on allocation_lock_)."""
 import json
 import sys
 import time
@@ -41,11 +42,14 @@ def sweep(lib, sizes, reps):
 
 
 if __name__ == "__main__":
-    ref = ROOT / "oracle" / "_ref" / "libydref.so"
-    if not ref.exists():
-        ref = ROOT / "oracle" / "libydoracle.so"
+    import argparse
+
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--cpu-library", default=None)
+    args = ap.parse_args()
     gpu = sweep(None, [1, 16, 256, 1024, 4096, 16384, 65536, 100_000], 200)
-    cpu = sweep(str(ref), [1, 256, 4096], 5)
-    print(json.dumps({"metric": "dispatch_latency_vs_batch", "cluster": "2000 servants x 8 digests (cfg2-mod)", "gpu": gpu,
-                      "cpu_reference": cpu, "cpu_impl": ref.name,
-                      "note": "latency of the whole call = latency seen by every request of the batch; L2 not flushed between calls"}))
+    line = {"metric": "dispatch_latency_vs_batch", "cluster": "2000 servants x 8 digests (cfg2-mod)", "gpu": gpu,
+            "note": "latency of the whole call = latency seen by every request of the batch; L2 not flushed between calls"}
+    if args.cpu_library:
+        line.update({"cpu_reference": sweep(args.cpu_library, [1, 256, 4096], 5), "cpu_impl": Path(args.cpu_library).name})
+    print(json.dumps(line))

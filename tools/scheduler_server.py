@@ -2,7 +2,7 @@
 """A minimal yadcc scheduler endpoint: TCP in, FlareStd frames through include/ydwire.h, TCP out.
 
     python tools/scheduler_server.py --port 8336 --user-tokens some_fancy_token \\
-        --servant-tokens some_fancy_token [--library oracle/libydoracle.so]
+        --servant-tokens some_fancy_token [--library <any library speaking the ydsched C ABI>]
 
 An unmodified yadcc daemon pointed at flare://host:8336 heartbeats, asks for grants, renews and
 frees them against it.  All frames that arrive within one batching window (--window-ms) are
