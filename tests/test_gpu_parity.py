@@ -472,3 +472,19 @@ def test_wire_front_end_over_cuda_backend(make_dispatcher):
     from wire_cases import run_wire_scenario
 
     assert run_wire_scenario(make_dispatcher, "cuda") == run_wire_scenario(make_dispatcher, "port")
+
+
+@pytest.mark.gpu
+def test_c_example_against_cuda_library(tmp_path):
+    """examples/minimal.c linked against the product library."""
+    import subprocess
+
+    from conftest import CUDA_LIB, ROOT
+
+    exe = tmp_path / "minimal"
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", f"-I{ROOT / 'include'}", str(ROOT / "examples" / "minimal.c"), "-o",
+                        str(exe), str(CUDA_LIB), f"-Wl,-rpath,{CUDA_LIB.parent}"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert r.stdout.strip().endswith("ok") and "request 4 -> timeout" in r.stdout
