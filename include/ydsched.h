@@ -246,9 +246,21 @@ typedef struct yd_rpc_wait_result {
  * reference's stop rules (:234-264) and status mapping (:242-246, :266-270; note that an
  * unknown environment on a prefetch-only RPC yields NO_QUOTA, not ENVIRONMENT_NOT_AVAILABLE).
  * All RPCs are solved as ONE batch.  Returns the total number of grants written (<= cap;
- * cap must be >= the sum of immediate_reqs + prefetch_reqs). */
+ * cap must be >= yd_rpc_expanded_requests(), which is <= the sum of immediate_reqs + prefetch_reqs). */
 size_t yd_wait_for_starting_task_rpcs(yd_sched* s, int64_t now_ns, const yd_rpc_wait* rpcs, size_t n_rpcs,
                                       yd_rpc_wait_result* results, yd_grant* grants_out, size_t cap);
+
+/* Upper bound on the grants one batch can produce: sum over servants of min(num_processors,
+ * max_tasks) (GetCapacityAvailable never exceeds either, task_dispatcher.cc:283-313). */
+uint64_t yd_grant_capacity_bound(yd_sched* s);
+
+/* Decisions yd_wait_for_starting_task_rpcs makes for these RPCs = the `cap` it needs.  Counts on
+ * the wire are arbitrary uint32s; an RPC is expanded to at most yd_grant_capacity_bound() + 1
+ * immediate and as many prefetch decisions, which is exact because nothing after an RPC's first
+ * failed decision is reported (scheduler_service_impl.cc:247-251, :260-262).  The call returns
+ * (size_t)-1, deciding nothing, if cap is too small, the batch exceeds 2^30 decisions or staging
+ * memory cannot be had. */
+size_t yd_rpc_expanded_requests(yd_sched* s, const yd_rpc_wait* rpcs, size_t n_rpcs);
 
 /* ---- compilation-cache bloom pre-filter ------------------- */
 

@@ -390,6 +390,12 @@ void yd_free_tasks(yd_sched* s, const uint64_t* ids, size_t n) {
 
 size_t yd_num_servants(yd_sched* s) { return s->servants.size(); }
 
+uint64_t yd_grant_capacity_bound(yd_sched* s) {
+  uint64_t b = 0;
+  for (auto&& v : s->servants) b += std::min(v->num_processors, v->max_tasks);
+  return b;
+}
+
 const char* yd_servant_location(yd_sched* s, uint32_t idx) {
   return idx < s->servants.size() ? s->servants[idx]->observed_location.c_str() : nullptr;
 }

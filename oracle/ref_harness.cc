@@ -236,6 +236,24 @@ void yd_free_tasks(yd_sched* s, const uint64_t* ids, size_t n) {
 
 size_t yd_num_servants(yd_sched* s) { return yd_oracle_access::Servants(*s->d).size(); }
 
+uint64_t yd_grant_capacity_bound(yd_sched* s) {
+  uint64_t b = 0;
+  for (auto&& v : yd_oracle_access::Servants(*s->d)) b += std::min(v->personality.num_processors, v->personality.max_tasks);
+  return b;
+}
+
+// (sizing helper of the batched entry point; the loops below are the reference's own and stop at
+// the first failure whatever the counts say)
+size_t yd_rpc_expanded_requests(yd_sched* s, const yd_rpc_wait* rpcs, size_t n_rpcs) {
+  const uint64_t bound = yd_grant_capacity_bound(s);
+  size_t total = 0;
+  for (size_t i = 0; i != n_rpcs; ++i) {
+    if (rpcs[i].milliseconds_to_wait > 10000u || rpcs[i].next_keep_alive_ns > 30000000000ll) continue;
+    total += (size_t)(std::min<uint64_t>(rpcs[i].immediate_reqs, bound + 1) + std::min<uint64_t>(rpcs[i].prefetch_reqs, bound + 1));
+  }
+  return total;
+}
+
 const char* yd_servant_location(yd_sched* s, uint32_t idx) {
   auto& sv = yd_oracle_access::Servants(*s->d);
   if (idx >= sv.size()) return nullptr;

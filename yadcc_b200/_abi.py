@@ -184,6 +184,8 @@ PROTOTYPES = [
     ("yd_keep_task_alive", None, [_P, C.c_int64, _P, C.c_size_t, C.c_int64, _P]),
     ("yd_free_tasks", None, [_P, _P, C.c_size_t]),
     ("yd_wait_for_starting_task_rpcs", C.c_size_t, [_P, C.c_int64, _P, C.c_size_t, _P, _P, C.c_size_t]),
+    ("yd_grant_capacity_bound", C.c_uint64, [_P]),
+    ("yd_rpc_expanded_requests", C.c_size_t, [_P, _P, C.c_size_t]),
     ("yd_bloom_reset", C.c_int, [_P, C.c_uint64, C.c_uint32]),
     ("yd_bloom_load", C.c_int, [_P, _P, C.c_size_t, C.c_uint32]),
     ("yd_bloom_add", None, [_P, _P, C.c_size_t, C.c_size_t, C.c_size_t]),

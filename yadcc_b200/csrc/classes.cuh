@@ -35,9 +35,14 @@ struct ClassTable {
   uint32_t* cls_nelig;       // eligible servants (max_tasks != 0, digest, version)
   uint32_t* cls_count;       // requests of the class in this batch
   uint32_t* cls_lbit;        // index of the class among the classes of its component (merge solver)
-  uint32_t* comp_flags;      // [C] bit 0: some request's "self" servant lives in the component
+  uint32_t* comp_flags;      // [C] bit 0: some requestor's IP is that of exactly ONE servant of the component ("self",
+                             //     cc:372-379); bit 1: of several servants of the component (self = the first FREE one)
   uint32_t* comp_ncls;       // [C] classes in the component
   uint32_t* comp_midx;       // [C] merge-mode components: index of their pseudo-class list, else kNone
+  uint32_t* merge_comp;      // [cls_bound] pseudo-class index -> component
+  uint32_t* comp_cls;        // [cls_bound * 32] (pseudo-class index, class index inside the component) -> class id
+  uint32_t force_stream;     // 1 (test switch): components with self-requests go to the sequential solver;
+                             // 2: so does everything the merge solver would take (its last-ditch retry)
 };
 
 struct TopoView {  // the parts of the topology the class kernels need
@@ -117,16 +122,30 @@ __global__ void __launch_bounds__(256) k_cls_insert(const yd_task_req* __restric
     }
     if (!done) atomicExch(&ct.meta[1], 1u);  // table full -> caller falls back to the row-scan solver
   }
-  // does the requestor's IP belong to a servant of this component?
+  // does the requestor's IP belong to one / several servants of this component?
   const uint32_t ip = __ldg(reinterpret_cast<const uint2*>(reqs + q) + 1).x;
   if (ip < t.n_ips) {
+    uint32_t mine = 0;
+    for (uint32_t u = t.ip_off[ip], e = t.ip_off[ip + 1]; u < e && mine < 2; ++u) {
+      if (t.sv_comp[t.ip_sv[u]] == comp) ++mine;
+    }
+    const uint32_t bit = mine >= 2 ? 2u : mine;
+    if (bit && !(ct.comp_flags[comp] & bit)) atomicOr(&ct.comp_flags[comp], bit);
+  }
+}
+
+// The requestor's own servant as the solvers see it: component-local index of the ONE servant of
+// component `comp` whose observed location is on the requestor's IP (IsNetworkAddressEqual,
+// cc:66-69), else kNone.  (Several such servants: the component takes the sequential solver.)
+__device__ __forceinline__ uint32_t self_servant(const TopoView& t, uint32_t ip, uint32_t comp) {
+  uint32_t self = kNone, mine = 0;
+  if (ip < t.n_ips) {
     for (uint32_t u = t.ip_off[ip], e = t.ip_off[ip + 1]; u < e; ++u) {
-      if (t.sv_comp[t.ip_sv[u]] == comp) {
-        if (!(ct.comp_flags[comp] & 1u)) atomicOr(&ct.comp_flags[comp], 1u);
-        break;
-      }
+      const uint32_t p = t.ip_sv[u];
+      if (t.sv_comp[p] == comp) { self = t.sv_local[p]; ++mine; }
     }
   }
+  return mine == 1 ? self : kNone;
 }
 
 // One block: deterministic class ids (= rank of the occupied table slot), per-class
@@ -213,7 +232,8 @@ __global__ void __launch_bounds__(1024) k_cls_finalize(TopoView t, ClassTable ct
   }
   // solver mode per component:
   //   1 = data-parallel (one class, nobody requests from one of its own servants)
-  //   2 = merge solver  (2..32 classes, nobody requests from one of its own servants)
+  //   2 = merge solver  (1..32 classes; requestors may be servants of the component, but no IP
+  //       carries several of its servants)
   //   0 = sequential slot-stream solver
   const bool healthy = ct.meta[1] == 0;
   __shared__ uint32_t s_nmerge;
@@ -222,11 +242,12 @@ __global__ void __launch_bounds__(1024) k_cls_finalize(TopoView t, ClassTable ct
   for (uint32_t c = tid; c < n_comps; c += 1024) {
     uint32_t mode = 0, midx = kNone;
     const uint32_t k = ct.comp_ncls[c];
-    if (healthy && !(ct.comp_flags[c] & 1u)) {
-      if (k == 1) mode = 1;
-      else if (k >= 2 && k <= 32) {
+    const uint32_t fl = ct.comp_flags[c];
+    if (healthy && !(fl & 2u) && !(ct.force_stream == 1 && (fl & 1u))) {
+      if (k == 1 && !(fl & 1u)) mode = 1;
+      else if (ct.force_stream != 2 && k >= 1 && k <= 32) {
         midx = atomicAdd(&s_nmerge, 1u);
-        if (ncls + midx < ct.cls_bound) mode = 2;
+        if (ncls + midx < ct.cls_bound) { mode = 2; ct.merge_comp[midx] = c; }
         else { midx = kNone; atomicMax(&ct.meta[1], 2u); }  // needs a bigger per-class grid: retry
       }
     }
@@ -234,6 +255,10 @@ __global__ void __launch_bounds__(1024) k_cls_finalize(TopoView t, ClassTable ct
     ct.comp_midx[c] = midx;
   }
   __syncthreads();
+  for (uint32_t c = tid; c < ncls; c += 1024) {
+    const uint32_t midx = ct.comp_midx[ct.cls_comp[c]];
+    if (midx != kNone && ct.cls_lbit[c] < 32) ct.comp_cls[midx * 32 + ct.cls_lbit[c]] = c;
+  }
   if (tid == 0) {
     ct.meta[2] = s_nmerge;
     ct.meta[3] = min(ncls + s_nmerge, ct.cls_bound);  // lists to build: classes + merge pseudo-classes

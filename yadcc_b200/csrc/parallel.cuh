@@ -27,6 +27,7 @@ __global__ void __launch_bounds__(kRankTile) k_rank_count(const yd_task_req* __r
                                                           const uint32_t* __restrict__ comp_mode, uint32_t n_tiles,
                                                           uint32_t* __restrict__ rcls,   // [n] class or kNone
                                                           uint32_t* __restrict__ rrank,  // [n] rank inside the tile
+                                                          uint32_t* __restrict__ rself,  // [n] own servant (merge solver)
                                                           uint32_t* __restrict__ tile_cnt /* [kMaxClasses][n_tiles] */) {
   __shared__ uint16_t wc[32][kMaxClasses];
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -34,7 +35,7 @@ __global__ void __launch_bounds__(kRankTile) k_rank_count(const yd_task_req* __r
   __syncthreads();
   const uint32_t n = dp->n;
   const uint32_t q = blockIdx.x * kRankTile + tid;
-  uint32_t cls = kNone;
+  uint32_t cls = kNone, self = kNone;
   if (q < n) {
     const uint2 w0 = __ldg(reinterpret_cast<const uint2*>(reqs + q));
     if (w0.x < t.n_envs) {
@@ -42,6 +43,9 @@ __global__ void __launch_bounds__(kRankTile) k_rank_count(const yd_task_req* __r
       if (comp != kNone && comp_mode[comp] != 0) {  // data-parallel or merge: both need FIFO ranks
         const uint32_t slot = cls_find(ct.keys, ((unsigned long long)w0.x << 32) | w0.y);
         if (slot != kNone) cls = ct.slot_cls[slot];
+        if (cls != kNone && comp_mode[comp] == 2 && (ct.comp_flags[comp] & 1u)) {
+          self = self_servant(t, __ldg(reinterpret_cast<const uint2*>(reqs + q) + 1).x, comp);
+        }
       }
     }
   }
@@ -65,6 +69,7 @@ __global__ void __launch_bounds__(kRankTile) k_rank_count(const yd_task_req* __r
   if (q < n) {
     rcls[q] = cls;
     rrank[q] = cls != kNone ? (uint32_t)wc[warp][cls] + wrank : 0u;
+    rself[q] = self;
   }
 }
 
@@ -73,11 +78,12 @@ __global__ void __launch_bounds__(256) k_rank_assign(const DynParams* __restrict
                                                      ClassTable ct,
                                                      const uint32_t* __restrict__ rcls,
                                                      const uint32_t* __restrict__ rrank,
+                                                     const uint32_t* __restrict__ rself,
                                                      const uint32_t* __restrict__ tile_off,
                                                      const uint32_t* __restrict__ list_off, uint32_t n_list_tiles,
                                                      const uint2* __restrict__ list, ServantArrays sv,
                                                      const uint32_t* __restrict__ comp_mode,
-                                                     uint32_t* __restrict__ rq, uint32_t* __restrict__ res) {
+                                                     uint2* __restrict__ rq, uint32_t* __restrict__ res) {
   const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= dp->n) return;
   // Overflow flagged by the class table or the list builder: the host reruns this batch (bigger
@@ -88,9 +94,10 @@ __global__ void __launch_bounds__(256) k_rank_assign(const DynParams* __restrict
   if (ct.cls_nelig[c] == 0) { res[q] = kResEnvNotFound; return; }  // cc:105-108
   const uint32_t rank = tile_off[c * n_tiles + q / kRankTile] - tile_off[c * n_tiles] + rrank[q];
   if (comp_mode[ct.cls_comp[c]] == 2) {
-    // merge solver: publish the class's FIFO request list (class c owns rq[tile_off[c][0] ...));
+    // merge solver: publish the class's FIFO request list (class c owns rq[tile_off[c][0] ...)) as
+    // (request, its own servant in the component or kNone);
     // the verdict stays Timeout unless a slot picks this request (solve_merge.cuh)
-    rq[tile_off[c * n_tiles] + rank] = q;
+    rq[tile_off[c * n_tiles] + rank] = make_uint2(q, rself[q]);
     res[q] = kResTimeout;
     return;
   }
@@ -98,10 +105,7 @@ __global__ void __launch_bounds__(256) k_rank_assign(const DynParams* __restrict
   if (rank >= le - lb) { res[q] = kResTimeout; return; }  // cc:116-118
   const uint2 e = list[lb + rank];  // (servant local index, running_tasks value of the slot)
   const uint32_t li = t.comp_sv_off[ct.cls_comp[c]] + e.x;
-  res[q] = li;
-  const uint32_t pos = t.comp_sv[li];
-  atomicAdd(&sv.run[pos], 1u);   // ++running_tasks, ++ever_assigned_tasks (cc:123-124)
-  atomicAdd(&sv.ever[pos], 1ull);
+  res[q] = li;  // (++running_tasks, ++ever_assigned_tasks happen in k_final_write)
 }
 
 }  // namespace yd

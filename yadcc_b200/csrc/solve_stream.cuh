@@ -35,7 +35,8 @@ struct StreamArgs {
   uint32_t n_list_tiles;
   const uint2* list;          // (servant local index, running_tasks value of the slot)
   uint32_t max_comp_servants; // dynamic shared memory holds 2 x this many u32
-  const uint32_t* comp_mode;  // [C] 0 = this kernel, 1 = handled by the parallel path
+  const uint32_t* comp_mode;  // [C] 0 = this kernel, 1 = handled by the parallel path, 2 = merge solver ...
+  const uint32_t* viol;       // [C] ... unless it handed the component back (solve_merge.cuh)
   Counters* counters;         // pad[0..3]: speculation steps, lanes committed by them, exact walks, walk windows
   uint32_t debug;             // test switches: bit 0 producers never pre-answer, bit 1 no speculation
 };
@@ -139,7 +140,8 @@ __global__ void __launch_bounds__((kStreamProducers + 1) * 32, 1) k_solve_stream
   __shared__ StreamShared sh;
   const uint32_t comp = blockIdx.x;
   if (a.ct.meta[1]) return;  // class table overflow: the host reruns this batch with the row-scan solver
-  if (a.comp_mode[comp] != 0 || a.ct.comp_ncls[comp] == 0) return;  // nothing (for us) to do
+  const uint32_t mode = a.comp_mode[comp];
+  if ((mode != 0 && !(mode == 2 && a.viol[comp])) || a.ct.comp_ncls[comp] == 0) return;  // nothing (for us) to do
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t nall = (kStreamProducers + 1) * 32;
   const uint32_t sv_begin = a.t.comp_sv_off[comp];
@@ -378,15 +380,7 @@ __global__ void __launch_bounds__((kStreamProducers + 1) * 32, 1) k_solve_stream
     atomicAdd(&a.counters->pad[0], st_steps); atomicAdd(&a.counters->pad[1], st_lanes);
     atomicAdd(&a.counters->pad[2], st_walks); atomicAdd(&a.counters->pad[3], st_windows);
   }
-  // ---- write back running_tasks / ever_assigned_tasks (cc:123-124) -----------
-  for (uint32_t i = lane; i < n_sv; i += 32) {
-    const uint32_t pos = a.t.comp_sv[sv_begin + i];
-    const uint32_t r0 = a.sv.run[pos], r1 = run_s[i];
-    if (r1 != r0) {
-      a.sv.run[pos] = r1;
-      a.sv.ever[pos] += (unsigned long long)(r1 - r0);
-    }
-  }
+  // (++running_tasks / ++ever_assigned_tasks, cc:123-124, are applied per grant by k_final_write)
 }
 
 }  // namespace yd

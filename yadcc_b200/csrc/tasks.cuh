@@ -83,7 +83,9 @@ __global__ void __launch_bounds__(1024) k_final_write(const uint32_t* __restrict
                                                       const uint32_t* __restrict__ block_off,
                                                       const uint32_t* __restrict__ comp_sv, TaskRing ring,
                                                       yd_grant* __restrict__ out,
-                                                      const uint32_t* __restrict__ abort_flag) {
+                                                      const uint32_t* __restrict__ abort_flag,
+                                                      uint32_t* __restrict__ run,
+                                                      unsigned long long* __restrict__ ever) {
   if (abort_flag && *abort_flag) return;
   const uint32_t n = dp->n;
   const long long now_ns = dp->now_ns;
@@ -111,6 +113,10 @@ __global__ void __launch_bounds__(1024) k_final_write(const uint32_t* __restrict
     ring.exp[slot] = now_ns + rq.expires_in_ns;
     ring.srv[slot] = r;
     ring.flags[slot] = kTaskAlive | ((rq.flags & YD_REQ_FLAG_PREFETCH) ? kTaskPrefetch : 0u);
+    if (run) {  // ++running_tasks, ++ever_assigned_tasks (cc:123-124); the slot-stream solvers leave it to us
+      atomicAdd(&run[r], 1u);
+      atomicAdd(&ever[r], 1ull);
+    }
   } else {
     g = make_uint4(0u, 0u, YD_NO_SERVANT,
                    (r == kResTimeout) ? YD_STATUS_TIMEOUT : YD_STATUS_ENVIRONMENT_NOT_FOUND);

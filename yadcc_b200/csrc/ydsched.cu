@@ -169,7 +169,14 @@ struct yd_sched {
   cudaStream_t st2 = nullptr, st_copy = nullptr;  // class/rank branch; request upload
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_h2d = nullptr;
   uint32_t cls_bound = 16;  // classes the per-class grids are sized for; grows on demand (<= yd::kMaxClasses)
-  DevBuf d_list, d_list_bal, d_rcls, d_rrank, d_rank_cnt, d_rq;
+  DevBuf d_list, d_list_bal, d_rcls, d_rrank, d_rank_cnt, d_rq, d_rself;
+  // merge solver (solve_merge.cuh): per-slot verdicts and the chunk boundary states
+  DevBuf d_slot_pick, d_mst_in, d_mst_out;
+  size_t z_merge_off = 0;
+  uint32_t merge_chunk = 1024, merge_rounds = 8, merge_max_chunks = 0;
+  uint32_t stream_debug = 0;   // YDSCHED_STREAM_DEBUG, read once at yd_create
+  uint32_t force_stream = 0;   // yd_config.reserved bit 1 / YDSCHED_FORCE_STREAM: no merge solver for self-requests
+  bool dump_env = false, debug_env = false;
   bool stream_attr_set = false;
   size_t res_words = 0;  // u32 words of res[] in d_res (the class-table keys follow)
   size_t staged_n = 0;   // requests placed in d_reqs by yd_stage_requests
@@ -194,12 +201,13 @@ struct yd_sched {
 
   // captured solve graphs, keyed by size class
   struct GraphKey {
-    uint32_t Nb = 0, S = 0, n_comps = 0, max_comp = 0, cls_bound = 0, solver = 0, wide = 0;
+    uint32_t Nb = 0, S = 0, n_comps = 0, max_comp = 0, cls_bound = 0, solver = 0, wide = 0, merge_rounds = 0, force_stream = 0;
     size_t slot_b = 0;
     unsigned long long gen = 0, topo_gen = 0;  // buffer reallocations; topology rebuilds (n_envs, n_ips, ... are baked in)
     uint64_t ring_cap = 0;
     bool operator==(const GraphKey& o) const {
       return Nb == o.Nb && S == o.S && n_comps == o.n_comps && max_comp == o.max_comp && cls_bound == o.cls_bound &&
+             merge_rounds == o.merge_rounds && force_stream == o.force_stream &&
              solver == o.solver && wide == o.wide && slot_b == o.slot_b && gen == o.gen && topo_gen == o.topo_gen &&
              ring_cap == o.ring_cap;
     }
@@ -495,6 +503,12 @@ yd_sched* yd_create(const yd_config* cfg) {
   s->id_stride = cfg->id_stride ? cfg->id_stride : 1;
   s->id_offset = cfg->id_stride ? cfg->id_offset : 0;
   s->use_graphs = !(cfg->reserved & 1u) && !getenv("YDSCHED_NO_GRAPH");
+  s->force_stream = ((cfg->reserved & 2u) || getenv("YDSCHED_FORCE_STREAM")) ? 1u : 0u;
+  if (const char* e = getenv("YDSCHED_STREAM_DEBUG")) s->stream_debug = (uint32_t)atoi(e);
+  if (const char* e = getenv("YDSCHED_MERGE_CHUNK")) s->merge_chunk = std::max(32u, (uint32_t)atoi(e) & ~31u);
+  if (const char* e = getenv("YDSCHED_MERGE_ROUNDS")) s->merge_rounds = std::max(2u, (uint32_t)atoi(e));
+  s->dump_env = getenv("YDSCHED_DUMP") != nullptr;
+  s->debug_env = getenv("YDSCHED_DEBUG") != nullptr;
   YD_CUDA_CHECK(cudaStreamCreateWithFlags(&s->st, cudaStreamNonBlocking));
   YD_CUDA_CHECK(cudaStreamCreateWithFlags(&s->st2, cudaStreamNonBlocking));
   YD_CUDA_CHECK(cudaStreamCreateWithFlags(&s->st_copy, cudaStreamNonBlocking));
@@ -526,7 +540,8 @@ void yd_destroy(yd_sched* s) {
                     &s->d_t_flags, &s->d_reqs, &s->d_res, &s->d_out, &s->d_blk, &s->d_row_off, &s->d_row_len,
                     &s->d_codes, &s->d_ids, &s->d_ok, &s->d_counters, &s->d_sv_env_off, &s->d_sv_envs,
                     &s->d_comp_mode, &s->d_slot_owner, &s->d_sort_k[0], &s->d_sort_k[1], &s->d_sort_v[0],
-                    &s->d_sort_v[1], &s->d_zero, &s->d_list, &s->d_list_bal, &s->d_rcls, &s->d_rrank, &s->d_rank_cnt, &s->d_rq, &s->d_bloom,
+                    &s->d_sort_v[1], &s->d_zero, &s->d_list, &s->d_list_bal, &s->d_rcls, &s->d_rrank, &s->d_rank_cnt, &s->d_rq, &s->d_rself,
+                    &s->d_slot_pick, &s->d_mst_in, &s->d_mst_out, &s->d_bloom,
                     &s->d_bloom_keys, &s->d_bloom_out, &s->d_rt_bytes, &s->d_rt_off, &s->d_rt_len, &s->d_rt_ids,
                     &s->d_rt_slots, &s->d_rt_keys, &s->d_rt_out}) {
     b->release();
@@ -617,9 +632,22 @@ yd::ClassTable MakeClassTable(yd_sched* s) {
   ct.cls_lbit = u;                       u += yd::kMaxClasses;
   ct.comp_flags = u;                     u += s->n_comps;
   ct.comp_ncls = u;                      u += s->n_comps;
-  ct.comp_midx = u;
+  ct.comp_midx = u;                      u += s->n_comps;
+  ct.merge_comp = u;                     u += yd::kMaxClasses;
+  ct.comp_cls = u;                       // [cls_bound * 32], the tail of the class region
   ct.cls_bound = s->cls_bound;
+  ct.force_stream = s->force_stream;
   return ct;
+}
+
+yd::MergePlan MakeMergePlan(yd_sched* s) {
+  uint32_t* u = reinterpret_cast<uint32_t*>(static_cast<char*>(s->d_zero.p) + s->z_merge_off);
+  yd::MergePlan mp{};
+  mp.chunk_base = u;                     u += yd::kMaxClasses + 1;
+  mp.changed = u;                        u += 16;
+  mp.viol = u;                           u += s->n_comps;
+  mp.tau = u;                            // [S]
+  return mp;
 }
 
 // Slot table (both solvers).  For the slot-stream solver it also records slot owners.
@@ -723,7 +751,9 @@ void PrepareStreamBuffers(yd_sched* s, uint32_t Nb, size_t slot_b) {
   size_t off = 0;
   for (int p = 0; p < passes; ++p) { s->z_hist_off[p] = off; off += yd::rs_pass_words(s->sort_nb) * 4; }
   s->z_cls_off = off;
-  off += (yd::kClsTableSize + 8 + 6 * yd::kMaxClasses + 3 * size_t(s->n_comps) + 8) * 4;
+  off += (yd::kClsTableSize + 8 + 7 * yd::kMaxClasses + 3 * size_t(s->n_comps) + 32 * size_t(s->cls_bound) + 8) * 4;
+  s->z_merge_off = off;
+  off += (yd::kMaxClasses + 1 + 16 + size_t(s->n_comps) + s->sv.size() + 8) * 4;
   const uint32_t n_tiles = (uint32_t)((slot_b + yd::kListTile - 1) / yd::kListTile);
   s->z_listcnt_off = off;
   off += (size_t(s->cls_bound) * n_tiles + 1) * 4;
@@ -732,7 +762,13 @@ void PrepareStreamBuffers(yd_sched* s, uint32_t Nb, size_t slot_b) {
   s->d_list.ensure(slot_b * 8 * 4);
   s->d_list_bal.ensure(size_t(n_tiles) * s->cls_bound * 32 * 4);  // membership ballots: (tile, list, warp)
   const uint32_t n_rtiles = (Nb + yd::kRankTile - 1) / yd::kRankTile;
-  s->d_rcls.ensure(size_t(Nb) * 4); s->d_rrank.ensure(size_t(Nb) * 4); s->d_rq.ensure(size_t(Nb) * 4);
+  s->d_rcls.ensure(size_t(Nb) * 4); s->d_rrank.ensure(size_t(Nb) * 4); s->d_rq.ensure(size_t(Nb) * 8);
+  s->d_rself.ensure(size_t(Nb) * 4);
+  s->d_slot_pick.ensure(slot_b * 4 * 4);  // one word per list entry
+  // every slot is in at most one pseudo-class list: chunks <= slots / chunk + one partial chunk per list
+  s->merge_max_chunks = (uint32_t)(slot_b / s->merge_chunk) + s->cls_bound + 1;
+  s->d_mst_in.ensure(size_t(s->merge_max_chunks) * yd::kMergeStateWords * 4);
+  s->d_mst_out.ensure(size_t(s->merge_max_chunks) * yd::kMergeStateWords * 4);
   s->d_rank_cnt.ensure((size_t(s->cls_bound) * n_rtiles + 1) * 4);
   if (!s->stream_attr_set) {
     YD_CUDA_CHECK(cudaFuncSetAttribute(yd::k_solve_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, 190 * 1024));
@@ -766,7 +802,7 @@ uint32_t LaunchStream(yd_sched* s, uint32_t N, size_t slot_b, bool capturing) {
   yd::k_rank_count<<<n_rtiles, yd::kRankTile, 0, st2>>>(s->d_reqs.as<yd_task_req>(), dp, t, ct,
                                                          s->d_comp_mode.as<uint32_t>(), n_rtiles,
                                                          s->d_rcls.as<uint32_t>(), s->d_rrank.as<uint32_t>(),
-                                                         s->d_rank_cnt.as<uint32_t>());
+                                                         s->d_rself.as<uint32_t>(), s->d_rank_cnt.as<uint32_t>());
   yd::k_scan_u32<<<1, 1024, 0, st2>>>(s->d_rank_cnt.as<uint32_t>(), 0, ct.meta, n_rtiles, nullptr, ct.cls_bound);
   YD_CUDA_CHECK(cudaEventRecord(s->ev_join, st2));
   launches += 4;
@@ -790,21 +826,34 @@ uint32_t LaunchStream(yd_sched* s, uint32_t N, size_t slot_b, bool capturing) {
 
   // ---- data-parallel path: single-class components without self-requests ----------------
   yd::k_rank_assign<<<(N + 255) / 256, 256, 0, st>>>(dp, n_rtiles, t, ct, s->d_rcls.as<uint32_t>(),
-                                                     s->d_rrank.as<uint32_t>(), s->d_rank_cnt.as<uint32_t>(), list_cnt,
+                                                     s->d_rrank.as<uint32_t>(), s->d_rself.as<uint32_t>(),
+                                                     s->d_rank_cnt.as<uint32_t>(), list_cnt,
                                                      n_tiles, s->d_list.as<uint2>(), arr, s->d_comp_mode.as<uint32_t>(),
-                                                     s->d_rq.as<uint32_t>(), s->d_res.as<uint32_t>());
+                                                     s->d_rq.as<uint2>(), s->d_res.as<uint32_t>());
   launches += 1;
 
-  // ---- merge solver: coupled components without self-requests ------------------------------
+  // ---- merge solver: everything but components with several servants behind one requestor IP -------
+  yd::MergePlan mp = MakeMergePlan(s);
   {
     yd::MergeArgs m{};
-    m.t = t; m.ct = ct; m.sv = arr;
+    m.t = t; m.ct = ct; m.mp = mp; m.sv = arr; m.dp = dp;
     m.comp_mode = s->d_comp_mode.as<uint32_t>();
     m.list_off = list_cnt; m.n_list_tiles = n_tiles; m.list = s->d_list.as<uint2>();
     m.rank_off = s->d_rank_cnt.as<uint32_t>(); m.n_rank_tiles = n_rtiles;
-    m.rq = s->d_rq.as<uint32_t>(); m.res = s->d_res.as<uint32_t>();
-    yd::k_solve_merge<<<s->n_comps, 32, 0, st>>>(m);
-    launches += 1;
+    m.rq = s->d_rq.as<uint2>(); m.rcls = s->d_rcls.as<uint32_t>(); m.rself = s->d_rself.as<uint32_t>();
+    m.slot_pick = s->d_slot_pick.as<uint32_t>();
+    m.st_in = s->d_mst_in.as<uint32_t>(); m.st_out = s->d_mst_out.as<uint32_t>();
+    m.chunk = s->merge_chunk; m.max_chunks = s->merge_max_chunks;
+    m.res = s->d_res.as<uint32_t>();
+    yd::k_merge_plan<<<1, 256, 0, st>>>(m);
+    for (uint32_t r = 0; r < s->merge_rounds; ++r) {
+      m.round = r;
+      yd::k_merge_round<<<s->merge_max_chunks, 32, 0, st>>>(m);
+    }
+    m.round = s->merge_rounds;
+    yd::k_merge_scatter<<<s->merge_max_chunks, 256, 0, st>>>(m);
+    yd::k_merge_check<<<(N + 255) / 256, 256, 0, st>>>(m);
+    launches += 3 + s->merge_rounds;
   }
 
   // ---- sequential decisions for everything else ---------------------------------------------
@@ -821,8 +870,9 @@ uint32_t LaunchStream(yd_sched* s, uint32_t N, size_t slot_b, bool capturing) {
   a.list = s->d_list.as<uint2>();
   a.max_comp_servants = s->max_comp_servants;
   a.comp_mode = s->d_comp_mode.as<uint32_t>();
+  a.viol = mp.viol;
   a.counters = s->d_counters.as<Counters>();
-  a.debug = getenv("YDSCHED_STREAM_DEBUG") ? (uint32_t)atoi(getenv("YDSCHED_STREAM_DEBUG")) : 0u;
+  a.debug = s->stream_debug;
   const size_t dyn = size_t(s->max_comp_servants) * 8;
   yd::k_solve_stream<<<s->n_comps, (yd::kStreamProducers + 1) * 32, dyn, st>>>(a);
   launches += 1;
@@ -872,13 +922,16 @@ uint32_t EnqueueSolve(yd_sched* s, uint32_t Nb, size_t slot_b, uint32_t solver, 
   yd::k_final_scan<<<1, 1024, 0, st>>>(s->d_blk.as<uint32_t>(), nb, s->d_counters.as<Counters>(), abort_flag);
   yd::k_final_write<<<nb, 1024, 0, st>>>(s->d_res.as<uint32_t>(), s->d_reqs.as<yd_task_req>(), dp,
                                          s->d_blk.as<uint32_t>(), s->d_comp_sv.as<uint32_t>(), s->ring(),
-                                         s->d_out.as<yd_grant>(), abort_flag);
+                                         s->d_out.as<yd_grant>(), abort_flag,
+                                         // the row-scan solver writes running_tasks back itself
+                                         solver == 2 ? s->d_run.as<uint32_t>() : nullptr,
+                                         s->d_ever.as<unsigned long long>());
   launches += 3;
   YD_CUDA_CHECK(cudaGetLastError());
   if (record_events) YD_CUDA_CHECK(cudaEventRecord(s->ev[4], st));
   YD_CUDA_CHECK(cudaMemcpyAsync(s->h_counters.p, s->d_counters.p, sizeof(Counters), cudaMemcpyDeviceToHost, st));
   if (abort_flag) {
-    YD_CUDA_CHECK(cudaMemcpyAsync(s->h_meta.p, abort_flag - 1, 8, cudaMemcpyDeviceToHost, st));
+    YD_CUDA_CHECK(cudaMemcpyAsync(s->h_meta.p, abort_flag - 1, 16, cudaMemcpyDeviceToHost, st));  // meta[0..3]
   }
   return launches;
 }
@@ -1029,8 +1082,10 @@ void yd_wait_for_starting_new_tasks(yd_sched* s, int64_t now_ns, const yd_task_r
   }
   YD_CUDA_CHECK(cudaEventRecord(s->ev_h2d, s->st_copy));
   bool graphed = false;
+  const uint32_t merge_rounds_cfg = s->merge_rounds, force_stream_cfg = s->force_stream;
+  int merge_retry = 0;
   for (int attempt = 0;; ++attempt) {
-    s->h_meta.as<uint32_t>()[0] = s->h_meta.as<uint32_t>()[1] = 0;
+    memset(s->h_meta.p, 0, 16);
     graphed = false;
     if (s->use_graphs) {
       // make sure every buffer the sequence touches exists BEFORE capturing (no allocation
@@ -1040,6 +1095,7 @@ void yd_wait_for_starting_new_tasks(yd_sched* s, int64_t now_ns, const yd_task_r
       key.Nb = Nb; key.S = S; key.n_comps = s->n_comps; key.max_comp = s->max_comp_servants;
       key.cls_bound = s->cls_bound; key.solver = solver; key.wide = s->wide; key.slot_b = slot_b;
       key.gen = g_buf_generation; key.topo_gen = s->topo_gen; key.ring_cap = s->ring_cap;
+      key.merge_rounds = s->merge_rounds; key.force_stream = s->force_stream;
       yd_sched::GraphEntry* hit = nullptr;
       for (auto& g : s->graphs) if (g.key == key) { hit = &g; break; }
       if (!hit) {
@@ -1069,12 +1125,21 @@ void yd_wait_for_starting_new_tasks(yd_sched* s, int64_t now_ns, const yd_task_r
     YD_CUDA_CHECK(cudaMemcpyAsync(out, s->d_out.p, size_t(N) * sizeof(yd_grant), cudaMemcpyDeviceToHost, st));
     YD_CUDA_CHECK(cudaEventRecord(s->ev[5], st));
     YD_CUDA_CHECK(cudaStreamSynchronize(st));
-    if (getenv("YDSCHED_DUMP") && solver == 2 && S && s->n_comps) DumpStreamState(s, Nb, slot_b);
+    if (s->dump_env && solver == 2 && S && s->n_comps) DumpStreamState(s, Nb, slot_b);
     if (solver == 2 && S && s->n_comps && s->h_meta.as<uint32_t>()[1] != 0) {
       // Nothing was decided (the stream solver and the final kernels all stood down).
       const uint32_t flag = s->h_meta.as<uint32_t>()[1], ncls = s->h_meta.as<uint32_t>()[0];
-      if (flag == 2 && attempt < 3) {  // more classes than provisioned: grow and go again
-        while (s->cls_bound < ncls && s->cls_bound < yd::kMaxClasses) s->cls_bound *= 2;
+      if (flag == 2 && attempt < 3 && s->cls_bound < yd::kMaxClasses) {  // more lists than provisioned: grow and go again
+        // one list per class plus one pseudo-class list per merge-mode component
+        const uint32_t want = ncls + s->h_meta.as<uint32_t>()[2] + 1;
+        s->cls_bound *= 2;
+        while (s->cls_bound < want && s->cls_bound < yd::kMaxClasses) s->cls_bound *= 2;
+      } else if (flag == 3 && merge_retry < 2) {
+        // the merge solver's boundary states had not settled after the rounds in the graph: more
+        // rounds first, then the sequential solver for everything it would have decided
+        if (merge_retry == 0) s->merge_rounds = std::min(s->merge_rounds * 8, s->merge_max_chunks + 2);
+        else s->force_stream = 2;
+        ++merge_retry;
       } else {
         if (s->max_comp_servants > kRowscanMaxComponent) {
           fprintf(stderr, "ydsched: class table overflow and components too large for the row-scan solver\n");
@@ -1088,6 +1153,8 @@ void yd_wait_for_starting_new_tasks(yd_sched* s, int64_t now_ns, const yd_task_r
   }
   const Counters* c = s->h_counters.as<Counters>();
   s->next_id += c->granted;
+  s->merge_rounds = merge_rounds_cfg;
+  s->force_stream = force_stream_cfg;
 
   float ms = 0;
   yd_solve_stats& stt = s->stats;
@@ -1108,7 +1175,7 @@ void yd_wait_for_starting_new_tasks(yd_sched* s, int64_t now_ns, const yd_task_r
   stt.h2d_bytes = (reqs ? size_t(N) * sizeof(yd_task_req) : 0) + sizeof(yd::DynParams);
   stt.d2h_bytes = size_t(N) * sizeof(yd_grant) + sizeof(Counters) + 8;
   s->have_stats = true;
-  if (getenv("YDSCHED_DEBUG")) {
+  if (s->debug_env) {
     fprintf(stderr, "ydsched: solver %u graph %d spec_steps %llu spec_lanes %llu walks %llu windows %llu solve_ms %.3f\n",
             solver, (int)graphed, c->pad[0], c->pad[1], c->pad[2], c->pad[3], stt.solve_ms);
   }
@@ -1274,6 +1341,12 @@ size_t yd_get_running_tasks(yd_sched* s, yd_running_task* out, size_t cap) {
 }
 
 size_t yd_num_servants(yd_sched* s) { return s->sv.size(); }
+
+uint64_t yd_grant_capacity_bound(yd_sched* s) {
+  uint64_t b = 0;
+  for (auto&& v : s->sv) b += std::min(v.nproc, v.max_tasks);
+  return b;
+}
 
 const char* yd_servant_location(yd_sched* s, uint32_t idx) {
   return idx < s->sv.size() ? s->sv[idx].observed.c_str() : nullptr;

@@ -230,7 +230,7 @@ class TaskDispatcher:
         results[i] = (status, n_grants, first_grant) and grants is a GRANT_DTYPE array."""
         assert rpcs.dtype == _abi.RPC_WAIT_DTYPE and rpcs.flags.c_contiguous
         n = rpcs.shape[0]
-        cap = int(rpcs["immediate_reqs"].sum() + rpcs["prefetch_reqs"].sum())
+        cap = int(self._lib.yd_rpc_expanded_requests(self._h, rpcs.ctypes.data, n))  # counts clamped to what can be granted
         results = np.zeros(n, dtype=_abi.RPC_RESULT_DTYPE)
         grants = np.zeros(max(cap, 1), dtype=GRANT_DTYPE)
         k = self._lib.yd_wait_for_starting_task_rpcs(self._h, _ns(now), rpcs.ctypes.data, n, results.ctypes.data,

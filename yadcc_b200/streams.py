@@ -516,6 +516,10 @@ def named_stream(name: str, d: TaskDispatcher) -> Stream:
         return rounds_stream(config3(20000, 300, 8, envs_per="mod"), d, max_rounds=4)
     if name == "cfg3":
         return rounds_stream(config3(), d, max_rounds=3)
+    if name == "cfg5-1m":  # BASELINE configs[4]'s servant pool and distributions, first 1 M requests of its queue
+        return config5(1_000_000, 8000).stream(d)
+    if name == "cfg5-1m-rounds":
+        return rounds_stream(config5(1_000_000, 8000), d, max_rounds=2)
     if name.startswith("fuzz-"):
         seed = int(name.split("-")[1])
         return fuzz_stream(d, seed, n_servants=8 + seed % 30, wide=(seed % 5 == 0))
