@@ -181,6 +181,21 @@ void yd_keep_servant_alive(yd_sched* s, int64_t now_ns, const yd_servant* servan
 size_t yd_notify_servant_running_tasks(yd_sched* s, const char* servant_location,
                                        const yd_running_task* tasks, size_t n,
                                        uint64_t* unknown_out);
+/* One tick's worth of heartbeats in one call.  SchedulerServiceImpl::Heartbeat does KeepServantAlive
+ * then NotifyServantRunningTasks per servant (scheduler_service_impl.cc:171-185); a scheduler front
+ * end that collects the heartbeats of a tick issues them here as two batches.  Both calls are
+ * defined as the loop over the single-servant calls above, in array order. */
+typedef struct yd_heartbeat_item {
+  const char* servant_location;  /* observed location, as for yd_notify_servant_running_tasks */
+  const yd_running_task* tasks;  /* the servant's reported running tasks */
+  size_t n_tasks;
+} yd_heartbeat_item;
+void yd_keep_servants_alive(yd_sched* s, int64_t now_ns, const yd_servant* servants,
+                            const int64_t* expires_in_ns, size_t n);
+/* unknown_out: the unknown ids of item 0, then item 1, ... (capacity: sum of n_tasks);
+ * unknown_counts[i]: how many belong to item i.  Returns the total. */
+size_t yd_notify_servants_running_tasks(yd_sched* s, const yd_heartbeat_item* items, size_t n,
+                                        uint64_t* unknown_out, size_t* unknown_counts);
 /* TaskDispatcher::GetRunningTasks (cc:279-281).  Returns the total count; at
  * most `cap` entries are written.  Returned strings are owned by the library
  * and valid until the next call that mutates the handle. */

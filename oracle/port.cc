@@ -388,6 +388,23 @@ void yd_free_tasks(yd_sched* s, const uint64_t* ids, size_t n) {
   for (size_t i = 0; i != n; ++i) s->FreeTasks({ids[i]});
 }
 
+// The batched heartbeat entry points are DEFINED as the loop over the single-servant calls.
+void yd_keep_servants_alive(yd_sched* s, int64_t now_ns, const yd_servant* servants, const int64_t* expires_in_ns, size_t n) {
+  for (size_t i = 0; i != n; ++i) yd_keep_servant_alive(s, now_ns, &servants[i], expires_in_ns[i]);
+}
+
+size_t yd_notify_servants_running_tasks(yd_sched* s, const yd_heartbeat_item* items, size_t n, uint64_t* unknown_out,
+                                        size_t* unknown_counts) {
+  size_t total = 0;
+  for (size_t i = 0; i != n; ++i) {
+    const size_t k = yd_notify_servant_running_tasks(s, items[i].servant_location, items[i].tasks, items[i].n_tasks,
+                                                     unknown_out + total);
+    if (unknown_counts) unknown_counts[i] = k;
+    total += k;
+  }
+  return total;
+}
+
 size_t yd_num_servants(yd_sched* s) { return s->servants.size(); }
 
 uint64_t yd_grant_capacity_bound(yd_sched* s) {

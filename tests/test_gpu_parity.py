@@ -87,6 +87,121 @@ def test_full_size_configs_match_reference_digest(make_dispatcher, name, solver)
     assert S.trace_digest(tr) == golden["sha256"]
 
 
+@pytest.mark.parametrize("merge_self", [True, False], ids=["merge", "sequential"])
+@pytest.mark.parametrize("name", ["cfg3", "cfg5-1m"])
+def test_million_request_configs_match_reference_digest(make_dispatcher, name, merge_self):
+    """BASELINE configs[2] at FULL size through its whole multi-round stream (1 M x 4 k; solve, free a
+    seeded half, renew, re-heartbeat, tick, re-offer: 2.7 M decisions) and configs[4]'s 8 k-servant
+    pool on the first 1 M requests of its queue, against the digests the reference itself produced
+    (tests/golden/make_golden.py HUGE) -- once with the merge solver deciding the coupled component
+    (20 % of the requestors are servants of it) and once with the sequential solver."""
+    golden = json.loads((GOLDEN / "digests.json").read_text())["streams"]
+    if name not in golden:
+        pytest.skip(f"no reference digest for {name}")
+    d = make_dispatcher("cuda", merge_self=merge_self)
+    r = S.Replayer(d, pinned=True)
+    tr = r.run(S.named_stream(name, d))
+    assert (r.decisions, r.granted) == (golden[name]["decisions"], golden[name]["granted"])
+    assert S.trace_digest(tr) == golden[name]["sha256"]
+
+
+@pytest.mark.parametrize("merge_self", [True, False], ids=["merge", "sequential"])
+@pytest.mark.parametrize("seed", range(3000, 3060))
+def test_fuzz_one_daemon_per_machine(make_dispatcher, seed, merge_self):
+    """Every servant on its own IP and many requestors that are servants: the merge solver's own-servant
+    rule, passed-over (pending) requests and -- capacity is tiny here -- the last-resort hand-back to the
+    sequential solver all get exercised; every third seed also against the reference itself."""
+    kinds = ("port", "ref") if REF_LIB.exists() and seed % 3 == 0 else ("port",)
+    traces = {}
+    for kind in ("cuda",) + kinds:
+        d = make_dispatcher(kind, merge_self=merge_self) if kind == "cuda" else make_dispatcher(kind)
+        st = S.fuzz_stream(d, seed, n_servants=6 + seed % 40, n_events=50, max_batch=30 + 40 * (seed % 5), unique_hosts=True)
+        traces[kind] = S.Replayer(d).run(st)
+        d.close()
+    for kind in kinds:
+        assert S.traces_equal(traces["cuda"], traces[kind]), f"cuda vs {kind}: " + S.first_mismatch(traces["cuda"], traces[kind])
+
+
+@pytest.mark.parametrize("chunk,rounds", [(32, 2), (64, 3), (256, 8)])
+@pytest.mark.parametrize("name", ["cfg2-random-small", "cfg-self-small", "cfg3-small"])
+def test_merge_solver_tiny_chunks_and_round_escalation(make_dispatcher, monkeypatch, name, chunk, rounds):
+    """Chunks far shorter than the healing length and too few rounds in the graph: the boundary states do
+    not settle, the solve stands down, reruns with more rounds and finally with the sequential solver --
+    the answers never change."""
+    monkeypatch.setenv("YDSCHED_MERGE_CHUNK", str(chunk))
+    monkeypatch.setenv("YDSCHED_MERGE_ROUNDS", str(rounds))
+    tr = _parity(make_dispatcher, name)
+    golden = json.loads((GOLDEN / "digests.json").read_text())["streams"]
+    assert S.trace_digest(tr) == golden[name]["sha256"]
+
+
+@pytest.mark.parametrize("burst", [3, 40, 400])
+def test_merge_solver_bursts_from_one_servant(make_dispatcher, burst):
+    """`make -j` on a machine that is itself a servant: long runs of consecutive requests from ONE servant's
+    IP.  Its own slots pass the whole run over (a pending run), other servants' slots then serve it."""
+    from yadcc_b200 import Servant, PRIORITY_USER
+
+    results = []
+    for kind in ("cuda", "port"):
+        d = make_dispatcher(kind)
+        dg = "ab" * 32
+        for i in range(60):
+            d.keep_servant_alive(Servant(f"10.9.0.{i}:8335", None, [dg], 8, 16, i % 3, 0, 64 << 30, 6 + i % 5, PRIORITY_USER),
+                                 10.0, now=0.0)
+        rng = np.random.default_rng(burst)
+        who = []
+        while len(who) < 500:
+            who += [int(rng.integers(0, 60))] * int(rng.integers(1, burst + 1))
+        ips = [f"10.9.0.{j}" if k % 7 else "172.16.0.1" for k, j in enumerate(who[:500])]
+        reqs = d.make_requests(500, [dg] * 500, ips, np.full(500, 8, np.uint32))
+        results.append(d.wait_for_starting_new_tasks(reqs, 0.5).copy())
+        results.append(d.servant_state()["running_tasks"].copy())
+    assert (results[0] == results[2]).all()
+    assert (results[1] == results[3]).all()
+
+
+@pytest.mark.parametrize("seed", range(0, 60, 2))
+def test_batched_heartbeats_on_cuda(make_dispatcher, seed):
+    """One tick's heartbeats as two calls (yd_keep_servants_alive, yd_notify_servants_running_tasks: one upload,
+    one sweep + one check kernel, one sync) against the reference's one-call-per-servant sequence."""
+    traces = {}
+    for kind in ("cuda", "port"):
+        d = make_dispatcher(kind)
+        st = S.fuzz_stream(d, seed, n_servants=8 + seed % 30, n_events=80)
+        # lengthen the notify runs: every servant reports after every tick
+        ev = []
+        for e in st.events:
+            ev.append(e)
+            if e[0] == "tick":
+                ev += [("notify_own", i, 17 * seed + i, [i, 10_000 + i]) for i in range(8 + seed % 30)]
+                ev += [("notify_own", 0, 5, []), ("notify", "203.0.113.9:1", [(1, 3, "aa")])]  # a repeat and a stranger
+        traces[kind] = S.Replayer(d, batch_heartbeats=(kind == "cuda")).run(S.Stream(st.name, ev))
+        d.close()
+    assert S.traces_equal(traces["cuda"], traces["port"]), S.first_mismatch(traces["cuda"], traces["port"])
+
+
+def test_heartbeat_reporting_ten_thousand_tasks(make_dispatcher):
+    """A heartbeat may list any number of running tasks (the reference takes whatever arrives,
+    task_dispatcher.cc:222-277), zombies or not: 10 000 ids, most of them bogus, with zombies present."""
+    from yadcc_b200 import PRIORITY_USER, RunningTask, Servant
+
+    out = []
+    for kind in ("cuda", "port"):
+        d = make_dispatcher(kind)
+        dg = "cd" * 32
+        for i in range(4):
+            d.keep_servant_alive(Servant(f"10.8.0.{i}:8335", None, [dg], 8, 64, 0, 0, 64 << 30, 40, PRIORITY_USER), 100.0, now=0.0)
+        g = d.wait_for_starting_new_tasks(d.make_requests(120, dg, "172.16.0.1", 8, expires_in=1.0), 0.0)
+        d.on_expiration_timer(now=5.0)  # every lease expired: 120 zombies
+        mine = [int(t) for t, sidx in zip(g["task_id"], g["servant_index"]) if sidx == 1]
+        ids = mine[::2] + list(range(1000, 1000 + 10_000))
+        loc = "10.8.0.1:8335"
+        unknown = d.notify_servant_running_tasks(loc, [RunningTask(k, t, loc, f"{t:064x}") for k, t in enumerate(ids)])
+        st = d.servant_state()
+        out.append((unknown, st["running_tasks"].tolist(), d.num_tasks()))
+    assert out[0] == out[1]
+
+
 def test_cfg1_vectors(make_dispatcher):
     z = np.load(GOLDEN / "cfg1_reference.npz")
     d = make_dispatcher("cuda")

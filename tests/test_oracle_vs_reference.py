@@ -50,3 +50,16 @@ def test_port_matches_committed_cfg1_vectors(make_dispatcher):
     assert (g["status"] == z["status"]).all()
     assert (g["task_id"] == z["task_id"]).all()
     assert (g["servant_index"] == z["servant_index"]).all()
+
+
+@pytest.mark.parametrize("kind", ["port", "ref"])
+@pytest.mark.parametrize("seed", range(0, 40, 3))
+def test_batched_heartbeats_equal_single_calls(make_dispatcher, kind, seed):
+    """yd_keep_servants_alive / yd_notify_servants_running_tasks are defined as the loop over the
+    single-servant calls: replaying a stream with its heartbeat runs batched changes nothing."""
+    traces = []
+    for batched in (False, True):
+        d = make_dispatcher(kind)
+        traces.append(S.Replayer(d, batch_heartbeats=batched).run(S.fuzz_stream(d, seed, n_servants=8 + seed % 30)))
+        d.close()
+    assert S.traces_equal(*traces), S.first_mismatch(*traces)

@@ -78,3 +78,42 @@ def test_wire_parser_survives_mutated_frames(make_dispatcher):
                     assert consumed == 0 and frame == b""
             batch = []
     assert min(verdicts.values()) > 100  # all three outcomes really occurred
+
+
+def test_wire_request_counts_are_not_trusted(make_dispatcher):
+    """immediate_reqs / prefetch_reqs are uint32s off the wire.  A caller with a BAD token and
+    immediate_reqs = 0xFFFFFFFF gets ACCESS_DENIED (scheduler_service_impl.cc:216-219) before
+    anything is sized for it; a caller with a good token gets exactly what the reference's loop
+    would hand out -- every free slot, then it stops at the first failure (:247-251)."""
+    import wire_protos as W
+    from yadcc_b200 import PRIORITY_USER, Servant
+    from yadcc_b200.service import SchedulerService
+
+    PB = W.PB
+    results = []
+    for kind in ("port", "ref"):
+        d = make_dispatcher(kind)
+        svc = SchedulerService(d, acceptable_user_tokens="usr", acceptable_servant_tokens="srv", token_seed=2)
+        dg = "d" * 64
+        for i in range(5):
+            d.keep_servant_alive(Servant(f"10.0.0.{i}:8335", None, [dg], 8, 16, 0, 0, 64 << 30, 4, PRIORITY_USER), 10.0, now=0.0)
+        bad = PB["WaitForStartingTaskRequest"](token="nope", immediate_reqs=0xFFFFFFFF, prefetch_reqs=0xFFFFFFFF,
+                                               next_keep_alive_in_ms=1000, min_version=1)
+        bad.env_desc.compiler_digest = dg
+        st, _, body = svc.call(W.SERVICE + "WaitForStartingTask", bad.SerializeToString(), "172.16.0.1", now=1.0)
+        assert st == 1003 and body == b""
+        good = PB["WaitForStartingTaskRequest"](token="usr", immediate_reqs=0xFFFFFFFF, prefetch_reqs=0xFFFFFFF0,
+                                                next_keep_alive_in_ms=1000, min_version=1)
+        good.env_desc.compiler_digest = dg
+        st, _, body = svc.call(W.SERVICE + "WaitForStartingTask", good.SerializeToString(), "172.16.0.1", now=1.0)
+        resp = PB["WaitForStartingTaskResponse"]()
+        resp.ParseFromString(body)
+        assert st == 0 and len(resp.grants) == 20  # 5 servants x max_tasks 4
+        results.append([(g.task_grant_id, g.servant_location) for g in resp.grants])
+        # and the same two as frames in one batch
+        frames = [(W.request_frame("WaitForStartingTask", bad, 7), "172.16.0.1"),
+                  (W.request_frame("WaitForStartingTask", good, 8), "172.16.0.1")]
+        out = svc.handle_frames(frames, now=1.5)
+        assert [o[2] for o in out] == [1003, 1001]  # the pool is full now: NO_QUOTA for the good caller
+        svc.close()
+    assert results[0] == results[1]

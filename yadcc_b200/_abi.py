@@ -96,6 +96,14 @@ class yd_running_task(C.Structure):
     ]
 
 
+class yd_heartbeat_item(C.Structure):
+    _fields_ = [
+        ("servant_location", C.c_char_p),
+        ("tasks", C.POINTER(yd_running_task)),
+        ("n_tasks", C.c_size_t),
+    ]
+
+
 class yd_service_config(C.Structure):
     _fields_ = [
         ("acceptable_user_tokens", C.c_char_p),
@@ -185,6 +193,9 @@ PROTOTYPES = [
     ("yd_free_tasks", None, [_P, _P, C.c_size_t]),
     ("yd_wait_for_starting_task_rpcs", C.c_size_t, [_P, C.c_int64, _P, C.c_size_t, _P, _P, C.c_size_t]),
     ("yd_grant_capacity_bound", C.c_uint64, [_P]),
+    ("yd_keep_servants_alive", None, [_P, C.c_int64, C.POINTER(yd_servant), C.POINTER(C.c_int64), C.c_size_t]),
+    ("yd_notify_servants_running_tasks", C.c_size_t,
+     [_P, C.POINTER(yd_heartbeat_item), C.c_size_t, C.POINTER(C.c_uint64), C.POINTER(C.c_size_t)]),
     ("yd_rpc_expanded_requests", C.c_size_t, [_P, _P, C.c_size_t]),
     ("yd_bloom_reset", C.c_int, [_P, C.c_uint64, C.c_uint32]),
     ("yd_bloom_load", C.c_int, [_P, _P, C.c_size_t, C.c_uint32]),

@@ -241,22 +241,43 @@ __global__ void k_compact_servants(uint32_t S_old, const uint32_t* __restrict__ 
   }
 }
 
-// ---- NotifyServantRunningTasks (cc:222-277) ----------------------------------
-// Sweep: zombies of servant `pos` that the servant no longer reports are freed
-// (UnsafeSweepZombiesOf, cc:453-476).  Reported ids are staged in shared memory.
-__global__ void k_notify_sweep(TaskRing ring, uint32_t pos, const unsigned long long* __restrict__ reported,
-                               uint32_t n, uint32_t* __restrict__ run, Counters* __restrict__ counters) {
-  extern __shared__ unsigned long long s_rep[];
-  for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) s_rep[i] = reported[i];
-  __syncthreads();
+// ---- NotifyServantRunningTasks (cc:222-277), any number of servants per launch ---------------
+// One heartbeat = (registry position, the task ids the servant reports).  The host sorts the
+// heartbeats of a batch by position: item_pos[] ascending, item_off[] the CSR offsets into ids[].
+struct NotifyBatch {
+  const uint32_t* item_pos;            // [n_items] ascending, distinct
+  const uint32_t* item_off;            // [n_items + 1]
+  const unsigned long long* ids;       // [item_off[n_items]] reported task_grant_ids
+  uint32_t n_items;
+};
+
+__device__ __forceinline__ uint32_t notify_find_item(const NotifyBatch& b, uint32_t pos) {
+  uint32_t lo = 0, hi = b.n_items;
+  while (lo < hi) {
+    const uint32_t mid = (lo + hi) >> 1;
+    const uint32_t p = b.item_pos[mid];
+    if (p == pos) return mid;
+    if (p < pos) lo = mid + 1; else hi = mid;
+  }
+  return kNone;
+}
+
+// Sweep: zombies of a heartbeating servant that the servant no longer reports are freed
+// (UnsafeSweepZombiesOf, cc:453-476).  One thread per lease of the live window; zombies are rare,
+// so the scan of the servant's reported ids (global memory, any length) is off the common path.
+__global__ void k_notify_sweep(TaskRing ring, NotifyBatch b, uint32_t* __restrict__ run,
+                               Counters* __restrict__ counters) {
   unsigned long long id = ring.lo + (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (id >= ring.next) return;
   uint64_t slot = id & ring.mask;
   uint32_t f = ring.flags[slot];
-  if ((f & (kTaskAlive | kTaskZombie)) != (kTaskAlive | kTaskZombie) || ring.srv[slot] != pos) return;
+  if ((f & (kTaskAlive | kTaskZombie)) != (kTaskAlive | kTaskZombie)) return;
+  const uint32_t pos = ring.srv[slot];
+  const uint32_t item = notify_find_item(b, pos);
+  if (item == kNone) return;  // that servant did not heartbeat in this batch
   const unsigned long long xid = ring.ext(id);
-  for (uint32_t i = 0; i < n; ++i) {
-    if (s_rep[i] == xid) return;  // still reported: stays a zombie
+  for (uint32_t i = b.item_off[item], e = b.item_off[item + 1]; i < e; ++i) {
+    if (b.ids[i] == xid) return;  // still reported: stays a zombie
   }
   ring.flags[slot] = 0;
   atomicSub(&run[pos], 1u);
@@ -264,15 +285,20 @@ __global__ void k_notify_sweep(TaskRing ring, uint32_t pos, const unsigned long 
   atomicAdd(&counters->zombies, ~0ull);
 }
 
-// Check: a reported id is "permitted" iff it is a live, non-zombie grant on this
-// servant (cc:257-262); everything else goes back to the daemon as unknown.
-__global__ void k_notify_check(TaskRing ring, uint32_t pos, const unsigned long long* __restrict__ reported,
-                               uint32_t n, uint8_t* __restrict__ permitted) {
+// Check: a reported id is "permitted" iff it is a live, non-zombie grant on the reporting
+// servant (cc:257-262); everything else goes back to the daemon as unknown.  One thread per id.
+__global__ void k_notify_check(TaskRing ring, NotifyBatch b, uint32_t n_ids, uint8_t* __restrict__ permitted) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+  if (i >= n_ids) return;
+  uint32_t lo = 0, hi = b.n_items;  // the item whose id range holds i
+  while (hi - lo > 1) {
+    const uint32_t mid = (lo + hi) >> 1;
+    if (b.item_off[mid] <= i) lo = mid; else hi = mid;
+  }
+  const uint32_t pos = b.item_pos[lo];
   unsigned long long id;
   uint8_t ok = 0;
-  if (ring.loc(reported[i], &id) && id >= ring.lo && id < ring.next) {
+  if (ring.loc(b.ids[i], &id) && id >= ring.lo && id < ring.next) {
     uint64_t slot = id & ring.mask;
     uint32_t f = ring.flags[slot];
     ok = (f & kTaskAlive) && !(f & kTaskZombie) && ring.srv[slot] == pos;

@@ -1270,63 +1270,130 @@ void yd_on_expiration_timer(yd_sched* s, int64_t now_ns) {
   s->lo = (c->min_live == ~0ull) ? s->next_id : c->min_live;
 }
 
-// NotifyServantRunningTasks, cc:222-277.
+// KeepServantAlive x n (cc:190-220): registry work only, the facts go up before the next solve.
+void yd_keep_servants_alive(yd_sched* s, int64_t now_ns, const yd_servant* servants, const int64_t* expires_in_ns, size_t n) {
+  for (size_t i = 0; i != n; ++i) yd_keep_servant_alive(s, now_ns, &servants[i], expires_in_ns[i]);
+}
+
+extern "C++" {
+namespace {
+// NotifyServantRunningTasks (cc:222-277) for heartbeats of DISTINCT known servants: one upload, one
+// sweep + one check kernel, one synchronisation, whatever the number of servants or reported tasks.
+// `idx` = the items of the caller's array handled here, `pos` their registry positions.
+void NotifyDistinct(yd_sched* s, const yd_heartbeat_item* items, const std::vector<uint32_t>& idx,
+                    const std::vector<uint32_t>& pos, std::vector<std::vector<uint8_t>>& permitted) {
+  const uint32_t m = (uint32_t)idx.size();
+  std::vector<uint32_t> order(m);
+  std::iota(order.begin(), order.end(), 0u);
+  std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return pos[a] < pos[b]; });
+  size_t total = 0;
+  for (uint32_t k = 0; k != m; ++k) total += items[idx[k]].n_tasks;
+  if (total > 0xfffffff0ull) { fprintf(stderr, "ydsched: heartbeat batch reports too many tasks\n"); abort(); }
+  const bool window = s->next_id > s->lo;
+  if (!window || (total == 0 && s->zombies_ub == 0)) return;  // nothing can be permitted, nothing to sweep
+  // staging layout: ids[total] (u64) | item_off[m + 1] | item_pos[m] | (device only) permitted[total]
+  const size_t b_ids = total * 8, b_off = (size_t(m) + 1) * 4, b_pos = size_t(m) * 4;
+  s->h_small.ensure(b_ids + b_off + b_pos + total + 64);
+  char* hb = s->h_small.as<char>();
+  unsigned long long* h_ids = reinterpret_cast<unsigned long long*>(hb);
+  uint32_t* h_off = reinterpret_cast<uint32_t*>(hb + b_ids);
+  uint32_t* h_pos = h_off + m + 1;
+  uint8_t* h_ok = reinterpret_cast<uint8_t*>(hb + b_ids + b_off + b_pos);
+  size_t at = 0;
+  for (uint32_t k = 0; k != m; ++k) {
+    const yd_heartbeat_item& it = items[idx[order[k]]];
+    h_off[k] = (uint32_t)at;
+    h_pos[k] = pos[order[k]];
+    for (size_t i = 0; i != it.n_tasks; ++i) h_ids[at++] = it.tasks[i].task_grant_id;
+  }
+  h_off[m] = (uint32_t)at;
+  cudaStream_t st = s->st;
+  s->d_ids.ensure(b_ids + b_off + b_pos + 8);
+  s->d_ok.ensure(std::max<size_t>(total, 1));
+  YD_CUDA_CHECK(cudaMemcpyAsync(s->d_ids.p, hb, b_ids + b_off + b_pos, cudaMemcpyHostToDevice, st));
+  yd::NotifyBatch nb{};
+  nb.ids = s->d_ids.as<unsigned long long>();
+  nb.item_off = reinterpret_cast<const uint32_t*>(s->d_ids.as<char>() + b_ids);
+  nb.item_pos = nb.item_off + m + 1;
+  nb.n_items = m;
+  if (s->zombies_ub) {
+    const uint64_t cnt = s->next_id - s->lo;
+    yd::k_notify_sweep<<<(unsigned)((cnt + 255) / 256), 256, 0, st>>>(s->ring(), nb, s->d_run.as<uint32_t>(),
+                                                                       s->d_counters.as<Counters>());
+    YD_CUDA_CHECK(cudaGetLastError());
+  }
+  if (total) {
+    yd::k_notify_check<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(s->ring(), nb, (uint32_t)total, s->d_ok.as<uint8_t>());
+    YD_CUDA_CHECK(cudaGetLastError());
+    YD_CUDA_CHECK(cudaMemcpyAsync(h_ok, s->d_ok.p, total, cudaMemcpyDeviceToHost, st));
+  }
+  s->FetchCounters();  // the one synchronisation
+  s->zombies_ub = s->h_counters.as<Counters>()->zombies;
+  for (uint32_t k = 0; k != m; ++k) {
+    std::vector<uint8_t>& p = permitted[idx[order[k]]];
+    if (total) memcpy(p.data(), h_ok + h_off[k], p.size());
+  }
+}
+}  // namespace
+}  // extern "C++"
+
+// NotifyServantRunningTasks x n, in array order (cc:222-277).
+size_t yd_notify_servants_running_tasks(yd_sched* s, const yd_heartbeat_item* items, size_t n, uint64_t* unknown_out,
+                                        size_t* unknown_counts) {
+  YD_CUDA_CHECK(cudaSetDevice(s->device));
+  s->SyncServantState();
+  std::vector<std::vector<uint8_t>> permitted(n);
+  for (size_t i = 0; i != n; ++i) permitted[i].assign(items[i].n_tasks, 0);
+  // Heartbeats of different servants touch disjoint leases, so any number of them is one device pass.
+  // A servant that appears twice must see its first heartbeat's sweep: the batch is cut there.
+  std::vector<uint32_t> idx, pos;
+  std::unordered_map<uint32_t, char> seen;
+  std::vector<uint32_t> item_pos(n, kNone);
+  for (size_t i = 0; i != n; ++i) {
+    auto it = s->loc2pos.find(items[i].servant_location ? items[i].servant_location : "");
+    if (it == s->loc2pos.end()) continue;  // the servant itself expired: every id is unknown (cc:243-245)
+    item_pos[i] = it->second;
+    if (seen.count(it->second)) {
+      NotifyDistinct(s, items, idx, pos, permitted);
+      idx.clear(); pos.clear(); seen.clear();
+    }
+    seen.emplace(it->second, 1);
+    idx.push_back((uint32_t)i);
+    pos.push_back(it->second);
+  }
+  if (!idx.empty()) NotifyDistinct(s, items, idx, pos, permitted);
+  size_t total = 0;
+  for (size_t i = 0; i != n; ++i) {
+    const yd_heartbeat_item& it = items[i];
+    size_t k = 0;
+    if (item_pos[i] == kNone) {
+      for (size_t t = 0; t != it.n_tasks; ++t) unknown_out[total + k++] = it.tasks[t].task_grant_id;
+    } else {
+      std::vector<RunningRec> kept;
+      for (size_t t = 0; t != it.n_tasks; ++t) {
+        if (!permitted[i][t]) {
+          unknown_out[total + k++] = it.tasks[t].task_grant_id;
+        } else {
+          kept.push_back(RunningRec{it.tasks[t].servant_task_id, it.tasks[t].task_grant_id,
+                                    it.tasks[t].servant_location ? it.tasks[t].servant_location : "",
+                                    it.tasks[t].task_digest ? it.tasks[t].task_digest : ""});
+        }
+      }
+      // RunningTaskBookkeeper::SetServantRunningTasks, running_task_bookkeeper.cc:24-29
+      s->running.erase(it.servant_location);
+      s->running.emplace(it.servant_location, std::move(kept));
+    }
+    if (unknown_counts) unknown_counts[i] = k;
+    total += k;
+  }
+  return total;
+}
+
+// NotifyServantRunningTasks, cc:222-277: a batch of one.
 size_t yd_notify_servant_running_tasks(yd_sched* s, const char* servant_location, const yd_running_task* tasks,
                                        size_t n, uint64_t* unknown_out) {
-  auto it = s->loc2pos.find(servant_location);
-  if (it == s->loc2pos.end()) {  // the servant itself expired: every id is unknown (cc:243-245)
-    for (size_t i = 0; i != n; ++i) unknown_out[i] = tasks[i].task_grant_id;
-    return n;
-  }
-  const uint32_t pos = it->second;
-  YD_CUDA_CHECK(cudaSetDevice(s->device));
-  cudaStream_t st = s->st;
-  s->SyncServantState();
-  std::vector<uint8_t> permitted(n, 0);
-  const bool window = s->next_id > s->lo;
-  if (window && (n || s->zombies_ub)) {
-    s->h_small.ensure(std::max<size_t>(n * 9, 64));
-    unsigned long long* hid = s->h_small.as<unsigned long long>();
-    for (size_t i = 0; i != n; ++i) hid[i] = tasks[i].task_grant_id;
-    s->d_ids.ensure(std::max<size_t>(n * 8, 8));
-    s->d_ok.ensure(std::max<size_t>(n, 1));
-    if (n) YD_CUDA_CHECK(cudaMemcpyAsync(s->d_ids.p, hid, n * 8, cudaMemcpyHostToDevice, st));
-    if (s->zombies_ub) {
-      if (n * 8 > 48 * 1024) { fprintf(stderr, "ydsched: heartbeat reports too many tasks\n"); abort(); }
-      uint64_t cnt = s->next_id - s->lo;
-      yd::k_notify_sweep<<<(unsigned)((cnt + 255) / 256), 256, n * 8, st>>>(
-          s->ring(), pos, s->d_ids.as<unsigned long long>(), (uint32_t)n, s->d_run.as<uint32_t>(),
-          s->d_counters.as<Counters>());
-      YD_CUDA_CHECK(cudaGetLastError());
-    }
-    if (n) {
-      yd::k_notify_check<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(
-          s->ring(), pos, s->d_ids.as<unsigned long long>(), (uint32_t)n, s->d_ok.as<uint8_t>());
-      YD_CUDA_CHECK(cudaGetLastError());
-      uint8_t* hp = reinterpret_cast<uint8_t*>(hid + n);
-      YD_CUDA_CHECK(cudaMemcpyAsync(hp, s->d_ok.p, n, cudaMemcpyDeviceToHost, st));
-      s->FetchCounters();
-      memcpy(permitted.data(), hp, n);
-    } else {
-      s->FetchCounters();
-    }
-    s->zombies_ub = s->h_counters.as<Counters>()->zombies;
-  }
-  size_t k = 0;
-  std::vector<RunningRec> kept;
-  for (size_t i = 0; i != n; ++i) {
-    if (!permitted[i]) {
-      unknown_out[k++] = tasks[i].task_grant_id;
-    } else {
-      kept.push_back(RunningRec{tasks[i].servant_task_id, tasks[i].task_grant_id,
-                                tasks[i].servant_location ? tasks[i].servant_location : "",
-                                tasks[i].task_digest ? tasks[i].task_digest : ""});
-    }
-  }
-  // RunningTaskBookkeeper::SetServantRunningTasks, running_task_bookkeeper.cc:24-29
-  s->running.erase(servant_location);
-  s->running.emplace(servant_location, std::move(kept));
-  return k;
+  const yd_heartbeat_item item{servant_location, tasks, n};
+  return yd_notify_servants_running_tasks(s, &item, 1, unknown_out, nullptr);
 }
 
 // RunningTaskBookkeeper::GetRunningTasks, running_task_bookkeeper.cc:36-43.

@@ -86,6 +86,7 @@ class TaskDispatcher:
         servant_min_memory_for_accepting_new_task: str | None = None,
         solver: int = 0,
         graphs: bool = True,
+        merge_self: bool = True,
         id_stride: int = 0,
         id_offset: int = 0,
     ):
@@ -99,7 +100,9 @@ class TaskDispatcher:
                 else None
             ),
             solver=solver,
-            reserved=0 if graphs else 1,  # bit 0: do not capture the solve into a CUDA graph (per-phase timing)
+            # bit 0: do not capture the solve into a CUDA graph (per-phase timing); bit 1 (test switch): components
+            # whose requestors are servants go to the sequential solver instead of the merge solver
+            reserved=(0 if graphs else 1) | (0 if merge_self else 2),
             id_stride=id_stride,
             id_offset=id_offset,
         )
@@ -256,11 +259,12 @@ class TaskDispatcher:
         self._lib.yd_free_tasks(self._h, ids.ctypes.data, ids.shape[0])
 
     # -- servant maintenance (task_dispatcher.h:157-181) -------------------
-    def keep_servant_alive(self, servant: Servant, expires_in: float, *, now: float = 0.0) -> None:
+    def _servant_struct(self, servant: Servant, keep: list) -> "_abi.yd_servant":
         envs = [e.encode() for e in servant.environments]
         arr = (C.c_char_p * max(len(envs), 1))(*envs)
         rep = servant.reported_location if servant.reported_location is not None else servant.observed_location
-        sv = _abi.yd_servant(
+        keep.append((envs, arr))
+        return _abi.yd_servant(
             version=servant.version,
             priority=servant.priority,
             not_accepting_task_reason=servant.not_accepting_task_reason,
@@ -274,7 +278,46 @@ class TaskDispatcher:
             total_memory_in_bytes=servant.total_memory_in_bytes,
             memory_available_in_bytes=servant.memory_available_in_bytes,
         )
+
+    def keep_servant_alive(self, servant: Servant, expires_in: float, *, now: float = 0.0) -> None:
+        keep: list = []
+        sv = self._servant_struct(servant, keep)
         self._lib.yd_keep_servant_alive(self._h, _ns(now), C.byref(sv), _ns(expires_in))
+
+    def keep_servants_alive(self, servants: Sequence[Servant], expires_in: Sequence[float] | float, *, now: float = 0.0) -> None:
+        """KeepServantAlive for a whole tick's heartbeats in one call (yd_keep_servants_alive)."""
+        n = len(servants)
+        keep: list = []
+        arr = (_abi.yd_servant * max(n, 1))(*[self._servant_struct(sv, keep) for sv in servants])
+        exp = [expires_in] * n if isinstance(expires_in, (int, float)) else list(expires_in)
+        ex = (C.c_int64 * max(n, 1))(*[_ns(e) for e in exp])
+        self._lib.yd_keep_servants_alive(self._h, _ns(now), arr, ex, n)
+
+    def notify_servants_running_tasks(self, batch: Sequence[tuple[str, Sequence[RunningTask]]]) -> list[list[int]]:
+        """NotifyServantRunningTasks for many servants in one call: [(location, tasks)] -> unknown ids per item."""
+        n = len(batch)
+        items = (_abi.yd_heartbeat_item * max(n, 1))()
+        keep = []
+        total = 0
+        for i, (loc, tasks) in enumerate(batch):
+            m = len(tasks)
+            arr = (_abi.yd_running_task * max(m, 1))()
+            for k, t in enumerate(tasks):
+                l2, dig = t.servant_location.encode(), t.task_digest.encode()
+                keep.append((l2, dig))
+                arr[k] = _abi.yd_running_task(t.servant_task_id, t.task_grant_id, l2, dig)
+            lb = loc.encode()
+            keep.append((arr, lb))
+            items[i] = _abi.yd_heartbeat_item(lb, arr, m)
+            total += m
+        out = (C.c_uint64 * max(total, 1))()
+        counts = (C.c_size_t * max(n, 1))()
+        self._lib.yd_notify_servants_running_tasks(self._h, items, n, out, counts)
+        res, at = [], 0
+        for i in range(n):
+            res.append([int(out[at + k]) for k in range(counts[i])])
+            at += counts[i]
+        return res
 
     def notify_servant_running_tasks(self, servant_location: str, tasks: Sequence[RunningTask]) -> list[int]:
         n = len(tasks)

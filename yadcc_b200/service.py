@@ -108,7 +108,7 @@ class SchedulerService:
         assert rpcs.dtype == _abi.RPC_WAIT_DTYPE and rpcs.flags.c_contiguous and len(tokens) == len(rpcs)
         n = rpcs.shape[0]
         tok = (C.c_char_p * max(n, 1))(*[t.encode() for t in tokens])
-        cap = int(rpcs["immediate_reqs"].sum() + rpcs["prefetch_reqs"].sum())
+        cap = int(self._lib.yd_rpc_expanded_requests(self.dispatcher._h, rpcs.ctypes.data, n))
         results = np.zeros(n, dtype=_abi.RPC_RESULT_DTYPE)
         grants = np.zeros(max(cap, 1), dtype=GRANT_DTYPE)
         k = self._lib.yd_service_wait_for_starting_tasks(self._h, _ns(now), tok, rpcs.ctypes.data, n,

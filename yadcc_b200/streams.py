@@ -66,8 +66,13 @@ class Stream:
 class Replayer:
     """Drives a TaskDispatcher with a Stream and records everything it returns."""
 
-    def __init__(self, dispatcher: TaskDispatcher, *, pinned: bool = False, on_solve: Callable | None = None):
+    def __init__(self, dispatcher: TaskDispatcher, *, pinned: bool = False, on_solve: Callable | None = None,
+                 batch_heartbeats: bool = False):
+        """`batch_heartbeats`: runs of consecutive "hb" events with one timestamp go through
+        keep_servants_alive, runs of consecutive "notify"/"notify_own" events through
+        notify_servants_running_tasks (one call each); the trace is the same by definition."""
         self.d = dispatcher
+        self.batch_heartbeats = batch_heartbeats
         self.pinned = pinned
         self.on_solve = on_solve
         self.pending = np.zeros(0, dtype=REQ_DTYPE)
@@ -94,11 +99,49 @@ class Replayer:
             self.on_solve(self.d, reqs, g)
         return g
 
+    def _notify_args(self, ev):
+        """(location, tasks) of a notify / notify_own event, or None if the servant index is gone."""
+        d = self.d
+        if ev[0] == "notify":
+            _, loc, tasks = ev
+            return loc, [RunningTask(a, b, loc, c) for a, b, c in tasks]
+        _, sidx, drop_seed, extra = ev
+        loc = d.servant_location(sidx)
+        if loc is None:
+            return None
+        own = sorted(t for t, s in self.outstanding.items() if s == sidx)
+        rng = np.random.default_rng(drop_seed)
+        own = [t for t in own if rng.random() < 0.8]
+        ids = own + list(extra)
+        return loc, [RunningTask(1000 + k, t, loc, f"{t:064x}") for k, t in enumerate(ids)]
+
     def run(self, stream: Stream) -> list[np.ndarray]:
         d = self.d
         trace: list[np.ndarray] = []
-        for ev in stream.events:
+        events = stream.events
+        pos = 0
+        while pos < len(events):
+            ev = events[pos]
+            pos += 1
             kind = ev[0]
+            if self.batch_heartbeats and kind == "hb":
+                run = [ev]
+                while pos < len(events) and events[pos][0] == "hb" and events[pos][1] == ev[1]:
+                    run.append(events[pos])
+                    pos += 1
+                d.keep_servants_alive([e[2] for e in run], [e[3] for e in run], now=ev[1])
+                continue
+            if self.batch_heartbeats and kind in ("notify", "notify_own"):
+                run = [ev]
+                while pos < len(events) and events[pos][0] in ("notify", "notify_own"):
+                    run.append(events[pos])
+                    pos += 1
+                # (servant indices and outstanding grants do not change inside the run: arguments up front)
+                args = [self._notify_args(e) for e in run]
+                res = iter(d.notify_servants_running_tasks([a for a in args if a is not None]))
+                for a in args:
+                    trace.append(np.asarray(next(res) if a is not None else [], dtype=np.uint64))
+                continue
             if kind == "hb":
                 _, now, sv, exp = ev
                 d.keep_servant_alive(sv, exp, now=now)
@@ -391,7 +434,7 @@ def rounds_stream(w: Workload, d: TaskDispatcher, max_rounds: int = 8, free_frac
 
 
 def fuzz_stream(d: TaskDispatcher, seed: int, n_servants: int = 24, n_events: int = 60, max_batch: int = 40,
-                wide: bool = False) -> Stream:
+                wide: bool = False, unique_hosts: bool = False) -> Stream:
     """Random interleaving of all event kinds over a small cluster.
 
     Covers: several ports on one IP (only the first free one is 'self'),
@@ -400,14 +443,16 @@ def fuzz_stream(d: TaskDispatcher, seed: int, n_servants: int = 24, n_events: in
     versions, unknown environments, capacity shrinking below running_tasks,
     lease expiry -> zombies -> sweep on heartbeat, servant expiry -> orphans,
     freeing unknown / duplicate ids, heartbeats from unknown locations.
-    `wide` adds capacities above 32768 (the wide-key solver path).
+    `wide` adds capacities above 32768 (the wide-key solver path).  `unique_hosts` gives every
+    servant its own IP (one daemon per machine): requestors that are servants then have exactly
+    one "self" servant, which is the shape the merge solver takes on itself.
     """
     rng = np.random.default_rng(seed)
     dgs = [hex_digest(rng) for _ in range(int(rng.integers(1, 5)))]
-    hosts = [f"10.0.0.{i}" for i in range(max(2, n_servants // 2))]
+    hosts = [f"10.0.{i >> 8}.{i & 255}" for i in range(n_servants if unique_hosts else max(2, n_servants // 2))]
 
     def rand_servant(i: int) -> Servant:
-        host = hosts[int(rng.integers(0, len(hosts)))]
+        host = hosts[i] if unique_hosts else hosts[int(rng.integers(0, len(hosts)))]
         nproc = int(rng.choice([0, 2, 4, 8, 16, 32, 40000 if wide else 24]))
         mt = int(rng.choice([0, 2, 3, 7, 8, 12, 70000 if wide else 30]))
         k = int(rng.integers(0 if rng.random() < 0.2 else 1, len(dgs) + 1))
