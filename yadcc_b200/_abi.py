@@ -243,9 +243,39 @@ def load_library(path: os.PathLike | str | None = None) -> C.CDLL:
         fn = getattr(lib, name)  # AttributeError if the symbol is missing
         fn.restype = restype
         fn.argtypes = argtypes
+    # include/ydshard.h: only the CUDA library has the range-sharded multi-GPU path
+    for name, restype, argtypes in SHARD_PROTOTYPES:
+        fn = getattr(lib, name, None)
+        if fn is not None:
+            fn.restype = restype
+            fn.argtypes = argtypes
     lib._yd_path = str(p)
     return lib
 
+
+class yd_shard_stats(C.Structure):
+    _fields_ = [
+        ("total_ms", C.c_float),
+        ("exchange_ms", C.c_float * 4),
+        ("exchange_bytes", C.c_uint64 * 4),
+        ("decisions_local", C.c_uint64),
+        ("granted_local", C.c_uint64),
+        ("granted_total", C.c_uint64),
+        ("merge_rounds", C.c_uint32),
+        ("kernel_launches", C.c_uint32),
+    ]
+
+
+SHARD_UNIQUE_ID_BYTES = 128
+# Every symbol include/ydshard.h declares.
+SHARD_PROTOTYPES = [
+    ("yd_shard_unique_id", C.c_int, [_P]),
+    ("yd_shard_init", C.c_int, [_P, C.c_int, C.c_int, _P]),
+    ("yd_shard_finalize", None, [_P]),
+    ("yd_shard_wait_for_starting_new_tasks", C.c_int, [_P, C.c_int64, _P, C.c_size_t, _P]),
+    ("yd_shard_free_tasks", C.c_int, [_P, _P, C.c_size_t]),
+    ("yd_shard_last_stats", C.c_int, [_P, C.POINTER(yd_shard_stats)]),
+]
 
 # Every symbol include/ydservice.h declares.
 SERVICE_PROTOTYPES = [

@@ -148,6 +148,46 @@ __device__ __forceinline__ uint32_t self_servant(const TopoView& t, uint32_t ip,
   return mine == 1 ? self : kNone;
 }
 
+// Range-sharded queue: every rank has inserted the classes of ITS requests; `gathered` holds all the
+// ranks' tables (per rank `stride` u32 words: kClsTableSize 8-byte keys, then n_comps component flags).
+// One warp rebuilds the table from them in a fixed order (rank-major, slot order, one insert at a
+// time), so every rank ends up with the SAME table -- and therefore the same class ids, lists and
+// solver modes -- and ORs the flags.
+__global__ void __launch_bounds__(32) k_cls_merge_tables(const uint32_t* __restrict__ gathered, uint32_t stride,
+                                                         uint32_t world, uint32_t n_comps, ClassTable ct) {
+  const uint32_t lane = threadIdx.x;
+  for (uint32_t i = lane; i < kClsTableSize; i += 32) ct.keys[i] = kClsEmpty;
+  for (uint32_t c = lane; c < n_comps; c += 32) {
+    uint32_t f = 0;
+    for (uint32_t g = 0; g < world; ++g) f |= gathered[size_t(g) * stride + 2 * kClsTableSize + c];
+    ct.comp_flags[c] = f;
+  }
+  __syncwarp();
+  for (uint32_t g = 0; g < world; ++g) {
+    const unsigned long long* keys = reinterpret_cast<const unsigned long long*>(gathered + size_t(g) * stride);
+    for (uint32_t s0 = 0; s0 < kClsTableSize; s0 += 32) {
+      const unsigned long long key = keys[s0 + lane];
+      uint32_t todo = __ballot_sync(0xffffffffu, key != kClsEmpty);
+      while (todo) {
+        const uint32_t b = __ffs(todo) - 1;
+        todo &= todo - 1;
+        if (lane == b) {
+          uint32_t s = cls_hash(key);
+          bool done = false;
+          for (uint32_t probe = 0; probe < kClsTableSize && !done; ++probe) {
+            const unsigned long long k = ct.keys[s];
+            if (k == kClsEmpty) { ct.keys[s] = key; done = true; }
+            else if (k == key) done = true;
+            else s = (s + 1) & (kClsTableSize - 1);
+          }
+          if (!done) ct.meta[1] = 1;
+        }
+        __syncwarp();
+      }
+    }
+  }
+}
+
 // One block: deterministic class ids (= rank of the occupied table slot), per-class
 // eligible-servant counts, and the solver mode of every component:
 //   comp_mode 1 = data-parallel path (one class, no request from one of its own servants),
@@ -276,6 +316,7 @@ struct SlotDecode {
   const uint32_t* row_off;
   const uint32_t* row_len;
   const uint32_t* run;
+  uint32_t static_rows;  // rows hold every running_tasks value from 0 (table kept across solves): slot k of a row IS r = k
 };
 
 __device__ __forceinline__ bool decode_slot(const SlotDecode& d, const TopoView& t, uint32_t i, uint32_t m,
@@ -286,7 +327,12 @@ __device__ __forceinline__ bool decode_slot(const SlotDecode& d, const TopoView&
   pos = d.slot_owner[orig];
   const uint32_t k = orig - d.row_off[pos];
   if (k >= d.row_len[pos]) return false;  // (defensive: the stream path's rows carry no sentinel)
-  r = d.run[pos] + k;
+  if (d.static_rows) {
+    r = k;
+    if (r < d.run[pos]) return false;  // the servant has filled that slot already
+  } else {
+    r = d.run[pos] + k;
+  }
   comp = t.sv_comp[pos];
   return comp != kNone;
 }

@@ -57,9 +57,30 @@ struct Counters {
 // of the same size class.
 struct DynParams {
   uint32_t n;  // exact number of requests (grids are sized for the next power of two)
-  uint32_t pad;
+  uint32_t slot_clamp;  // no servant needs more slots than the batch has requests: n on one GPU, the whole
+                        // queue's length (or "no limit") when the queue is sharded over ranks
   long long now_ns;
   unsigned long long ring_lo, ring_next;
+};
+
+// Where the per-class FIFO request records of the merge solver live, and how this rank's piece of
+// the queue fits into the whole (one GPU: the whole queue is this rank's).  Filled by k_rq_layout.
+struct RqLayout {
+  uint32_t* goff;    // [classes] requests of the class on LOWER ranks (0 on one GPU)
+  uint32_t* gn;      // [classes] requests of the class in the whole queue
+  uint32_t* win;     // [classes] how many of them have a record in rq: global class ranks [0, win)
+  uint32_t* base;    // [classes] first record of the class in rq
+  uint32_t* total;   // [1] records in rq
+  uint32_t q_base;   // global queue index of this rank's first request
+  uint32_t n_local;  // requests this rank holds (bounds res[] writes; exact value, not the grid bound)
+  uint32_t sharded;  // 1: the queue is range-sharded over several ranks (shard.cuh); 0: the four arrays above are not
+                     //    used, the layout is the FIFO rank scan itself (class c's records start where its ranks do)
+  const uint32_t* rank_off;  // scanned (class-major, tile-minor) request counts of this rank
+  uint32_t nrt;              // tiles per class row
+  __device__ __forceinline__ uint32_t Goff(uint32_t c) const { return sharded ? goff[c] : 0u; }
+  __device__ __forceinline__ uint32_t Gn(uint32_t c) const { return sharded ? gn[c] : rank_off[(c + 1) * nrt] - rank_off[c * nrt]; }
+  __device__ __forceinline__ uint32_t Win(uint32_t c) const { return sharded ? win[c] : Gn(c); }
+  __device__ __forceinline__ uint32_t Base(uint32_t c) const { return sharded ? base[c] : rank_off[c * nrt]; }
 };
 
 struct ServantArrays {

@@ -73,6 +73,49 @@ __global__ void __launch_bounds__(kRankTile) k_rank_count(const yd_task_req* __r
   }
 }
 
+// Per-class layout of the merge solver's request records (RqLayout) for the range-sharded queue.  (One GPU: class
+// c's records are its whole FIFO list, stored where the rank scan put it -- RqLayout derives that itself and this
+// kernel is not launched.)  Called twice: first (`lcnt_all` == null) it only reports this rank's per-class
+// request counts for the exchange; then (`lcnt_all` = every
+// rank's per-class request counts, rank-major, cls_bound words per rank): this rank's requests of class
+// c follow those of the lower ranks, and only the head of the class list that slots can reach is kept --
+// one record per slot of the class's list plus a margin for requests passed over by their own servant
+// (a request beyond it makes the merge solver hand the batch back, solve_merge.cuh).
+constexpr uint32_t kRqMargin = 1024;
+
+__global__ void __launch_bounds__(256) k_rq_layout(ClassTable ct, const uint32_t* __restrict__ comp_mode,
+                                                   const uint32_t* __restrict__ rank_off, uint32_t n_rank_tiles,
+                                                   const uint32_t* __restrict__ list_off, uint32_t n_list_tiles,
+                                                   const uint32_t* __restrict__ lcnt_all, uint32_t rank, uint32_t world,
+                                                   uint32_t* __restrict__ lcnt_out, RqLayout L) {
+  __shared__ uint32_t s_win[kMaxClasses];
+  const uint32_t ncls = min(ct.meta[0], ct.cls_bound);
+  for (uint32_t c = threadIdx.x; c < ncls; c += blockDim.x) {
+    const uint32_t mine = rank_off[(c + 1) * n_rank_tiles] - rank_off[c * n_rank_tiles];
+    if (lcnt_out) lcnt_out[c] = mine;  // (sharded: what this rank contributes to the next exchange)
+    if (lcnt_all) {
+      uint32_t before = 0, all = 0;
+      for (uint32_t g = 0; g < world; ++g) {
+        const uint32_t v = lcnt_all[g * ct.cls_bound + c];
+        if (g < rank) before += v;
+        all += v;
+      }
+      const uint32_t len = list_off[(c + 1) * n_list_tiles] - list_off[c * n_list_tiles];
+      L.goff[c] = before; L.gn[c] = all;
+      s_win[c] = comp_mode[ct.cls_comp[c]] == 2 ? min(all, len + kRqMargin) : 0u;  // only the merge solver reads records
+      L.win[c] = s_win[c];
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t run = 0;
+    if (lcnt_all) {
+      for (uint32_t c = 0; c < ncls; ++c) { L.base[c] = run; run += s_win[c]; }
+    }
+    *L.total = run;
+  }
+}
+
 // tile_off = exclusive scan of tile_cnt over (class-major, tile-minor).
 __global__ void __launch_bounds__(256) k_rank_assign(const DynParams* __restrict__ dp, uint32_t n_tiles, TopoView t,
                                                      ClassTable ct,
@@ -83,7 +126,7 @@ __global__ void __launch_bounds__(256) k_rank_assign(const DynParams* __restrict
                                                      const uint32_t* __restrict__ list_off, uint32_t n_list_tiles,
                                                      const uint2* __restrict__ list, ServantArrays sv,
                                                      const uint32_t* __restrict__ comp_mode,
-                                                     uint2* __restrict__ rq, uint32_t* __restrict__ res) {
+                                                     uint2* __restrict__ rq, uint32_t* __restrict__ res, RqLayout L) {
   const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= dp->n) return;
   // Overflow flagged by the class table or the list builder: the host reruns this batch (bigger
@@ -92,12 +135,13 @@ __global__ void __launch_bounds__(256) k_rank_assign(const DynParams* __restrict
   const uint32_t c = rcls[q];
   if (c == kNone) return;  // not ours: the sequential solver (or nobody) answers it
   if (ct.cls_nelig[c] == 0) { res[q] = kResEnvNotFound; return; }  // cc:105-108
-  const uint32_t rank = tile_off[c * n_tiles + q / kRankTile] - tile_off[c * n_tiles] + rrank[q];
+  // FIFO rank inside the class, over the whole queue (lower ranks' requests come first)
+  const uint32_t rank = L.Goff(c) + tile_off[c * n_tiles + q / kRankTile] - tile_off[c * n_tiles] + rrank[q];
   if (comp_mode[ct.cls_comp[c]] == 2) {
     // merge solver: publish the class's FIFO request list (class c owns rq[tile_off[c][0] ...)) as
     // (request, its own servant in the component or kNone);
     // the verdict stays Timeout unless a slot picks this request (solve_merge.cuh)
-    rq[tile_off[c * n_tiles] + rank] = make_uint2(q, rself[q]);
+    if (rank < L.Win(c)) rq[L.Base(c) + rank] = make_uint2(L.q_base + q, rself[q]);
     res[q] = kResTimeout;
     return;
   }

@@ -29,11 +29,14 @@ namespace yd {
 __global__ void __launch_bounds__(1024) k_slot_rows(uint32_t S, const DynParams* __restrict__ dp,
                                                     ServantArrays sv, uint32_t* __restrict__ row_off,
                                                     uint32_t* __restrict__ row_len,
-                                                    Counters* __restrict__ counters, uint32_t sentinel) {
+                                                    Counters* __restrict__ counters, uint32_t sentinel,
+                                                    uint32_t static_rows) {
   __shared__ uint32_t warp_sums[32];
   __shared__ uint32_t carry_s;
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const uint32_t n_requests = dp->n;
+  // static_rows: the rows of ALL running_tasks values [0, free_end) -- the table then depends on the heartbeat
+  // facts only and is kept across solves (slots a servant has already filled are filtered out per solve)
+  const uint32_t n_requests = static_rows ? 0xFFFFFFFFu : dp->slot_clamp;
   if (tid == 0) carry_s = 0;
   __syncthreads();
   for (uint32_t base = 0; base < S; base += 1024) {
@@ -41,7 +44,7 @@ __global__ void __launch_bounds__(1024) k_slot_rows(uint32_t S, const DynParams*
     uint32_t len = 0;
     if (s < S) {
       uint32_t end = free_end(sv.max_tasks[s], sv.nproc[s], sv.load[s], sv.flags[s]);
-      uint32_t r0 = sv.run[s];
+      uint32_t r0 = static_rows ? 0u : sv.run[s];
       len = end > r0 ? end - r0 : 0;
       if (len > n_requests) len = n_requests;  // a servant cannot win more than n times
       row_len[s] = len;
@@ -90,13 +93,14 @@ __global__ void __launch_bounds__(256) k_slot_fill(uint32_t S, ServantArrays sv,
                                                    const uint32_t* __restrict__ row_len,
                                                    uint32_t* __restrict__ codes,
                                                    unsigned long long* __restrict__ codes_wide,
-                                                   uint32_t* __restrict__ slot_owner, uint32_t sentinel) {
+                                                   uint32_t* __restrict__ slot_owner, uint32_t sentinel,
+                                                   uint32_t static_rows) {
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t s = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (s >= S) return;
   const uint32_t len = row_len[s], off = row_off[s];
   const uint32_t M = sv.max_tasks[s], P = sv.nproc[s], L = sv.load[s], fl = sv.flags[s];
-  const uint32_t r0 = sv.run[s];
+  const uint32_t r0 = static_rows ? 0u : sv.run[s];
   for (uint32_t i = lane; i < len + sentinel; i += 32) {
     if (slot_owner) slot_owner[off + i] = s;  // slot-stream solver: slot -> registry position
     if (i == len) {

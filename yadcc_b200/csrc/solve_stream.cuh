@@ -30,11 +30,14 @@ struct StreamArgs {
   TopoView t;
   ClassTable ct;
   ServantArrays sv;
-  const uint32_t* row_len;    // free slots per servant (this solve)
+  const uint32_t* row_len;    // free slots per servant (this solve), or with static_rows: its free_end
+  uint32_t static_rows;
   const uint32_t* list_off;   // [n_classes * n_list_tiles + 1] scanned counts; class c starts at list_off[c * n_list_tiles]
   uint32_t n_list_tiles;
   const uint2* list;          // (servant local index, running_tasks value of the slot)
-  uint32_t max_comp_servants; // dynamic shared memory holds 2 x this many u32
+  uint32_t max_comp_servants; // dynamic shared memory holds 2 x this many u32; a larger component keeps its
+  uint32_t* gscratch;         // running_tasks copy in HBM/L2 instead: gscratch[2 * S], [comp_sv_off .. ) per component
+  uint32_t n_servants;
   const uint32_t* comp_mode;  // [C] 0 = this kernel, 1 = handled by the parallel path, 2 = merge solver ...
   const uint32_t* viol;       // [C] ... unless it handed the component back (solve_merge.cuh)
   Counters* counters;         // pad[0..3]: speculation steps, lanes committed by them, exact walks, walk windows
@@ -146,8 +149,11 @@ __global__ void __launch_bounds__((kStreamProducers + 1) * 32, 1) k_solve_stream
   const uint32_t nall = (kStreamProducers + 1) * 32;
   const uint32_t sv_begin = a.t.comp_sv_off[comp];
   const uint32_t n_sv = a.t.comp_sv_off[comp + 1] - sv_begin;
-  uint32_t* run_s = dyn_smem;
-  uint32_t* lim_s = dyn_smem + a.max_comp_servants;  // first running_tasks value at which the servant is full
+  // running_tasks of the component for the whole solve: shared memory, or (components beyond what it holds --
+  // tens of thousands of servants behind one digest) a per-component slice of an HBM scratch array, L2-resident
+  const bool big = n_sv > a.max_comp_servants;
+  uint32_t* run_s = big ? a.gscratch + sv_begin : dyn_smem;
+  uint32_t* lim_s = big ? a.gscratch + a.n_servants + sv_begin : dyn_smem + a.max_comp_servants;  // first value at which the servant is full
 
   const uint32_t n_cls = a.ct.meta[0];
   for (uint32_t c = tid; c < kMaxClasses; c += nall) {
@@ -163,7 +169,7 @@ __global__ void __launch_bounds__((kStreamProducers + 1) * 32, 1) k_solve_stream
     const uint32_t pos = a.t.comp_sv[sv_begin + i];
     const uint32_t r0 = a.sv.run[pos];
     run_s[i] = r0;
-    lim_s[i] = r0 + a.row_len[pos];
+    lim_s[i] = a.static_rows ? max(r0, a.row_len[pos]) : r0 + a.row_len[pos];
   }
   __syncthreads();
 
@@ -377,7 +383,6 @@ __global__ void __launch_bounds__((kStreamProducers + 1) * 32, 1) k_solve_stream
   }
 
   if (lane == 0 && a.counters) {
-    atomicAdd(&a.counters->pad[0], st_steps); atomicAdd(&a.counters->pad[1], st_lanes);
     atomicAdd(&a.counters->pad[2], st_walks); atomicAdd(&a.counters->pad[3], st_windows);
   }
   // (++running_tasks / ++ever_assigned_tasks, cc:123-124, are applied per grant by k_final_write)

@@ -18,10 +18,14 @@ namespace yd {
 __global__ void __launch_bounds__(1024) k_final_count(const uint32_t* __restrict__ res,
                                                       const DynParams* __restrict__ dp,
                                                       uint32_t* __restrict__ block_counts,
-                                                      const uint32_t* __restrict__ abort_flag) {
+                                                      const uint32_t* __restrict__ abort_flag,
+                                                      const uint32_t* __restrict__ comp_sv = nullptr,
+                                                      uint32_t* __restrict__ claims = nullptr) {
   if (abort_flag && *abort_flag) return;
   uint32_t q = blockIdx.x * 1024 + threadIdx.x;
   const bool granted = (q < dp->n) && (res[q] < kResTimeout);
+  // range-sharded queue: slots this rank's requests claimed, per servant (summed over the ranks afterwards)
+  if (claims && granted) atomicAdd(&claims[comp_sv[res[q]]], 1u);
   // ballot + per-warp counters, the same way k_final_write ranks the grants
   // (bar.red-based __syncthreads_count under-counted under compute-sanitizer)
   __shared__ uint32_t warp_cnt[32];
@@ -34,9 +38,12 @@ __global__ void __launch_bounds__(1024) k_final_count(const uint32_t* __restrict
   }
 }
 
+// `id_prefix` (may be null): grants of the lower ranks of a range-sharded queue, i.e. where this rank's
+// first grant sits in the batch's FIFO numbering.
 __global__ void __launch_bounds__(1024) k_final_scan(uint32_t* __restrict__ block_counts, uint32_t nb,
                                                      Counters* __restrict__ counters,
-                                                     const uint32_t* __restrict__ abort_flag) {
+                                                     const uint32_t* __restrict__ abort_flag,
+                                                     const uint32_t* __restrict__ id_prefix = nullptr) {
   if (abort_flag && *abort_flag) return;
   __shared__ uint32_t warp_sums[32];
   __shared__ uint32_t carry_s;
@@ -65,7 +72,7 @@ __global__ void __launch_bounds__(1024) k_final_scan(uint32_t* __restrict__ bloc
     }
     __syncthreads();
     uint32_t carry = carry_s;
-    if (i < nb) block_counts[i] = carry + (warp ? warp_sums[warp - 1] : 0) + x - v;  // exclusive
+    if (i < nb) block_counts[i] = (id_prefix ? *id_prefix : 0u) + carry + (warp ? warp_sums[warp - 1] : 0) + x - v;  // exclusive
     __syncthreads();
     if (tid == 1023) carry_s = carry + warp_sums[31];
     __syncthreads();
@@ -122,6 +129,108 @@ __global__ void __launch_bounds__(1024) k_final_write(const uint32_t* __restrict
                    (r == kResTimeout) ? YD_STATUS_TIMEOUT : YD_STATUS_ENVIRONMENT_NOT_FOUND);
   }
   *reinterpret_cast<uint4*>(out + q) = g;  // one 16-byte store
+}
+
+// The three kernels above in ONE launch: task ids are the FIFO ordinals of the grants, i.e. an exclusive prefix over
+// the per-block grant counts -- here a single-pass scan with decoupled look-back: a block takes a ticket (so that its
+// predecessors are running or done), publishes its count, sums its predecessors' published counts back to the nearest
+// one that already knows its inclusive prefix, and publishes its own.  `look` = one zeroed 64-bit word per block
+// (bits 63..62: 1 = count, 2 = inclusive prefix; low bits: the value) + the ticket counter behind them.
+__global__ void __launch_bounds__(1024) k_final_fused(const uint32_t* __restrict__ res,
+                                                      const yd_task_req* __restrict__ reqs,
+                                                      const DynParams* __restrict__ dp,
+                                                      unsigned long long* __restrict__ look, uint32_t nb,
+                                                      const uint32_t* __restrict__ comp_sv, TaskRing ring,
+                                                      yd_grant* __restrict__ out, Counters* __restrict__ counters,
+                                                      const uint32_t* __restrict__ abort_flag,
+                                                      uint32_t* __restrict__ run, unsigned long long* __restrict__ ever) {
+  if (abort_flag && *abort_flag) return;
+  __shared__ uint32_t warp_cnt[32];
+  __shared__ uint32_t s_vb;
+  __shared__ unsigned long long s_excl;
+  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) s_vb = (uint32_t)atomicAdd(&look[nb], 1ull);
+  __syncthreads();
+  const uint32_t vb = s_vb;
+  const uint32_t n = dp->n;
+  const long long now_ns = dp->now_ns;
+  ring.next = dp->ring_next;
+  const uint32_t q = vb * 1024 + tid;
+  uint32_t r = q < n ? res[q] : kResEnvNotFound;
+  const bool granted = r < kResTimeout;
+  if (granted) r = comp_sv[r];  // solver results index the component-ordered servant list
+  const uint32_t bal = __ballot_sync(0xffffffffu, granted);
+  if (lane == 0) warp_cnt[warp] = __popc(bal);
+  __syncthreads();
+  if (warp == 0) {
+    const uint32_t mine = __reduce_add_sync(0xffffffffu, warp_cnt[lane]);
+    volatile unsigned long long* vl = look;
+    if (lane == 0) { __threadfence(); vl[vb] = (1ull << 62) | mine; }
+    unsigned long long excl = 0;
+    int at = (int)vb - 1;
+    while (at >= 0) {
+      const int idx = at - (int)lane;
+      unsigned long long v;
+      do {
+        v = idx >= 0 ? vl[idx] : (2ull << 62);  // before the first block: an inclusive prefix of zero
+      } while (__any_sync(0xffffffffu, (v >> 62) == 0));
+      const uint32_t incl = __ballot_sync(0xffffffffu, (v >> 62) == 2);
+      const unsigned long long val = v & ((1ull << 62) - 1);
+      if (incl) {
+        const uint32_t first = __ffs(incl) - 1;  // the nearest predecessor that knows its inclusive prefix
+        unsigned long long part = lane <= first ? val : 0ull;
+#pragma unroll
+        for (int d = 16; d; d >>= 1) part += __shfl_xor_sync(0xffffffffu, part, d);
+        excl += part;
+        break;
+      }
+      unsigned long long part = val;
+#pragma unroll
+      for (int d = 16; d; d >>= 1) part += __shfl_xor_sync(0xffffffffu, part, d);
+      excl += part;
+      at -= 32;
+    }
+    if (lane == 0) {
+      __threadfence();
+      vl[vb] = (2ull << 62) | (excl + mine);
+      s_excl = excl;
+      if (vb == nb - 1) {  // the last block knows the batch's total
+        counters->granted = excl + mine;
+        counters->alive += excl + mine;
+      }
+    }
+  }
+  __syncthreads();
+  if (q >= n) return;
+  uint32_t before = 0;
+  for (uint32_t w = 0; w < warp; ++w) before += warp_cnt[w];
+  before += __popc(bal & ((1u << lane) - 1));
+  uint4 g;  // {task_id lo, task_id hi, servant_index, status} == yd_grant
+  if (granted) {
+    const uint64_t id = ring.next + s_excl + before;
+    const unsigned long long xid = ring.ext(id);
+    g = make_uint4((uint32_t)xid, (uint32_t)(xid >> 32), r, YD_STATUS_GRANTED);
+    const uint64_t slot = id & ring.mask;
+    const yd_task_req rq = reqs[q];
+    ring.exp[slot] = now_ns + rq.expires_in_ns;
+    ring.srv[slot] = r;
+    ring.flags[slot] = kTaskAlive | ((rq.flags & YD_REQ_FLAG_PREFETCH) ? kTaskPrefetch : 0u);
+    atomicAdd(&run[r], 1u);  // ++running_tasks, ++ever_assigned_tasks (cc:123-124)
+    atomicAdd(&ever[r], 1ull);
+  } else {
+    g = make_uint4(0u, 0u, YD_NO_SERVANT, (r == kResTimeout) ? YD_STATUS_TIMEOUT : YD_STATUS_ENVIRONMENT_NOT_FOUND);
+  }
+  *reinterpret_cast<uint4*>(out + q) = g;  // one 16-byte store
+}
+
+// run[] += claims, ever[] += claims: the all-reduced per-servant slot claims of a range-sharded solve.
+__global__ void k_apply_claims(uint32_t S, const uint32_t* __restrict__ claims, uint32_t* __restrict__ run,
+                               unsigned long long* __restrict__ ever, const uint32_t* __restrict__ abort_flag) {
+  if (abort_flag && *abort_flag) return;
+  const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= S || claims[s] == 0) return;
+  run[s] += claims[s];
+  ever[s] += claims[s];
 }
 
 // ---- FreeTask (cc:167-188), one thread per id --------------------------------

@@ -130,8 +130,11 @@ struct RunningRec {
 
 }  // namespace
 
+struct yd_shard_ctx;  // range-sharded queue over several GPUs (shard_host.inc)
+
 struct yd_sched {
   int device = 0;
+  yd_shard_ctx* shard = nullptr;
   cudaStream_t st = nullptr;
   uint64_t min_mem = 0;
   uint32_t solver_pref = 0;
@@ -144,6 +147,13 @@ struct yd_sched {
   std::vector<ServantHost> sv;
   std::unordered_map<std::string, uint32_t> loc2pos;
   bool topo_dirty = true, facts_dirty = true;
+  // The sorted slot order depends on the heartbeat facts only (key(s, r) is static, slots.cuh): it is built when
+  // a capacity fact, a priority or the servant set changes and kept across solves; a solve only filters out the
+  // slots servants have filled meanwhile.  (Above kStaticSlotLimit slots the table is rebuilt per solve, clamped
+  // to the batch size.)
+  bool order_dirty = true, order_static = false;
+  size_t order_slot_b = 0;
+  unsigned long long order_rebuilds = 0;
 
   // device servant arrays; state (run/ever) is valid for positions < S_dev
   DevBuf d_nproc, d_load, d_maxt, d_flags, d_ver, d_run, d_ever;
@@ -171,9 +181,9 @@ struct yd_sched {
   uint32_t cls_bound = 16;  // classes the per-class grids are sized for; grows on demand (<= yd::kMaxClasses)
   DevBuf d_list, d_list_bal, d_rcls, d_rrank, d_rank_cnt, d_rq, d_rself;
   // merge solver (solve_merge.cuh): per-slot verdicts and the chunk boundary states
-  DevBuf d_slot_pick, d_mst_in, d_mst_out;
-  size_t z_merge_off = 0;
-  uint32_t merge_chunk = 1024, merge_rounds = 8, merge_max_chunks = 0;
+  DevBuf d_slot_pick, d_mst_in, d_mst_out, d_stream_scratch;
+  size_t z_merge_off = 0, z_layout_off = 0, z_final_off = 0;
+  uint32_t merge_chunk = 1024, merge_rounds = 8, merge_max_chunks = 0, merge_grid = 0, merge_grid_kcap = 0;
   uint32_t stream_debug = 0;   // YDSCHED_STREAM_DEBUG, read once at yd_create
   uint32_t force_stream = 0;   // yd_config.reserved bit 1 / YDSCHED_FORCE_STREAM: no merge solver for self-requests
   bool dump_env = false, debug_env = false;
@@ -201,13 +211,14 @@ struct yd_sched {
 
   // captured solve graphs, keyed by size class
   struct GraphKey {
-    uint32_t Nb = 0, S = 0, n_comps = 0, max_comp = 0, cls_bound = 0, solver = 0, wide = 0, merge_rounds = 0, force_stream = 0;
+    uint32_t Nb = 0, S = 0, n_comps = 0, max_comp = 0, cls_bound = 0, solver = 0, wide = 0, merge_rounds = 0, force_stream = 0,
+             order_static = 0;
     size_t slot_b = 0;
     unsigned long long gen = 0, topo_gen = 0;  // buffer reallocations; topology rebuilds (n_envs, n_ips, ... are baked in)
     uint64_t ring_cap = 0;
     bool operator==(const GraphKey& o) const {
       return Nb == o.Nb && S == o.S && n_comps == o.n_comps && max_comp == o.max_comp && cls_bound == o.cls_bound &&
-             merge_rounds == o.merge_rounds && force_stream == o.force_stream &&
+             merge_rounds == o.merge_rounds && force_stream == o.force_stream && order_static == o.order_static &&
              solver == o.solver && wide == o.wide && slot_b == o.slot_b && gen == o.gen && topo_gen == o.topo_gen &&
              ring_cap == o.ring_cap;
     }
@@ -305,6 +316,7 @@ void yd_sched::SyncFacts() {
       h[4 * S + i] = (uint32_t)s.version;
       maxcap = std::max(maxcap, std::min(s.nproc, s.max_tasks));
     }
+    if (wide != (maxcap > yd::kNarrowCapLimit)) order_dirty = true;
     wide = maxcap > yd::kNarrowCapLimit;
     d_nproc.ensure(size_t(S) * 4); d_load.ensure(size_t(S) * 4); d_maxt.ensure(size_t(S) * 4);
     d_flags.ensure(size_t(S) * 4); d_ver.ensure(size_t(S) * 4);
@@ -529,8 +541,11 @@ yd_sched* yd_create(const yd_config* cfg) {
   return s;
 }
 
+extern "C" void yd_shard_finalize(yd_sched* s);
+
 void yd_destroy(yd_sched* s) {
   if (!s) return;
+  yd_shard_finalize(s);
   cudaSetDevice(s->device);
   cudaStreamSynchronize(s->st);
   for (DevBuf* b : {&s->d_nproc, &s->d_load, &s->d_maxt, &s->d_flags, &s->d_ver, &s->d_run, &s->d_ever,
@@ -541,7 +556,7 @@ void yd_destroy(yd_sched* s) {
                     &s->d_codes, &s->d_ids, &s->d_ok, &s->d_counters, &s->d_sv_env_off, &s->d_sv_envs,
                     &s->d_comp_mode, &s->d_slot_owner, &s->d_sort_k[0], &s->d_sort_k[1], &s->d_sort_v[0],
                     &s->d_sort_v[1], &s->d_zero, &s->d_list, &s->d_list_bal, &s->d_rcls, &s->d_rrank, &s->d_rank_cnt, &s->d_rq, &s->d_rself,
-                    &s->d_slot_pick, &s->d_mst_in, &s->d_mst_out, &s->d_bloom,
+                    &s->d_slot_pick, &s->d_mst_in, &s->d_mst_out, &s->d_stream_scratch, &s->d_bloom,
                     &s->d_bloom_keys, &s->d_bloom_out, &s->d_rt_bytes, &s->d_rt_off, &s->d_rt_len, &s->d_rt_ids,
                     &s->d_rt_slots, &s->d_rt_keys, &s->d_rt_out}) {
     b->release();
@@ -575,9 +590,17 @@ void yd_keep_servant_alive(yd_sched* s, int64_t now_ns, const yd_servant* v, int
     rec->observed = loc;
     rec->discovered_at = now_ns;
     s->topo_dirty = true;
+    s->order_dirty = true;
   } else {
     rec = &s->sv[it->second];
     if (rec->envs != envs) s->topo_dirty = true;
+    uint32_t nf = 0;  // FactFlags of the new personality
+    if (v->priority == YD_PRIORITY_DEDICATED) nf |= yd::kFlagDedicated;
+    if (v->total_memory_in_bytes != 0 && v->memory_available_in_bytes < s->min_mem) nf |= yd::kFlagLowMem;
+    if (rec->nproc != v->num_processors || rec->load != v->current_load || rec->max_tasks != v->max_tasks ||
+        nf != s->FactFlags(*rec)) {
+      s->order_dirty = true;  // a slot key or a free_end changed: the sorted slot order is rebuilt before the next solve
+    }
   }
   rec->version = v->version;
   rec->reported = v->reported_location ? v->reported_location : "";
@@ -643,31 +666,48 @@ yd::ClassTable MakeClassTable(yd_sched* s) {
 yd::MergePlan MakeMergePlan(yd_sched* s) {
   uint32_t* u = reinterpret_cast<uint32_t*>(static_cast<char*>(s->d_zero.p) + s->z_merge_off);
   yd::MergePlan mp{};
-  mp.chunk_base = u;                     u += yd::kMaxClasses + 1;
+  mp.bar = u;                            u += yd::kMaxClasses + 1;  // (only the first cell is used)
   mp.changed = u;                        u += 16;
   mp.viol = u;                           u += s->n_comps;
   mp.tau = u;                            // [S]
   return mp;
 }
 
+yd::RqLayout MakeRqLayout(yd_sched* s, uint32_t q_base, uint32_t n_local, bool sharded) {
+  uint32_t* u = reinterpret_cast<uint32_t*>(static_cast<char*>(s->d_zero.p) + s->z_layout_off);
+  yd::RqLayout L{};
+  L.goff = u;                            u += yd::kMaxClasses;
+  L.gn = u;                              u += yd::kMaxClasses;
+  L.win = u;                             u += yd::kMaxClasses;
+  L.base = u;                            u += yd::kMaxClasses;
+  L.total = u;
+  L.q_base = q_base;
+  L.n_local = n_local;
+  L.sharded = sharded ? 1u : 0u;
+  L.rank_off = s->d_rank_cnt.as<uint32_t>();
+  L.nrt = (uint32_t)((s->res_words + yd::kRankTile - 1) / yd::kRankTile);
+  return L;
+}
+
 // Slot table (both solvers).  For the slot-stream solver it also records slot owners.
 // Returns the number of kernels launched.
-uint32_t LaunchSlotTable(yd_sched* s, bool for_stream) {
+uint32_t LaunchSlotTable(yd_sched* s, bool for_stream, bool static_rows = false) {
   const uint32_t S = (uint32_t)s->sv.size();
   cudaStream_t st = s->st;
   yd::ServantArrays arr = s->arrays();
   const uint32_t sentinel = for_stream ? 0u : 1u;
+  const uint32_t sr = static_rows ? 1u : 0u;
   yd::k_slot_rows<<<1, 1024, 0, st>>>(S, s->d_dyn.as<yd::DynParams>(), arr, s->d_row_off.as<uint32_t>(),
-                                      s->d_row_len.as<uint32_t>(), s->d_counters.as<Counters>(), sentinel);
+                                      s->d_row_len.as<uint32_t>(), s->d_counters.as<Counters>(), sentinel, sr);
   uint32_t* owner = for_stream ? s->d_slot_owner.as<uint32_t>() : nullptr;
   if (s->wide) {
     yd::k_slot_fill<true><<<(S + 7) / 8, 256, 0, st>>>(S, arr, s->d_row_off.as<uint32_t>(),
                                                        s->d_row_len.as<uint32_t>(), nullptr,
-                                                       s->d_codes.as<unsigned long long>(), owner, sentinel);
+                                                       s->d_codes.as<unsigned long long>(), owner, sentinel, sr);
   } else {
     yd::k_slot_fill<false><<<(S + 7) / 8, 256, 0, st>>>(S, arr, s->d_row_off.as<uint32_t>(),
                                                         s->d_row_len.as<uint32_t>(), s->d_codes.as<uint32_t>(),
-                                                        nullptr, owner, sentinel);
+                                                        nullptr, owner, sentinel, sr);
   }
   return 2;
 }
@@ -719,7 +759,7 @@ uint32_t LaunchSort(yd_sched* s, int first_bit, int last_bit) {
   const int passes = (last_bit - first_bit) / yd::kRsBits + 1;
   const KeyT* kin = s->d_codes.as<KeyT>();
   const uint32_t* vin = nullptr;
-  int cur = 0;
+  int cur = (passes - 1) & 1;  // ping-pong so that the LAST pass writes buffer 0 (captured graphs keep its address)
   // digit histograms of all passes in one read, then one kernel per pass
   yd::k_rs_ghist<KeyT><<<nb, yd::kRsThreads, 0, st>>>(kin, n_ptr, first_bit, passes, nb, zbase);
   uint32_t launches = 1;
@@ -732,10 +772,6 @@ uint32_t LaunchSort(yd_sched* s, int first_bit, int last_bit) {
     kin = kout;
     vin = vout;
     cur ^= 1;
-  }
-  if (cur == 0) {  // an even number of passes leaves the result in [1]: normalise to [0]
-    std::swap(s->d_sort_k[0], s->d_sort_k[1]);
-    std::swap(s->d_sort_v[0], s->d_sort_v[1]);
   }
   return launches;
 }
@@ -754,6 +790,11 @@ void PrepareStreamBuffers(yd_sched* s, uint32_t Nb, size_t slot_b) {
   off += (yd::kClsTableSize + 8 + 7 * yd::kMaxClasses + 3 * size_t(s->n_comps) + 32 * size_t(s->cls_bound) + 8) * 4;
   s->z_merge_off = off;
   off += (yd::kMaxClasses + 1 + 16 + size_t(s->n_comps) + s->sv.size() + 8) * 4;
+  s->z_layout_off = off;
+  off += (4 * yd::kMaxClasses + 8) * 4;
+  off = (off + 7) & ~size_t(7);
+  s->z_final_off = off;
+  off += (size_t(Nb + 1023) / 1024 + 2) * 8;
   const uint32_t n_tiles = (uint32_t)((slot_b + yd::kListTile - 1) / yd::kListTile);
   s->z_listcnt_off = off;
   off += (size_t(s->cls_bound) * n_tiles + 1) * 4;
@@ -764,6 +805,7 @@ void PrepareStreamBuffers(yd_sched* s, uint32_t Nb, size_t slot_b) {
   const uint32_t n_rtiles = (Nb + yd::kRankTile - 1) / yd::kRankTile;
   s->d_rcls.ensure(size_t(Nb) * 4); s->d_rrank.ensure(size_t(Nb) * 4); s->d_rq.ensure(size_t(Nb) * 8);
   s->d_rself.ensure(size_t(Nb) * 4);
+  s->d_stream_scratch.ensure(std::max<size_t>(s->sv.size(), 1) * 8);
   s->d_slot_pick.ensure(slot_b * 4 * 4);  // one word per list entry
   // every slot is in at most one pseudo-class list: chunks <= slots / chunk + one partial chunk per list
   s->merge_max_chunks = (uint32_t)(slot_b / s->merge_chunk) + s->cls_bound + 1;
@@ -774,6 +816,54 @@ void PrepareStreamBuffers(yd_sched* s, uint32_t Nb, size_t slot_b) {
     YD_CUDA_CHECK(cudaFuncSetAttribute(yd::k_solve_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, 190 * 1024));
     s->stream_attr_set = true;
   }
+}
+
+// The merge solver: ONE persistent launch (rounds, scatter and check are phases behind grid barriers), so the
+// grid must be co-resident: occupancy x SMs blocks at most, each looping over its chunks.
+uint32_t LaunchMerge(yd_sched* s, yd::MergeArgs& m, cudaStream_t st) {
+  m.kcap = std::min(32u, s->cls_bound);
+  const size_t dyn = size_t(1 + m.kcap) * yd::kRingRecs * sizeof(uint2);
+  if (s->merge_grid_kcap != m.kcap) {
+    int per_sm = 0, sms = 0;
+    YD_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, yd::k_merge_solve, 32, dyn));
+    YD_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device));
+    s->merge_grid = (uint32_t)std::max(1, std::min(per_sm, 16) * sms);
+    s->merge_grid_kcap = m.kcap;
+  }
+  m.chunk = s->merge_chunk;
+  m.max_chunks = s->merge_max_chunks;
+  m.diag = &s->d_counters.as<Counters>()->pad[0];
+  m.rq_blocks = (uint32_t)(s->d_rq.cap / 256);
+  m.ls_blocks = (uint32_t)(s->d_list.cap / 256);
+  const uint32_t grid = std::min(s->merge_grid, s->merge_max_chunks);
+  yd::k_merge_solve<<<grid, 32, dyn, st>>>(m);
+  return 1;
+}
+
+constexpr size_t kStaticSlotLimit = size_t(1) << 26;
+
+// Slots of every servant for running_tasks = 0 .. free_end - 1 (+1 spare per servant), whatever the batch.
+size_t StaticSlotBound(yd_sched* s) {
+  size_t b = 0;
+  for (auto&& v : s->sv) b += size_t(std::min(v.nproc, v.max_tasks)) + 1;
+  return b;
+}
+
+// (Re)builds the kept slot order: slot table over ALL running_tasks values + its sort, outside any graph.
+// Buffers must exist (PrepareStreamBuffers).  Returns the number of kernels launched.
+uint32_t RebuildSlotOrder(yd_sched* s, size_t slot_b) {
+  cudaStream_t st = s->st;
+  // the sort's digit histograms live in the zeroed scratch region
+  YD_CUDA_CHECK(cudaMemsetAsync(static_cast<char*>(s->d_zero.p) + s->z_hist_off[0], 0, s->z_cls_off - s->z_hist_off[0], st));
+  uint32_t l = LaunchSlotTable(s, true, true);
+  if (s->wide) l += LaunchSort<unsigned long long>(s, 0, 62);
+  else l += LaunchSort<uint32_t>(s, 3, 30);
+  YD_CUDA_CHECK(cudaGetLastError());
+  s->order_dirty = false;
+  s->order_static = true;
+  s->order_slot_b = slot_b;
+  s->order_rebuilds += 1;
+  return l;
 }
 
 // Solver 2: sorted slot streams.  Two concurrent branches:
@@ -806,17 +896,19 @@ uint32_t LaunchStream(yd_sched* s, uint32_t N, size_t slot_b, bool capturing) {
   yd::k_scan_u32<<<1, 1024, 0, st2>>>(s->d_rank_cnt.as<uint32_t>(), 0, ct.meta, n_rtiles, nullptr, ct.cls_bound);
   YD_CUDA_CHECK(cudaEventRecord(s->ev_join, st2));
   launches += 4;
-  // branch A: slot table and its sort
-  launches += LaunchSlotTable(s, true);
-  if (s->wide) launches += LaunchSort<unsigned long long>(s, 0, 62);
-  else launches += LaunchSort<uint32_t>(s, 3, 30);
+  // branch A: slot table and its sort -- unless the kept (static) order is valid
+  if (!s->order_static) {
+    launches += LaunchSlotTable(s, true);
+    if (s->wide) launches += LaunchSort<unsigned long long>(s, 0, 62);
+    else launches += LaunchSort<uint32_t>(s, 3, 30);
+  }
   // ---- join -----------------------------------------------------------------------
   YD_CUDA_CHECK(cudaStreamWaitEvent(st, s->ev_join, 0));
 
   // ---- per-class sorted slot lists ----------------------------------------------------
   const unsigned long long* m_ptr = &s->d_counters.as<Counters>()->slots;
   yd::SlotDecode dec{s->d_sort_v[0].as<uint32_t>(), s->d_slot_owner.as<uint32_t>(), s->d_row_off.as<uint32_t>(),
-                     s->d_row_len.as<uint32_t>(), s->d_run.as<uint32_t>()};
+                     s->d_row_len.as<uint32_t>(), s->d_run.as<uint32_t>(), s->order_static ? 1u : 0u};
   yd::k_list_count<<<n_tiles, yd::kListTile, 0, st>>>(m_ptr, dec, t, ct, arr, n_tiles, list_cnt,
                                                       s->d_list_bal.as<uint32_t>());
   yd::k_scan_u32<<<1, 1024, 0, st>>>(list_cnt, 0, ct.meta + 3, n_tiles, nullptr, ct.cls_bound);
@@ -825,11 +917,13 @@ uint32_t LaunchStream(yd_sched* s, uint32_t N, size_t slot_b, bool capturing) {
   launches += 3;
 
   // ---- data-parallel path: single-class components without self-requests ----------------
+  // (n_local = the grid bound: res[] has that many cells and only requests < dp->n are ever named)
+  const yd::RqLayout L = MakeRqLayout(s, 0, N, false);
   yd::k_rank_assign<<<(N + 255) / 256, 256, 0, st>>>(dp, n_rtiles, t, ct, s->d_rcls.as<uint32_t>(),
                                                      s->d_rrank.as<uint32_t>(), s->d_rself.as<uint32_t>(),
                                                      s->d_rank_cnt.as<uint32_t>(), list_cnt,
                                                      n_tiles, s->d_list.as<uint2>(), arr, s->d_comp_mode.as<uint32_t>(),
-                                                     s->d_rq.as<uint2>(), s->d_res.as<uint32_t>());
+                                                     s->d_rq.as<uint2>(), s->d_res.as<uint32_t>(), L);
   launches += 1;
 
   // ---- merge solver: everything but components with several servants behind one requestor IP -------
@@ -843,17 +937,9 @@ uint32_t LaunchStream(yd_sched* s, uint32_t N, size_t slot_b, bool capturing) {
     m.rq = s->d_rq.as<uint2>(); m.rcls = s->d_rcls.as<uint32_t>(); m.rself = s->d_rself.as<uint32_t>();
     m.slot_pick = s->d_slot_pick.as<uint32_t>();
     m.st_in = s->d_mst_in.as<uint32_t>(); m.st_out = s->d_mst_out.as<uint32_t>();
-    m.chunk = s->merge_chunk; m.max_chunks = s->merge_max_chunks;
     m.res = s->d_res.as<uint32_t>();
-    yd::k_merge_plan<<<1, 256, 0, st>>>(m);
-    for (uint32_t r = 0; r < s->merge_rounds; ++r) {
-      m.round = r;
-      yd::k_merge_round<<<s->merge_max_chunks, 32, 0, st>>>(m);
-    }
-    m.round = s->merge_rounds;
-    yd::k_merge_scatter<<<s->merge_max_chunks, 256, 0, st>>>(m);
-    yd::k_merge_check<<<(N + 255) / 256, 256, 0, st>>>(m);
-    launches += 3 + s->merge_rounds;
+    m.L = L;
+    launches += LaunchMerge(s, m, st);
   }
 
   // ---- sequential decisions for everything else ---------------------------------------------
@@ -865,15 +951,18 @@ uint32_t LaunchStream(yd_sched* s, uint32_t N, size_t slot_b, bool capturing) {
   a.ct = ct;
   a.sv = arr;
   a.row_len = s->d_row_len.as<uint32_t>();
+  a.static_rows = s->order_static ? 1u : 0u;
   a.list_off = list_cnt;
   a.n_list_tiles = n_tiles;
   a.list = s->d_list.as<uint2>();
-  a.max_comp_servants = s->max_comp_servants;
+  a.max_comp_servants = (uint32_t)std::min<size_t>(s->max_comp_servants, kStreamMaxComponent);
+  a.gscratch = s->d_stream_scratch.as<uint32_t>();
+  a.n_servants = (uint32_t)s->sv.size();
   a.comp_mode = s->d_comp_mode.as<uint32_t>();
   a.viol = mp.viol;
   a.counters = s->d_counters.as<Counters>();
   a.debug = s->stream_debug;
-  const size_t dyn = size_t(s->max_comp_servants) * 8;
+  const size_t dyn = size_t(a.max_comp_servants) * 8;
   yd::k_solve_stream<<<s->n_comps, (yd::kStreamProducers + 1) * 32, dyn, st>>>(a);
   launches += 1;
   return launches;
@@ -918,15 +1007,25 @@ uint32_t EnqueueSolve(yd_sched* s, uint32_t Nb, size_t slot_b, uint32_t solver, 
     if (have_work) launches += LaunchRowscan(s);
   }
   if (record_events) YD_CUDA_CHECK(cudaEventRecord(s->ev[3], st));
-  yd::k_final_count<<<nb, 1024, 0, st>>>(s->d_res.as<uint32_t>(), dp, s->d_blk.as<uint32_t>(), abort_flag);
-  yd::k_final_scan<<<1, 1024, 0, st>>>(s->d_blk.as<uint32_t>(), nb, s->d_counters.as<Counters>(), abort_flag);
-  yd::k_final_write<<<nb, 1024, 0, st>>>(s->d_res.as<uint32_t>(), s->d_reqs.as<yd_task_req>(), dp,
-                                         s->d_blk.as<uint32_t>(), s->d_comp_sv.as<uint32_t>(), s->ring(),
-                                         s->d_out.as<yd_grant>(), abort_flag,
-                                         // the row-scan solver writes running_tasks back itself
-                                         solver == 2 ? s->d_run.as<uint32_t>() : nullptr,
-                                         s->d_ever.as<unsigned long long>());
-  launches += 3;
+  if (solver == 2 && have_work) {
+    // grants, task ids (single-pass scan with look-back), leases, ++running_tasks: one launch
+    unsigned long long* look = reinterpret_cast<unsigned long long*>(static_cast<char*>(s->d_zero.p) + s->z_final_off);
+    yd::k_final_fused<<<nb, 1024, 0, st>>>(s->d_res.as<uint32_t>(), s->d_reqs.as<yd_task_req>(), dp, look, nb,
+                                           s->d_comp_sv.as<uint32_t>(), s->ring(), s->d_out.as<yd_grant>(),
+                                           s->d_counters.as<Counters>(), abort_flag, s->d_run.as<uint32_t>(),
+                                           s->d_ever.as<unsigned long long>());
+    launches += 1;
+  } else {
+    yd::k_final_count<<<nb, 1024, 0, st>>>(s->d_res.as<uint32_t>(), dp, s->d_blk.as<uint32_t>(), abort_flag);
+    yd::k_final_scan<<<1, 1024, 0, st>>>(s->d_blk.as<uint32_t>(), nb, s->d_counters.as<Counters>(), abort_flag);
+    yd::k_final_write<<<nb, 1024, 0, st>>>(s->d_res.as<uint32_t>(), s->d_reqs.as<yd_task_req>(), dp,
+                                           s->d_blk.as<uint32_t>(), s->d_comp_sv.as<uint32_t>(), s->ring(),
+                                           s->d_out.as<yd_grant>(), abort_flag,
+                                           // the row-scan solver writes running_tasks back itself
+                                           solver == 2 ? s->d_run.as<uint32_t>() : nullptr,
+                                           s->d_ever.as<unsigned long long>());
+    launches += 3;
+  }
   YD_CUDA_CHECK(cudaGetLastError());
   if (record_events) YD_CUDA_CHECK(cudaEventRecord(s->ev[4], st));
   YD_CUDA_CHECK(cudaMemcpyAsync(s->h_counters.p, s->d_counters.p, sizeof(Counters), cudaMemcpyDeviceToHost, st));
@@ -1041,10 +1140,18 @@ void yd_wait_for_starting_new_tasks(yd_sched* s, int64_t now_ns, const yd_task_r
   // Size classes: grids, scratch arrays and memsets are dimensioned for the next power of
   // two; kernels read the exact n from DynParams.
   const uint32_t Nb = (uint32_t)NextPow2(N, 1024);
-  size_t slot_bound = 0;
-  for (auto&& v : s->sv) slot_bound += size_t(std::min(std::min(v.nproc, v.max_tasks), N)) + 1;
+  // The slot table: kept across solves (all running_tasks values of every servant) while it is small enough,
+  // else rebuilt per solve and clamped to the batch size.
+  const size_t static_bound = StaticSlotBound(s);
+  const bool want_static = s->solver_pref != 1 && static_bound <= kStaticSlotLimit;
+  size_t slot_bound = static_bound;
+  if (!want_static) {
+    slot_bound = 0;
+    for (auto&& v : s->sv) slot_bound += size_t(std::min(std::min(v.nproc, v.max_tasks), N)) + 1;
+  }
   if (slot_bound > 0x7ffffff0ull) { fprintf(stderr, "ydsched: slot table too large\n"); abort(); }
   const size_t slot_b = (size_t)NextPow2(std::max<size_t>(slot_bound, 1), 4096);
+  if (!want_static) s->order_static = false;
   const uint32_t nb = (Nb + 1023) / 1024;
   s->d_reqs.ensure(size_t(Nb) * sizeof(yd_task_req));
   s->res_words = Nb;
@@ -1057,16 +1164,14 @@ void yd_wait_for_starting_new_tasks(yd_sched* s, int64_t now_ns, const yd_task_r
   s->d_slot_owner.ensure(slot_b * 4);
 
   // solver choice: 2 (slot streams) unless asked otherwise or a component is too big for it
+  // (the slot-stream solver takes components of any size: its sequential fallback keeps running_tasks of a
+  // component beyond kStreamMaxComponent servants in HBM instead of shared memory)
   uint32_t solver = s->solver_pref == 1 ? 1 : 2;
-  if (solver == 2 && s->max_comp_servants > kStreamMaxComponent) solver = 1;
-  if (solver == 1 && s->max_comp_servants > kRowscanMaxComponent) {
-    fprintf(stderr, "ydsched: a digest component has %u servants: too large for both solvers (%zu / %zu)\n",
-            s->max_comp_servants, kRowscanMaxComponent, kStreamMaxComponent);
-    abort();
-  }
+  if (solver == 1 && s->max_comp_servants > kRowscanMaxComponent) solver = 2;  // the row-scan solver holds 8192 servants per component
 
   yd::DynParams* hd = s->h_dyn.as<yd::DynParams>();
   hd->n = N;
+  hd->slot_clamp = N;
   hd->now_ns = now_ns;
   hd->ring_lo = s->lo;
   hd->ring_next = s->next_id;
@@ -1091,11 +1196,15 @@ void yd_wait_for_starting_new_tasks(yd_sched* s, int64_t now_ns, const yd_task_r
       // make sure every buffer the sequence touches exists BEFORE capturing (no allocation
       // inside a capture), then look the size class up
       if (solver == 2) PrepareStreamBuffers(s, Nb, slot_b);
+      if (solver == 2 && want_static && S && s->n_comps && (s->order_dirty || !s->order_static || s->order_slot_b != slot_b)) {
+        launches += RebuildSlotOrder(s, slot_b);
+      }
       yd_sched::GraphKey key;
       key.Nb = Nb; key.S = S; key.n_comps = s->n_comps; key.max_comp = s->max_comp_servants;
       key.cls_bound = s->cls_bound; key.solver = solver; key.wide = s->wide; key.slot_b = slot_b;
       key.gen = g_buf_generation; key.topo_gen = s->topo_gen; key.ring_cap = s->ring_cap;
       key.merge_rounds = s->merge_rounds; key.force_stream = s->force_stream;
+      key.order_static = (solver == 2 && s->order_static) ? 1u : 0u;
       yd_sched::GraphEntry* hit = nullptr;
       for (auto& g : s->graphs) if (g.key == key) { hit = &g; break; }
       if (!hit) {
@@ -1120,8 +1229,12 @@ void yd_wait_for_starting_new_tasks(yd_sched* s, int64_t now_ns, const yd_task_r
       graphed = true;
     } else {
       if (solver == 2) PrepareStreamBuffers(s, Nb, slot_b);
+      if (solver == 2 && want_static && S && s->n_comps && (s->order_dirty || !s->order_static || s->order_slot_b != slot_b)) {
+        launches += RebuildSlotOrder(s, slot_b);
+      }
       launches += EnqueueSolve(s, Nb, slot_b, solver, true, false);
     }
+    if (solver == 1) { s->order_dirty = true; s->order_static = false; }  // the row-scan solver's table overwrote the kept one
     YD_CUDA_CHECK(cudaMemcpyAsync(out, s->d_out.p, size_t(N) * sizeof(yd_grant), cudaMemcpyDeviceToHost, st));
     YD_CUDA_CHECK(cudaEventRecord(s->ev[5], st));
     YD_CUDA_CHECK(cudaStreamSynchronize(st));
@@ -1176,7 +1289,7 @@ void yd_wait_for_starting_new_tasks(yd_sched* s, int64_t now_ns, const yd_task_r
   stt.d2h_bytes = size_t(N) * sizeof(yd_grant) + sizeof(Counters) + 8;
   s->have_stats = true;
   if (s->debug_env) {
-    fprintf(stderr, "ydsched: solver %u graph %d spec_steps %llu spec_lanes %llu walks %llu windows %llu solve_ms %.3f\n",
+    fprintf(stderr, "ydsched: solver %u graph %d merge_rounds %llu merge_chunks %llu walks %llu windows %llu solve_ms %.3f\n",
             solver, (int)graphed, c->pad[0], c->pad[1], c->pad[2], c->pad[3], stt.solve_ms);
   }
 }
@@ -1240,7 +1353,7 @@ void yd_on_expiration_timer(yd_sched* s, int64_t now_ns) {
     s->sv.swap(alive);
     s->loc2pos.clear();
     for (uint32_t i = 0; i != s->sv.size(); ++i) s->loc2pos.emplace(s->sv[i].observed, i);
-    s->topo_dirty = s->facts_dirty = true;
+    s->topo_dirty = s->facts_dirty = s->order_dirty = true;
     s->d_remap.ensure(size_t(S_old) * 4);
     YD_CUDA_CHECK(cudaMemcpyAsync(s->d_remap.p, remap.data(), size_t(S_old) * 4, cudaMemcpyHostToDevice, st));
   }
@@ -1668,3 +1781,5 @@ int yd_running_index_entry(yd_sched* s, uint32_t i, yd_running_task* out) {
 
 }  // extern "C"
 
+// ---- range-sharded queue over the GPUs of a node (include/ydshard.h) ------------------------------------
+#include "shard_host.inc"

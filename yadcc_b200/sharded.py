@@ -163,3 +163,79 @@ class ShardedDispatcher:
         for chunk, pos, where in self._lookup(global_ids):
             out[where] = self.local.keep_tasks_alive(chunk[1][pos], new_expires_in, now=now)
         return out
+
+
+class RangeShardedDispatcher:
+    """ONE scheduler whose pending queue is range-sharded over the GPUs of a node (include/ydshard.h;
+    SURVEY.md 8(e) option 2, BASELINE.json north_star): rank g keeps the g-th contiguous FIFO range in
+    its HBM, the servant table is replicated (every rank is fed the same heartbeats and ticks through
+    the ordinary TaskDispatcher calls of `local`), and a solve makes exactly the decisions one
+    TaskDispatcher would make on the concatenated queue.  The exchanges (class tables, per-class
+    counts, reachable request records, per-servant claimed-slot counts) are NCCL collectives issued
+    by the C++ library on its own stream; torch.distributed only carries the 128-byte ncclUniqueId
+    here.  CUDA library only."""
+
+    def __init__(self, local: TaskDispatcher, rank: int, world: int, *, device=None, group=None):
+        import ctypes as C
+
+        import torch
+        import torch.distributed as dist
+
+        from . import _abi
+
+        self.local, self.rank, self.world = local, rank, world
+        lib = local._lib
+        if not hasattr(lib, "yd_shard_init"):
+            raise RuntimeError(f"{lib._yd_path} has no range-sharded path (CUDA library only)")
+        buf = (C.c_uint8 * _abi.SHARD_UNIQUE_ID_BYTES)()
+        if rank == 0 and lib.yd_shard_unique_id(buf) != 0:
+            raise RuntimeError("yd_shard_unique_id failed (libnccl.so.2 not loadable?)")
+        t = torch.tensor(list(buf), dtype=torch.uint8, device=device if dist.get_backend(group) == "nccl" else "cpu")
+        dist.broadcast(t, src=0, group=group)
+        uid = (C.c_uint8 * _abi.SHARD_UNIQUE_ID_BYTES)(*t.cpu().tolist())
+        rc = lib.yd_shard_init(local._h, rank, world, uid)
+        if rc != 0:
+            raise RuntimeError(f"yd_shard_init failed: {rc}")
+
+    def wait_for_starting_new_tasks(self, reqs_local, now: float, out=None):
+        """Collective.  reqs_local: this rank's FIFO range (REQ_DTYPE), or an int n = the first n staged
+        requests (TaskDispatcher.stage_requests).  Returns this rank's grants, or None if the batch has to
+        be solved on one rank (yd_shard_wait_for_starting_new_tasks returned 2: nothing was decided)."""
+        from .dispatcher import _ns
+
+        lib, h = self.local._lib, self.local._h
+        if isinstance(reqs_local, (int, np.integer)):
+            n, ptr = int(reqs_local), None
+        else:
+            assert reqs_local.dtype == REQ_DTYPE and reqs_local.flags.c_contiguous
+            n, ptr = reqs_local.shape[0], reqs_local.ctypes.data
+        if out is None:
+            out = np.zeros(max(n, 1), dtype=GRANT_DTYPE)
+        rc = lib.yd_shard_wait_for_starting_new_tasks(h, _ns(now), ptr, n, out.ctypes.data)
+        if rc == 2:
+            return None
+        if rc != 0:
+            raise RuntimeError(f"yd_shard_wait_for_starting_new_tasks failed: {rc}")
+        return out[:n]
+
+    def free_tasks(self, ids) -> None:
+        """Collective FreeTask: every rank passes the ids it wants released (its own grants, typically)."""
+        ids = np.ascontiguousarray(np.asarray(ids, dtype=np.uint64))
+        rc = self.local._lib.yd_shard_free_tasks(self.local._h, ids.ctypes.data if len(ids) else None, len(ids))
+        if rc != 0:
+            raise RuntimeError(f"yd_shard_free_tasks failed: {rc}")
+
+    def last_stats(self) -> dict | None:
+        import ctypes as C
+
+        from . import _abi
+
+        st = _abi.yd_shard_stats()
+        if not self.local._lib.yd_shard_last_stats(self.local._h, C.byref(st)):
+            return None
+        return {"total_ms": st.total_ms, "exchange_ms": list(st.exchange_ms), "exchange_bytes": list(st.exchange_bytes),
+                "decisions_local": st.decisions_local, "granted_local": st.granted_local, "granted_total": st.granted_total,
+                "merge_rounds": st.merge_rounds, "kernel_launches": st.kernel_launches}
+
+    def close(self) -> None:
+        self.local._lib.yd_shard_finalize(self.local._h)
