@@ -45,11 +45,12 @@
 // soon as one slot can serve both affected classes; measured: a few hundred slots).  A round in
 // which no chunk re-ran certifies the chain: every start state equals its predecessor's end state.
 //
-// Inside a chunk the warp takes 32 slots per step: lane j's choice depends on how many earlier
-// lanes chose each class; the lanes iterate "recompute my choice given the lanes before me" to
-// the (unique) fixed point.  A step in which a lane would pick a request from its own servant
-// commits the lanes before it and handles that slot -- and every slot while requests are
-// pending -- one at a time.
+// Inside a chunk the warp takes 32 slots per step.  With three or more classes the CLASSES sit in the
+// lanes (lane k holds the head of class k's queue) and the 32 slots are decided one after the other
+// by a warp-wide min each; with one or two classes the SLOTS sit in the lanes and iterate
+// "recompute my choice given the lanes before me" to the (unique) fixed point.  A slot that would
+// serve a request from its own servant ends the step: it -- and every slot while requests are
+// pending -- is handled by the exact one-slot step.
 #pragma once
 #include "classes.cuh"
 
@@ -138,7 +139,7 @@ struct MergeSmem {                // static part; the rings are dynamic shared m
   uint32_t lim[32];               // per class: records at hand from there (window - h)
   uint32_t more[32];              // per class: requests beyond the window exist (sharded queue only)
   uint32_t ovf;
-  unsigned long long mbar;
+  unsigned long long mbar[33];    // one mbarrier per stream: class k's records (k < 32), the slot list (32)
 };
 
 
@@ -256,7 +257,7 @@ __device__ __forceinline__ void merge_grid_sync(uint32_t* bar, uint32_t& epoch, 
 
 // Runs chunk t in round r.  Returns 1 if it ran (its start state was new), 0 otherwise.
 __device__ uint32_t merge_run_chunk(const MergeArgs& a, MergeSmem& sm, uint2* ring_ls, uint2* ring_rq, uint32_t ncls,
-                                    uint32_t midx, uint32_t b, uint32_t t, uint32_t r, uint32_t& par) {
+                                    uint32_t midx, uint32_t b, uint32_t t, uint32_t r, uint32_t& par_rq, uint32_t& par_ls) {
   const uint32_t lane = threadIdx.x;
   const uint32_t lt_mask = (1u << lane) - 1;
   const uint32_t comp = a.ct.merge_comp[midx];
@@ -309,16 +310,19 @@ __device__ uint32_t merge_run_chunk(const MergeArgs& a, MergeSmem& sm, uint2* ri
   uint32_t np = st[kMsNp];
 
   // ---- the chunk's slots -----------------------------------------------------------------------
-  uint64_t* mbar = reinterpret_cast<uint64_t*>(&sm.mbar);
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(sm.mbar);
   uint32_t base = lb;
   bool dead = false;
   // Ring bookkeeping, per stream owner (lane k for class k's records, lane 0 also for the slot list): blocks below
   // `*_hi` are in the ring or on their way, blocks below `*_ok` have landed.  A step reads blocks jb and jb + 1 of a
-  // stream; block jb + 2 is requested as soon as jb is reached, i.e. a block is asked for a whole block of progress
-  // before it is read, and nobody waits for it until then: steady-state steps touch neither the barrier nor HBM.
+  // stream; block jb + 2 is requested as soon as jb is reached, i.e. a whole block of progress before it is read,
+  // and nobody waits for it until then.  Every stream has its OWN mbarrier (one request in flight per stream), so a
+  // class that crosses a block boundary never waits for another class's copy: steady-state steps touch neither a
+  // barrier nor HBM.
   uint32_t rq_hi = 0, rq_ok = 0, ls_hi = 0, ls_ok = 0;
-  bool prime = true;     // the rings hold nothing useful (chunk start, or a one-slot step moved h): refill, then wait
-  bool pending = false;  // copies of the last request may still be in flight
+  bool prime = true;          // the rings hold nothing useful (chunk start, or a one-slot step moved h)
+  bool rq_pend = false, ls_pend = false;
+  uint32_t rq_par = par_rq, ls_par = par_ls;  // phase parity of my barriers (kept across chunks by the caller)
   while (base < le) {
     if (np == 0 && __reduce_add_sync(0xffffffffu, lane < K ? n - h : 0u) == 0) break;  // every request is served
     // ---- top up the rings ---------------------------------------------------------------------------------
@@ -326,53 +330,109 @@ __device__ uint32_t merge_run_chunk(const MergeArgs& a, MergeSmem& sm, uint2* ri
       const uint32_t jb = (rq_base + h) >> 5;
       const bool mine = lane < K && h < win;
       if (mine && (prime || rq_hi < jb || rq_hi > jb + 3)) { rq_hi = jb; rq_ok = jb; }  // nothing useful there
-      const uint32_t from = mine ? rq_hi : 0u, to = mine ? jb + 3 : 0u;
+      const bool need = mine && rq_hi < jb + 3;
       const uint32_t ljb = base >> 5;
       if (lane == 0 && (prime || ls_hi < ljb || ls_hi > ljb + 3)) { ls_hi = ljb; ls_ok = ljb; }
       const bool lneed = lane == 0 && ls_hi < ljb + 3;
-      if (__any_sync(0xffffffffu, from < to || lneed)) {
-        if (pending) {  // one request in flight at a time: its data has had at least a block of progress to arrive
-          mbar_wait(mbar, par); par ^= 1; pending = false;
-          rq_ok = rq_hi; ls_ok = ls_hi;
-        }
-        uint32_t bytes = 0;
+      if (__any_sync(0xffffffffu, need || lneed)) {
+        // my previous request (a block of progress ago) must have landed before the stream's barrier is reused
+        if (need && rq_pend) { mbar_wait(&mbar[lane], rq_par); rq_par ^= 1; rq_pend = false; rq_ok = rq_hi; }
+        if (lneed && ls_pend) { mbar_wait(&mbar[32], ls_par); ls_par ^= 1; ls_pend = false; ls_ok = ls_hi; }
+        __syncwarp();
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // earlier generic reads of a slot before its refill
-        for (uint32_t k = 0; k < K; ++k) {
-          const uint32_t f = __shfl_sync(0xffffffffu, from, k), e2 = __shfl_sync(0xffffffffu, to, k);
+        const uint32_t needb = __ballot_sync(0xffffffffu, need);
+        for (uint32_t todo = needb; todo; todo &= todo - 1) {
+          const uint32_t k = __ffs(todo) - 1;
+          const uint32_t f = __shfl_sync(0xffffffffu, rq_hi, k), e2 = __shfl_sync(0xffffffffu, jb + 3, k);
           if (lane == 0) {
+            uint32_t bytes = 0;
             for (uint32_t blk = f; blk < e2; ++blk) {
               if (blk >= a.rq_blocks) break;
-              bulk_g2s(ring_rq + size_t(k) * kRingRecs + (blk & (kRingBlocks - 1)) * 32, a.rq + size_t(blk) * 32, 256, mbar);
+              bulk_g2s(ring_rq + size_t(k) * kRingRecs + (blk & (kRingBlocks - 1)) * 32, a.rq + size_t(blk) * 32, 256, &mbar[k]);
               bytes += 256;
             }
+            mbar_arrive_expect_tx(&mbar[k], bytes);
           }
         }
-        if (lane == 0) {
-          for (uint32_t blk = ls_hi; blk < ljb + 3; ++blk) {
-            if (blk >= a.ls_blocks) break;
-            bulk_g2s(ring_ls + (blk & (kRingBlocks - 1)) * 32, a.list + size_t(blk) * 32, 256, mbar);
-            bytes += 256;
+        if (__shfl_sync(0xffffffffu, lneed ? 1u : 0u, 0)) {
+          if (lane == 0) {
+            uint32_t bytes = 0;
+            for (uint32_t blk = ls_hi; blk < ljb + 3; ++blk) {
+              if (blk >= a.ls_blocks) break;
+              bulk_g2s(ring_ls + (blk & (kRingBlocks - 1)) * 32, a.list + size_t(blk) * 32, 256, &mbar[32]);
+              bytes += 256;
+            }
+            mbar_arrive_expect_tx(&mbar[32], bytes);
+            ls_hi = ljb + 3;
+            ls_pend = true;
           }
-          ls_hi = ljb + 3;
-          mbar_arrive_expect_tx(mbar, bytes);
-        } else {
-          mbar_arrive(mbar);
         }
-        if (from < to) rq_hi = to;
-        pending = true;
+        if (need) { rq_hi = jb + 3; rq_pend = true; }
+        __syncwarp();
       }
       // this step reads blocks jb, jb + 1 of every stream: have they landed?
-      const bool short_rq = mine && rq_ok < jb + 2, short_ls = lane == 0 && ls_ok < ljb + 2;
-      if (pending && __any_sync(0xffffffffu, short_rq || short_ls)) {
-        mbar_wait(mbar, par); par ^= 1; pending = false;
-        rq_ok = rq_hi; ls_ok = ls_hi;
-      }
+      if (mine && rq_ok < jb + 2 && rq_pend) { mbar_wait(&mbar[lane], rq_par); rq_par ^= 1; rq_pend = false; rq_ok = rq_hi; }
+      if (lane == 0 && ls_ok < ljb + 2 && ls_pend) { mbar_wait(&mbar[32], ls_par); ls_par ^= 1; ls_pend = false; ls_ok = ls_hi; }
+      __syncwarp();
       prime = false;
     }
 
     if (np == 0) {
       const uint32_t idx = base + lane;
       const uint2 e = idx < le ? ring_ls[idx & (kRingRecs - 1)] : make_uint2(0, 0);  // mask 0: no slot in this lane
+      uint32_t fb = 32, my_pick = kNone;
+      if (K > 2) {
+        // Slot by slot, the CLASSES in the lanes: lane k holds the head of class k's queue (`cur`, and the record
+        // behind it) and a bit per slot "my class is eligible on that slot's servant"; a slot's verdict is one
+        // warp-wide min over those heads.  The loop carries one dependency -- the winner's head moves on -- through a
+        // redux and a handful of ALU instructions; no votes, no shuffles, no branches inside.
+        constexpr uint32_t kMissing = 0xFFFFFFFEu;  // "a request exists here but its record was not gathered" (sharded queue)
+        const uint32_t my_a = rq_base + h, my_lim = (lane < K && win > h) ? win - h : 0u;
+        const uint32_t my_more = (lane < K && n > win) ? n - h : 0u;
+        const uint2* my_ring = ring_rq + size_t(lane < K ? lane : 0) * kRingRecs;
+        uint32_t elig = 0;  // bit j: slot j's servant is eligible for my class
+        for (uint32_t k = 0; k < K; ++k) {
+          const uint32_t bk = __ballot_sync(0xffffffffu, (e.y >> k) & 1u);
+          if (lane == k) elig = bk;
+        }
+        auto rec = [&](uint32_t i) -> uint2 {  // my class's i-th record from h
+          if (i < my_lim) return my_ring[(my_a + i) & (kRingRecs - 1)];
+          return make_uint2(i < my_more ? kMissing : kNone, kNone);
+        };
+        uint32_t taken = 0;
+        bool miss = false;
+        uint2 cur = rec(0), nxt = rec(1);
+#pragma unroll 4
+        for (int j = 0; j < 32; ++j) {
+          const bool in = (elig >> j) & 1u;
+          const uint32_t cand = in ? cur.x : kNone;
+          miss |= in && cur.x == kMissing;  // whoever wins this slot, an unseen request might have been earlier
+          const uint32_t m = __reduce_min_sync(0xffffffffu, cand);
+          const bool won = in && cand == m;  // (m == kNone: nobody is `in` with a request left; harmless below)
+          if (lane == (uint32_t)j) my_pick = m;
+          if (won && m < kMissing) {
+            sm.a[j] = cur.y;    // the served request's own servant ...
+            sm.lim[j] = lane;   // ... and its class, for the check after the loop
+            ++taken;
+            cur = nxt;
+            nxt = rec(taken + 1);
+          }
+        }
+        __syncwarp();
+        if (__any_sync(0xffffffffu, miss)) { dead = true; break; }
+        // a slot that took a request from its own servant: the step ends before it (the one-slot step decides it)
+        const uint32_t cb = __ballot_sync(0xffffffffu, my_pick != kNone && sm.a[lane] == e.x);
+        if (cb) {
+          fb = (uint32_t)__ffs(cb) - 1u;
+          const uint32_t pc_ = (my_pick != kNone && lane < fb) ? sm.lim[lane] : 32u;  // class of the request my slot took
+          taken = 0;
+          for (uint32_t k = 0; k < K; ++k) {
+            const uint32_t tk = __popc(__ballot_sync(0xffffffffu, pc_ == k));
+            if (lane == k) taken = tk;
+          }
+        }
+        h += taken;
+      } else {
       if (lane < K) { sm.a[lane] = rq_base + h; sm.lim[lane] = win > h ? win - h : 0u; sm.more[lane] = n > win ? n - h : 0u; }
       __syncwarp();
       uint32_t pick = 32, best = kNone, bself = kNone;
@@ -397,12 +457,14 @@ __device__ uint32_t merge_run_chunk(const MergeArgs& a, MergeSmem& sm, uint2* ri
       if (sm.ovf) { dead = true; break; }
       // a lane that would serve a request from its own servant: commit the lanes before it only
       const uint32_t cb = __ballot_sync(0xffffffffu, pick < 32 && bself == e.x);
-      const uint32_t fb = cb ? (uint32_t)__ffs(cb) - 1u : 32u;
+      fb = cb ? (uint32_t)__ffs(cb) - 1u : 32u;
       for (uint32_t k = 0; k < K; ++k) {
         const uint32_t took = __popc(__ballot_sync(0xffffffffu, lane < fb && pick == k));
         if (lane == k) h += took;
       }
-      if (lane < fb && idx < le) a.slot_pick[idx] = pick < 32 ? best : kNone;
+      my_pick = pick < 32 ? best : kNone;
+      }
+      if (lane < fb && idx < le) a.slot_pick[idx] = my_pick;
       __syncwarp();
       base += fb;
       if (fb == 32) continue;
@@ -477,7 +539,11 @@ __device__ uint32_t merge_run_chunk(const MergeArgs& a, MergeSmem& sm, uint2* ri
       base += 1;
     }
   }
-  if (pending) { mbar_wait(mbar, par); par ^= 1; }  // nothing may still be landing in the rings when the warp moves on
+  // nothing may still be landing in the rings when the warp moves on
+  if (rq_pend) { mbar_wait(&mbar[lane], rq_par); rq_par ^= 1; }
+  if (ls_pend) { mbar_wait(&mbar[32], ls_par); ls_par ^= 1; }
+  par_rq = rq_par; par_ls = ls_par;
+  __syncwarp();
   if (dead) {  // more pending runs than a state carries / a record that was not gathered: the sequential solver decides
     if (lane == 0) atomicExch(a.mp.viol + comp, 1u);
     return 1;
@@ -520,10 +586,12 @@ __global__ void __launch_bounds__(32) k_merge_solve(MergeArgs a) {
     carry += __shfl_sync(0xffffffffu, x, 31);
   }
   const uint32_t total = min(carry, a.max_chunks);
-  if (lane == 0) { sm.chunk_base[nmerge] = carry; mbar_init(reinterpret_cast<uint64_t*>(&sm.mbar), 32); }
+  if (lane == 0) sm.chunk_base[nmerge] = carry;
+  mbar_init(reinterpret_cast<uint64_t*>(sm.mbar) + lane, 1);  // one arrival per phase: the elected lane's expect_tx
+  if (lane == 0) mbar_init(reinterpret_cast<uint64_t*>(sm.mbar) + 32, 1);
   __syncwarp();
   if (total == 0) return;
-  uint32_t par = 0, epoch = 0;
+  uint32_t par_rq = 0, par_ls = 0, epoch = 0;
   // ---- rounds -----------------------------------------------------------------------------------------------
   for (uint32_t r = 0;; ++r) {
     if (blockIdx.x == 0 && lane == 0) atomicExch(&a.mp.changed[(r + 1) & 15u], 0u);  // (nobody touches that cell during round r)
@@ -531,7 +599,7 @@ __global__ void __launch_bounds__(32) k_merge_solve(MergeArgs a) {
     for (uint32_t t = blockIdx.x; t < total; t += gridDim.x) {
       uint32_t midx, b;
       merge_locate(sm, nmerge, t, midx, b);
-      ran += merge_run_chunk(a, sm, ring_ls, ring_rq, ncls, midx, b, t, r, par);
+      ran += merge_run_chunk(a, sm, ring_ls, ring_rq, ncls, midx, b, t, r, par_rq, par_ls);
       __syncwarp();
     }
     if (r > 0 && ran && lane == 0) atomicAdd(&a.mp.changed[r & 15u], ran);
@@ -562,22 +630,25 @@ __global__ void __launch_bounds__(32) k_merge_solve(MergeArgs a) {
       if (q != kNone && q - a.L.q_base < a.L.n_local) a.res[q - a.L.q_base] = li;  // (requests of this rank's range)
     }
   }
-  merge_grid_sync(a.mp.bar, epoch, lane);
-  // ---- the last-resort rule (cc:394-396): an unserved request whose own servant still had a slot at its turn would
-  // have taken it.  One such request and the component goes to the sequential solver. --------------------------------------
-  const uint32_t nreq = a.dp->n;
-  for (uint32_t q = blockIdx.x * 32 + lane; q < nreq; q += gridDim.x * 32) {
-    const uint32_t c = a.rcls[q];
-    if (c == kNone) continue;
-    const uint32_t comp = a.ct.cls_comp[c];
-    if (a.comp_mode[comp] != 2 || !(a.ct.comp_flags[comp] & 1u)) continue;
-    const uint32_t self = a.rself[q];
-    if (self == kNone || __ldcg(a.res + q) != kResTimeout) continue;
-    const uint32_t pos = a.t.comp_sv[a.t.comp_sv_off[comp] + self];
-    if (__ldcg(a.mp.tau + pos) <= a.L.q_base + q) continue;  // every slot of the own servant went to an earlier request
-    if (a.sv.max_tasks[pos] != 0 && (uint32_t)a.sv.version[pos] >= a.ct.cls_mv[c] && servant_has_env(a.t, pos, a.ct.cls_env[c])) {
-      atomicExch(a.mp.viol + comp, 1u);
-    }
+}
+
+// The last-resort rule (cc:394-396): an unserved request whose own servant still had a slot at its turn would have
+// taken it.  One such request and the component goes to the sequential solver.  (Its own launch: it is a pass over
+// all REQUESTS, far wider than the merge kernel's co-resident grid.)
+__global__ void __launch_bounds__(256) k_merge_check(MergeArgs a) {
+  if (a.ct.meta[1] || a.ct.meta[2] == 0) return;
+  const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= a.dp->n) return;
+  const uint32_t c = a.rcls[q];
+  if (c == kNone) return;
+  const uint32_t comp = a.ct.cls_comp[c];
+  if (a.comp_mode[comp] != 2 || !(a.ct.comp_flags[comp] & 1u)) return;
+  const uint32_t self = a.rself[q];
+  if (self == kNone || a.res[q] != kResTimeout) return;
+  const uint32_t pos = a.t.comp_sv[a.t.comp_sv_off[comp] + self];
+  if (a.mp.tau[pos] <= a.L.q_base + q) return;  // every slot of the own servant went to an earlier request
+  if (a.sv.max_tasks[pos] != 0 && (uint32_t)a.sv.version[pos] >= a.ct.cls_mv[c] && servant_has_env(a.t, pos, a.ct.cls_env[c])) {
+    atomicExch(a.mp.viol + comp, 1u);
   }
 }
 

@@ -183,7 +183,7 @@ struct yd_sched {
   // merge solver (solve_merge.cuh): per-slot verdicts and the chunk boundary states
   DevBuf d_slot_pick, d_mst_in, d_mst_out, d_stream_scratch;
   size_t z_merge_off = 0, z_layout_off = 0, z_final_off = 0;
-  uint32_t merge_chunk = 1024, merge_rounds = 8, merge_max_chunks = 0, merge_grid = 0, merge_grid_kcap = 0;
+  uint32_t merge_chunk = 512, merge_rounds = 8, merge_max_chunks = 0, merge_grid = 0, merge_grid_kcap = 0;
   uint32_t stream_debug = 0;   // YDSCHED_STREAM_DEBUG, read once at yd_create
   uint32_t force_stream = 0;   // yd_config.reserved bit 1 / YDSCHED_FORCE_STREAM: no merge solver for self-requests
   bool dump_env = false, debug_env = false;
@@ -837,7 +837,8 @@ uint32_t LaunchMerge(yd_sched* s, yd::MergeArgs& m, cudaStream_t st) {
   m.ls_blocks = (uint32_t)(s->d_list.cap / 256);
   const uint32_t grid = std::min(s->merge_grid, s->merge_max_chunks);
   yd::k_merge_solve<<<grid, 32, dyn, st>>>(m);
-  return 1;
+  yd::k_merge_check<<<(std::max(m.L.n_local, 1u) + 255) / 256, 256, 0, st>>>(m);
+  return 2;
 }
 
 constexpr size_t kStaticSlotLimit = size_t(1) << 26;
