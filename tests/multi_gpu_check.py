@@ -69,6 +69,7 @@ def check(name, w, skew, rank, world, dev, golden=None):
     if rank == 0:
         single = TaskDispatcher(device=dev.index)
         w.register(single, now=0.0, expires_in=3600.0)
+        full_single = w.build_requests(single)  # (digest / IP ids are per handle)
     ok_all = True
     for rnd in range(2):
         now = 0.001 + rnd
@@ -81,7 +82,7 @@ def check(name, w, skew, rank, world, dev, golden=None):
         dist.all_reduce(alive)
         stats = sd.last_stats()
         if rank == 0:
-            g_one = single.wait_for_starting_new_tasks(full, now)
+            g_one = single.wait_for_starting_new_tasks(full_single, now)
             st1 = single.servant_state()
             same = (bool((g_all["status"] == g_one["status"]).all()) and bool((g_all["servant_index"] == g_one["servant_index"]).all())
                     and bool((g_all["task_id"] == g_one["task_id"]).all()))
@@ -92,6 +93,12 @@ def check(name, w, skew, rank, world, dev, golden=None):
                     "granted": int((g_one["status"] == STATUS_GRANTED).sum()), "grants_equal": same, "state_equal": same_state,
                     "ids_equal": same_ids, "exchange_ms": [round(x, 4) for x in stats["exchange_ms"]],
                     "exchange_bytes": stats["exchange_bytes"], "total_ms": round(stats["total_ms"], 4)}
+            if not same:
+                bad = {k: int((g_all[k] != g_one[k]).sum()) for k in ("status", "servant_index", "task_id")}
+                first = int(np.nonzero((g_all["status"] != g_one["status"]) | (g_all["servant_index"] != g_one["servant_index"])
+                                       | (g_all["task_id"] != g_one["task_id"]))[0][0])
+                line["mismatches"] = bad
+                line["first"] = {"index": first, "cuts": cuts, "sharded": [int(x) for x in g_all[first]], "single": [int(x) for x in g_one[first]]}
             if golden is not None and rnd == 0:
                 trace = [g_all, np.stack([st["running_tasks"], st["ever_assigned_tasks"], st["capacity_available"]], axis=1),
                          np.asarray([d.next_task_id(), int(alive.item()), d.num_servants()], dtype=np.uint64)]
