@@ -49,6 +49,8 @@ from pathlib import Path
 
 import numpy as np
 
+os.environ["NCCL_DEBUG"] = os.environ.get("YD_NCCL_DEBUG", "WARN")  # (NCCL's version banner goes to stdout: one JSON line only)
+
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 

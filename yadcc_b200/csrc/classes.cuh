@@ -195,7 +195,7 @@ __global__ void __launch_bounds__(32) k_cls_merge_tables(const uint32_t* __restr
 __global__ void __launch_bounds__(1024) k_cls_finalize(TopoView t, ClassTable ct, ServantArrays sv, uint32_t n_comps,
                                                        uint32_t* __restrict__ comp_mode) {
   __shared__ uint32_t warp_sums[32];
-  __shared__ uint32_t carry_s, s_sum;
+  __shared__ uint32_t carry_s;
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) carry_s = 0;
   __syncthreads();
@@ -248,21 +248,6 @@ __global__ void __launch_bounds__(1024) k_cls_finalize(TopoView t, ClassTable ct
   }
   __threadfence_block();
   __syncthreads();
-  // eligible servants per class: max_tasks != 0, digest held, version >= min_version (cc:316-344)
-  for (uint32_t c = 0; c < ncls; ++c) {
-    if (tid == 0) s_sum = 0;
-    __syncthreads();
-    const uint32_t comp = ct.cls_comp[c], env = ct.cls_env[c], mv = ct.cls_mv[c];
-    uint32_t mine = 0;
-    for (uint32_t i = t.comp_sv_off[comp] + tid, e = t.comp_sv_off[comp + 1]; i < e; i += 1024) {
-      const uint32_t pos = t.comp_sv[i];
-      mine += (sv.max_tasks[pos] != 0 && (uint32_t)sv.version[pos] >= mv && servant_has_env(t, pos, env)) ? 1u : 0u;
-    }
-    if (mine) atomicAdd(&s_sum, mine);
-    __syncthreads();
-    if (tid == 0) ct.cls_nelig[c] = s_sum;
-    __syncthreads();
-  }
   // index of each class among the classes of its component
   for (uint32_t c = tid; c < ncls; c += 1024) {
     uint32_t lb = 0;
@@ -303,6 +288,26 @@ __global__ void __launch_bounds__(1024) k_cls_finalize(TopoView t, ClassTable ct
     ct.meta[2] = s_nmerge;
     ct.meta[3] = min(ncls + s_nmerge, ct.cls_bound);  // lists to build: classes + merge pseudo-classes
   }
+}
+
+// Eligible servants per class: max_tasks != 0, digest held, version >= min_version (cc:316-344); 0 => every request
+// of the class is EnvironmentNotFound (cc:105-108).  One block per class, beside the list kernels.
+__global__ void __launch_bounds__(256) k_cls_elig(TopoView t, ClassTable ct, ServantArrays sv) {
+  __shared__ uint32_t s_sum;
+  const uint32_t c = blockIdx.x;
+  if (c >= min(ct.meta[0], ct.cls_bound)) return;
+  if (threadIdx.x == 0) s_sum = 0;
+  __syncthreads();
+  const uint32_t comp = ct.cls_comp[c], env = ct.cls_env[c], mv = ct.cls_mv[c];
+  uint32_t mine = 0;
+  for (uint32_t i = t.comp_sv_off[comp] + threadIdx.x, e = t.comp_sv_off[comp + 1]; i < e; i += blockDim.x) {
+    const uint32_t pos = t.comp_sv[i];
+    mine += (sv.max_tasks[pos] != 0 && (uint32_t)sv.version[pos] >= mv && servant_has_env(t, pos, env)) ? 1u : 0u;
+  }
+  mine = __reduce_add_sync(0xffffffffu, mine);
+  if ((threadIdx.x & 31) == 0 && mine) atomicAdd(&s_sum, mine);
+  __syncthreads();
+  if (threadIdx.x == 0) ct.cls_nelig[c] = s_sum;
 }
 
 // Per-class sorted slot lists.  A block owns a tile of 1024 SORTED slots, decodes each

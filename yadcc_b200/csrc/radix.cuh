@@ -33,6 +33,84 @@ __device__ __forceinline__ uint32_t rs_digit(KeyT k, int shift) {
   return (uint32_t)(k >> shift) & (kRsBins - 1);
 }
 
+constexpr int kScanItems8 = 8;
+
+// Exclusive scan (in place) of a (rows x per_row) count matrix laid out row-major, + the grand total in the cell
+// behind it -- the (class, tile) count tables of classes.cuh / parallel.cuh.  One block per row: the row is scanned
+// on its own, its total published (a 64-bit word per row in `pub`, gridDim.x + 1 words zeroed by the caller: bit 63 = ready), the totals of
+// the rows before it summed, and the base added in a second sweep.  rows = min(*n_rows_dyn, gridDim.x) blocks take
+// part; they are co-resident (<= 256 blocks), so waiting for lower rows cannot dead-lock.
+__global__ void __launch_bounds__(1024) k_scan_rows(uint32_t* __restrict__ data, const uint32_t* __restrict__ n_rows_dyn,
+                                                    uint32_t per_row, unsigned long long* __restrict__ pub) {
+  __shared__ uint32_t warp_sums[32];
+  __shared__ uint32_t carry_s, base_s, row_s;
+  const uint32_t rows = min(*n_rows_dyn, gridDim.x);
+  // rows are handed out by ticket (pub[gridDim.x]): whoever waits for a lower row knows that row is running
+  if (threadIdx.x == 0) row_s = (uint32_t)atomicAdd(&pub[gridDim.x], 1ull);
+  __syncthreads();
+  const uint32_t row = row_s;
+  if (row >= rows) return;
+  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  uint32_t* d = data + size_t(row) * per_row;
+  if (tid == 0) carry_s = 0;
+  __syncthreads();
+  for (uint32_t b0 = 0; b0 < per_row; b0 += 1024 * kScanItems8) {
+    const uint32_t i0 = b0 + tid * kScanItems8;
+    uint32_t v[kScanItems8];
+#pragma unroll
+    for (int k = 0; k < kScanItems8; ++k) v[k] = (i0 + k < per_row) ? d[i0 + k] : 0;
+    uint32_t sum = 0;
+#pragma unroll
+    for (int k = 0; k < kScanItems8; ++k) sum += v[k];
+    uint32_t x = sum;
+#pragma unroll
+    for (int s = 1; s < 32; s <<= 1) {
+      const uint32_t y = __shfl_up_sync(0xffffffffu, x, s);
+      if (lane >= s) x += y;
+    }
+    if (lane == 31) warp_sums[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+      uint32_t w = warp_sums[lane];
+#pragma unroll
+      for (int s = 1; s < 32; s <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xffffffffu, w, s);
+        if (lane >= s) w += y;
+      }
+      warp_sums[lane] = w;
+    }
+    __syncthreads();
+    const uint32_t carry = carry_s;
+    uint32_t run = carry + (warp ? warp_sums[warp - 1] : 0) + x - sum;
+#pragma unroll
+    for (int k = 0; k < kScanItems8; ++k) {
+      if (i0 + k < per_row) d[i0 + k] = run;
+      run += v[k];
+    }
+    __syncthreads();
+    if (tid == 1023) carry_s = carry + warp_sums[31];
+    __syncthreads();
+  }
+  volatile unsigned long long* vp = pub;
+  if (tid == 0) { __threadfence(); vp[row] = (1ull << 63) | carry_s; }
+  if (warp == 0) {  // totals of the rows before mine
+    uint32_t base = 0;
+    for (uint32_t r0 = 0; r0 < row; r0 += 32) {
+      const uint32_t r = r0 + lane;
+      unsigned long long w = 1ull << 63;
+      if (r < row) { do { w = vp[r]; } while (!(w >> 63)); }
+      base += __reduce_add_sync(0xffffffffu, r < row ? (uint32_t)w : 0u);
+    }
+    if (lane == 0) base_s = base;
+  }
+  __syncthreads();
+  const uint32_t base = base_s;
+  if (base) {
+    for (uint32_t i = tid; i < per_row; i += 1024) d[i] += base;
+  }
+  if (row == rows - 1 && tid == 0) data[size_t(rows) * per_row] = base + carry_s;  // the end cell
+}
+
 // Generic one-block exclusive scan (in place).  Each thread owns 8 consecutive
 // values (two 16-byte loads), so 8192 values need one block-wide round.  The length
 // is n_static, or min(*n_dyn, dyn_cap) * per_dyn + 1 when n_dyn != nullptr (sizes that only

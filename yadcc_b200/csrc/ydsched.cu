@@ -177,12 +177,12 @@ struct yd_sched {
   size_t z_hist_off[10] = {}, z_cls_off = 0, z_listcnt_off = 0, z_bytes = 0;
   uint32_t sort_nb = 0;
   cudaStream_t st2 = nullptr, st_copy = nullptr;  // class/rank branch; request upload
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_h2d = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_h2d = nullptr, ev_fin = nullptr;
   uint32_t cls_bound = 16;  // classes the per-class grids are sized for; grows on demand (<= yd::kMaxClasses)
   DevBuf d_list, d_list_bal, d_rcls, d_rrank, d_rank_cnt, d_rq, d_rself;
   // merge solver (solve_merge.cuh): per-slot verdicts and the chunk boundary states
   DevBuf d_slot_pick, d_mst_in, d_mst_out, d_stream_scratch;
-  size_t z_merge_off = 0, z_layout_off = 0, z_final_off = 0;
+  size_t z_merge_off = 0, z_layout_off = 0, z_final_off = 0, z_scan_off = 0;
   uint32_t merge_chunk = 512, merge_rounds = 8, merge_max_chunks = 0, merge_grid = 0, merge_grid_kcap = 0;
   uint32_t stream_debug = 0;   // YDSCHED_STREAM_DEBUG, read once at yd_create
   uint32_t force_stream = 0;   // yd_config.reserved bit 1 / YDSCHED_FORCE_STREAM: no merge solver for self-requests
@@ -528,6 +528,7 @@ yd_sched* yd_create(const yd_config* cfg) {
   YD_CUDA_CHECK(cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming));
   YD_CUDA_CHECK(cudaEventCreateWithFlags(&s->ev_join, cudaEventDisableTiming));
   YD_CUDA_CHECK(cudaEventCreateWithFlags(&s->ev_h2d, cudaEventDisableTiming));
+  YD_CUDA_CHECK(cudaEventCreateWithFlags(&s->ev_fin, cudaEventDisableTiming));
   s->ips.emplace_back();  // id 0 == YD_IP_NONE == the empty requestor string
   s->ip_ids.emplace("", 0);
   s->d_counters.ensure(sizeof(Counters));
@@ -565,7 +566,7 @@ void yd_destroy(yd_sched* s) {
   s->d_dyn.release();
   for (PinBuf* b : {&s->h_facts, &s->h_topo, &s->h_counters, &s->h_small, &s->h_dyn, &s->h_meta}) b->release();
   for (auto& e : s->ev) cudaEventDestroy(e);
-  cudaEventDestroy(s->ev_fork); cudaEventDestroy(s->ev_join); cudaEventDestroy(s->ev_h2d);
+  cudaEventDestroy(s->ev_fork); cudaEventDestroy(s->ev_join); cudaEventDestroy(s->ev_h2d); cudaEventDestroy(s->ev_fin);
   cudaStreamDestroy(s->st2); cudaStreamDestroy(s->st_copy);
   cudaStreamDestroy(s->st);
   delete s;
@@ -671,6 +672,11 @@ yd::MergePlan MakeMergePlan(yd_sched* s) {
   mp.viol = u;                           u += s->n_comps;
   mp.tau = u;                            // [S]
   return mp;
+}
+
+// Row-total mailboxes of the two row-parallel scans (k_scan_rows), in the zeroed scratch region.
+unsigned long long* ScanPub(yd_sched* s, int which) {
+  return reinterpret_cast<unsigned long long*>(static_cast<char*>(s->d_zero.p) + s->z_scan_off) + size_t(which) * (yd::kMaxClasses + 1);
 }
 
 yd::RqLayout MakeRqLayout(yd_sched* s, uint32_t q_base, uint32_t n_local, bool sharded) {
@@ -793,6 +799,8 @@ void PrepareStreamBuffers(yd_sched* s, uint32_t Nb, size_t slot_b) {
   s->z_layout_off = off;
   off += (4 * yd::kMaxClasses + 8) * 4;
   off = (off + 7) & ~size_t(7);
+  s->z_scan_off = off;
+  off += 2 * (yd::kMaxClasses + 1) * 8;
   s->z_final_off = off;
   off += (size_t(Nb + 1023) / 1024 + 2) * 8;
   const uint32_t n_tiles = (uint32_t)((slot_b + yd::kListTile - 1) / yd::kListTile);
@@ -890,21 +898,22 @@ uint32_t LaunchStream(yd_sched* s, uint32_t N, size_t slot_b, bool capturing) {
   YD_CUDA_CHECK(cudaStreamWaitEvent(st2, s->ev_h2d, capturing ? cudaEventWaitExternal : 0));
   yd::k_cls_insert<<<(N + 255) / 256, 256, 0, st2>>>(s->d_reqs.as<yd_task_req>(), dp, t, ct);
   yd::k_cls_finalize<<<1, 1024, 0, st2>>>(t, ct, arr, s->n_comps, s->d_comp_mode.as<uint32_t>());
+  YD_CUDA_CHECK(cudaEventRecord(s->ev_fin, st2));  // the list kernels on `st` need the class table, not what follows
+  yd::k_cls_elig<<<ct.cls_bound, 256, 0, st2>>>(t, ct, arr);
   yd::k_rank_count<<<n_rtiles, yd::kRankTile, 0, st2>>>(s->d_reqs.as<yd_task_req>(), dp, t, ct,
                                                          s->d_comp_mode.as<uint32_t>(), n_rtiles,
                                                          s->d_rcls.as<uint32_t>(), s->d_rrank.as<uint32_t>(),
                                                          s->d_rself.as<uint32_t>(), s->d_rank_cnt.as<uint32_t>());
-  yd::k_scan_u32<<<1, 1024, 0, st2>>>(s->d_rank_cnt.as<uint32_t>(), 0, ct.meta, n_rtiles, nullptr, ct.cls_bound);
+  yd::k_scan_rows<<<ct.cls_bound, 1024, 0, st2>>>(s->d_rank_cnt.as<uint32_t>(), ct.meta, n_rtiles, ScanPub(s, 0));
   YD_CUDA_CHECK(cudaEventRecord(s->ev_join, st2));
-  launches += 4;
+  launches += 5;
   // branch A: slot table and its sort -- unless the kept (static) order is valid
   if (!s->order_static) {
     launches += LaunchSlotTable(s, true);
     if (s->wide) launches += LaunchSort<unsigned long long>(s, 0, 62);
     else launches += LaunchSort<uint32_t>(s, 3, 30);
   }
-  // ---- join -----------------------------------------------------------------------
-  YD_CUDA_CHECK(cudaStreamWaitEvent(st, s->ev_join, 0));
+  YD_CUDA_CHECK(cudaStreamWaitEvent(st, s->ev_fin, 0));
 
   // ---- per-class sorted slot lists ----------------------------------------------------
   const unsigned long long* m_ptr = &s->d_counters.as<Counters>()->slots;
@@ -912,11 +921,13 @@ uint32_t LaunchStream(yd_sched* s, uint32_t N, size_t slot_b, bool capturing) {
                      s->d_row_len.as<uint32_t>(), s->d_run.as<uint32_t>(), s->order_static ? 1u : 0u};
   yd::k_list_count<<<n_tiles, yd::kListTile, 0, st>>>(m_ptr, dec, t, ct, arr, n_tiles, list_cnt,
                                                       s->d_list_bal.as<uint32_t>());
-  yd::k_scan_u32<<<1, 1024, 0, st>>>(list_cnt, 0, ct.meta + 3, n_tiles, nullptr, ct.cls_bound);
+  yd::k_scan_rows<<<ct.cls_bound, 1024, 0, st>>>(list_cnt, ct.meta + 3, n_tiles, ScanPub(s, 1));
   yd::k_list_fill<<<n_tiles, yd::kListTile, 0, st>>>(m_ptr, dec, t, ct, n_tiles, list_cnt, s->d_list_bal.as<uint32_t>(),
                                                      s->d_list.as<uint2>(), (uint32_t)(slot_b * 4));
   launches += 3;
 
+  // ---- join: FIFO ranks and eligibility counts are needed from here on ---------------------------------------
+  YD_CUDA_CHECK(cudaStreamWaitEvent(st, s->ev_join, 0));
   // ---- data-parallel path: single-class components without self-requests ----------------
   // (n_local = the grid bound: res[] has that many cells and only requests < dp->n are ever named)
   const yd::RqLayout L = MakeRqLayout(s, 0, N, false);
@@ -1008,8 +1019,9 @@ uint32_t EnqueueSolve(yd_sched* s, uint32_t Nb, size_t slot_b, uint32_t solver, 
     if (have_work) launches += LaunchRowscan(s);
   }
   if (record_events) YD_CUDA_CHECK(cudaEventRecord(s->ev[3], st));
-  if (solver == 2 && have_work) {
-    // grants, task ids (single-pass scan with look-back), leases, ++running_tasks: one launch
+  if (solver == 2 && have_work && nb <= 2048) {
+    // grants, task ids (single-pass scan with look-back), leases, ++running_tasks: one launch (beyond ~2 M requests the
+    // look-back chain of 1024-thread blocks is slower than three plain passes)
     unsigned long long* look = reinterpret_cast<unsigned long long*>(static_cast<char*>(s->d_zero.p) + s->z_final_off);
     yd::k_final_fused<<<nb, 1024, 0, st>>>(s->d_res.as<uint32_t>(), s->d_reqs.as<yd_task_req>(), dp, look, nb,
                                            s->d_comp_sv.as<uint32_t>(), s->ring(), s->d_out.as<yd_grant>(),
