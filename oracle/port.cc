@@ -443,26 +443,6 @@ uint64_t yd_next_task_id(yd_sched* s) { return s->next_task_id * s->id_stride + 
 uint64_t yd_num_tasks(yd_sched* s) { return s->tasks.size(); }
 
 // DumpInternals summary, task_dispatcher.cc:540-547,581-584,603-612.
-size_t yd_dump_internals_json(yd_sched* s, char* buf, size_t cap) {
-  std::uint64_t capacity = 0, unavailable = 0, running = 0;
-  for (auto&& e : s->servants) {
-    running += e->running_tasks;
-    capacity += e->max_tasks;
-    unavailable += e->max_tasks - s->CapacityAvailable(*e);
-  }
-  std::uint64_t avail = static_cast<std::uint64_t>(
-      std::max<std::int64_t>(static_cast<std::int64_t>(capacity - running - unavailable), 0));
-  char tmp[512];
-  int len = std::snprintf(tmp, sizeof(tmp),
-                          "{\"servants_up\":%llu,\"running_tasks\":%llu,\"capacity\":%llu,"
-                          "\"capacity_available\":%llu,\"capacity_unavailable\":%llu}",
-                          (unsigned long long)s->servants.size(), (unsigned long long)running,
-                          (unsigned long long)capacity, (unsigned long long)avail,
-                          (unsigned long long)unavailable);
-  if (buf && cap) std::snprintf(buf, cap, "%s", tmp);
-  return static_cast<size_t>(len);
-}
-
 int yd_last_solve_stats(yd_sched* s, yd_solve_stats* out) {
   if (!s->have_stats) return 0;
   *out = s->stats;
@@ -474,6 +454,7 @@ void yd_free_host(void* p) { std::free(p); }
 
 }  // extern "C"
 #include "ydsched_rpc_impl.inc"
+#include "yddump_impl.inc"
 #include "ydservice_impl.inc"
 #include "ydwire_impl.inc"
 

@@ -309,22 +309,54 @@ int yd_get_servant_personality(yd_sched* s, uint32_t idx, yd_servant* out) {
 uint64_t yd_next_task_id(yd_sched* s) { return yd_oracle_access::NextTaskId(*s->d); }
 uint64_t yd_num_tasks(yd_sched* s) { return yd_oracle_access::Tasks(*s->d).size(); }
 
-size_t yd_dump_internals_json(yd_sched* s, char* buf, size_t cap) {
-  auto j = yd_oracle_access::Dump(*s->d);
-  char tmp[512];
-  int len = std::snprintf(
-      tmp, sizeof(tmp),
-      "{\"servants_up\":%llu,\"running_tasks\":%llu,\"capacity\":%llu,"
-      "\"capacity_available\":%llu,\"capacity_unavailable\":%llu}",
-      (unsigned long long)j["servants_up"].asUInt64(),
-      (unsigned long long)j["running_tasks"].asUInt64(),
-      (unsigned long long)j["capacity"].asUInt64(),
-      (unsigned long long)j["capacity_available"].asUInt64(),
-      (unsigned long long)j["capacity_unavailable"].asUInt64());
-  if (buf && cap) {
-    std::snprintf(buf, cap, "%s", tmp);
+// TaskDispatcher::DumpInternals (task_dispatcher.cc:538-614), the reference's own Json::Value written out as text:
+// everything it holds except the wall-clock strings ("discovered_at", "expires_at") and the "tasks" map.
+static void WriteJson(const Json::Value& v, std::string* o) {
+  char num[64];
+  switch (v.kind()) {
+    case Json::Value::kNull: *o += "null"; break;
+    case Json::Value::kBool: *o += v.asInt64() ? "true" : "false"; break;
+    case Json::Value::kInt: std::snprintf(num, sizeof num, "%lld", (long long)v.asInt64()); *o += num; break;
+    case Json::Value::kUInt: std::snprintf(num, sizeof num, "%llu", (unsigned long long)v.asUInt64()); *o += num; break;
+    case Json::Value::kString: {
+      o->push_back('"');
+      for (unsigned char c : v.asString()) {
+        if (c == '"' || c == '\\') { o->push_back('\\'); o->push_back((char)c); }
+        else if (c < 0x20) { std::snprintf(num, sizeof num, "\\u%04x", c); *o += num; }
+        else o->push_back((char)c);
+      }
+      o->push_back('"');
+      break;
+    }
+    case Json::Value::kArray: {
+      o->push_back('[');
+      bool first = true;
+      for (auto&& e : v.array()) { if (!first) o->push_back(','); first = false; WriteJson(e, o); }
+      o->push_back(']');
+      break;
+    }
+    case Json::Value::kObject: {
+      o->push_back('{');
+      bool first = true;
+      for (auto&& [k, e] : v.object()) {
+        if (k == "discovered_at" || k == "expires_at" || k == "tasks") continue;
+        if (!first) o->push_back(',');
+        first = false;
+        o->push_back('"'); *o += k; *o += "\":";
+        WriteJson(e, o);
+      }
+      o->push_back('}');
+      break;
+    }
   }
-  return static_cast<size_t>(len);
+}
+
+size_t yd_dump_internals_json(yd_sched* s, char* buf, size_t cap) {
+  Json::Value j = yd_oracle_access::Dump(*s->d);
+  std::string o;
+  WriteJson(j, &o);
+  if (buf && cap) std::snprintf(buf, cap, "%s", o.c_str());
+  return o.size();
 }
 
 int yd_last_solve_stats(yd_sched* s, yd_solve_stats* out) {

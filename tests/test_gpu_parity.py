@@ -22,7 +22,7 @@ def test_reference_golden_cases_on_cuda(make_dispatcher, case):
     case(make_dispatcher("cuda"))
 
 
-SOLVERS = {1: "rowscan", 2: "stream"}
+SOLVERS = {0: "auto", 1: "rowscan", 2: "stream"}  # auto = slot streams + the one-launch path for batches of <= 8
 
 
 def _parity(make_dispatcher, name_or_builder, kinds=("port",), solver=0):
@@ -39,7 +39,7 @@ def _parity(make_dispatcher, name_or_builder, kinds=("port",), solver=0):
     return traces["cuda"]
 
 
-@pytest.mark.parametrize("solver", [1, 2], ids=SOLVERS.get)
+@pytest.mark.parametrize("solver", [0, 1, 2], ids=SOLVERS.get)
 @pytest.mark.parametrize("seed", range(150))
 def test_fuzz_cuda_equals_oracle(make_dispatcher, seed, solver):
     kinds = ("port", "ref") if REF_LIB.exists() and seed % 3 == 0 else ("port",)
@@ -200,6 +200,48 @@ def test_heartbeat_reporting_ten_thousand_tasks(make_dispatcher):
         st = d.servant_state()
         out.append((unknown, st["running_tasks"].tolist(), d.num_tasks()))
     assert out[0] == out[1]
+
+
+@pytest.mark.parametrize("seed", [3, 11])
+def test_dump_internals_on_cuda(make_dispatcher, seed):
+    """DumpInternals (task_dispatcher.cc:538-614): per-servant rows and summary of the CUDA backend against the
+    reference's own function after the same stream."""
+    dumps = []
+    for kind in ("cuda", "ref" if REF_LIB.exists() else "port"):
+        d = make_dispatcher(kind)
+        S.Replayer(d).run(S.fuzz_stream(d, seed, n_servants=12 + seed))
+        dumps.append(d.dump_internals())
+    assert dumps[0] == dumps[1]
+
+
+def test_thirty_thousand_servants_behind_one_digest(make_dispatcher):
+    """One compiler digest on 30 000 servants is ONE component: the merge solver has no per-component size limit and
+    the sequential solver keeps running_tasks of such a component in HBM instead of shared memory (no abort).  Every
+    requestor is a servant (self rule live); then the same with two servants behind one requestor IP, which forces the
+    sequential solver."""
+    from yadcc_b200 import PRIORITY_DEDICATED, PRIORITY_USER, Servant
+
+    dg = "ef" * 32
+    for twin in (False, True):
+        results = []
+        for kind in ("cuda", "port"):
+            d = make_dispatcher(kind)
+            r = np.random.default_rng(5)
+            svs = [Servant(f"10.{i >> 16}.{(i >> 8) & 255}.{i & 255}:8335", None, [dg], 8, int(r.choice([8, 16, 32])), int(r.integers(0, 4)),
+                           0, 64 << 30, int(r.integers(1, 5)), PRIORITY_DEDICATED if i % 9 == 0 else PRIORITY_USER) for i in range(30_000)]
+            if twin:
+                svs.append(Servant("10.0.0.7:9000", None, [dg], 8, 16, 0, 0, 64 << 30, 3, PRIORITY_USER))
+            d.keep_servants_alive(svs, 10.0, now=0.0)
+            n = 40_000
+            who = r.integers(0, 30_000, n)
+            ips = [f"10.{j >> 16}.{(j >> 8) & 255}.{j & 255}" for j in who]
+            if twin:
+                ips[::50] = ["10.0.0.7"] * len(ips[::50])
+            reqs = d.make_requests(n, dg, ips, 8)
+            results.append(d.wait_for_starting_new_tasks(reqs, 0.5).copy())
+            results.append(d.servant_state()["running_tasks"].copy())
+        assert (results[0] == results[2]).all()
+        assert (results[1] == results[3]).all()
 
 
 def test_cfg1_vectors(make_dispatcher):

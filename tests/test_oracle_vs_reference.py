@@ -63,3 +63,19 @@ def test_batched_heartbeats_equal_single_calls(make_dispatcher, kind, seed):
         traces.append(S.Replayer(d, batch_heartbeats=batched).run(S.fuzz_stream(d, seed, n_servants=8 + seed % 30)))
         d.close()
     assert S.traces_equal(*traces), S.first_mismatch(*traces)
+
+
+@pytest.mark.parametrize("seed", [0, 7, 13, 21])
+def test_dump_internals_port_equals_reference(make_dispatcher, seed):
+    """TaskDispatcher::DumpInternals (task_dispatcher.cc:538-614): the per-servant rows and the five summary fields
+    the reference's own function produces (written out by the harness from its Json::Value) against the
+    restatement's -- after a stream that leaves servants in every state (full, low memory, not accepting, expired)."""
+    dumps = []
+    for kind in ("ref", "port"):
+        d = make_dispatcher(kind)
+        assert d.dump_internals() == {"servants_up": 0, "running_tasks": 0, "capacity": 0, "capacity_available": 0,
+                                      "capacity_unavailable": 0}
+        S.Replayer(d).run(S.fuzz_stream(d, seed, n_servants=10 + seed))
+        dumps.append(d.dump_internals())
+    assert dumps[0] == dumps[1]
+    assert len(dumps[0].get("servants", [])) == dumps[0]["servants_up"]

@@ -32,6 +32,7 @@
 #include "bloom.cuh"
 #include "running_index.cuh"
 #include "tasks.cuh"
+#include "tiny.cuh"
 
 namespace {
 
@@ -186,7 +187,7 @@ struct yd_sched {
   uint32_t merge_chunk = 512, merge_rounds = 8, merge_max_chunks = 0, merge_grid = 0, merge_grid_kcap = 0;
   uint32_t stream_debug = 0;   // YDSCHED_STREAM_DEBUG, read once at yd_create
   uint32_t force_stream = 0;   // yd_config.reserved bit 1 / YDSCHED_FORCE_STREAM: no merge solver for self-requests
-  bool dump_env = false, debug_env = false;
+  bool dump_env = false, debug_env = false, tiny_ok = true;
   bool stream_attr_set = false;
   size_t res_words = 0;  // u32 words of res[] in d_res (the class-table keys follow)
   size_t staged_n = 0;   // requests placed in d_reqs by yd_stage_requests
@@ -519,6 +520,7 @@ yd_sched* yd_create(const yd_config* cfg) {
   if (const char* e = getenv("YDSCHED_STREAM_DEBUG")) s->stream_debug = (uint32_t)atoi(e);
   if (const char* e = getenv("YDSCHED_MERGE_CHUNK")) s->merge_chunk = std::max(32u, (uint32_t)atoi(e) & ~31u);
   if (const char* e = getenv("YDSCHED_MERGE_ROUNDS")) s->merge_rounds = std::max(2u, (uint32_t)atoi(e));
+  s->tiny_ok = !(cfg->reserved & 4u) && !getenv("YDSCHED_NO_TINY");
   s->dump_env = getenv("YDSCHED_DUMP") != nullptr;
   s->debug_env = getenv("YDSCHED_DEBUG") != nullptr;
   YD_CUDA_CHECK(cudaStreamCreateWithFlags(&s->st, cudaStreamNonBlocking));
@@ -1150,6 +1152,42 @@ void yd_wait_for_starting_new_tasks(yd_sched* s, int64_t now_ns, const yd_task_r
   s->SyncTopology();
   s->EnsureRing(N);
 
+  // ---- a handful of requests: one launch, arguments in, pinned memory out (tiny.cuh) ------------------------------
+  if (reqs && N <= yd::kTinyMax && s->solver_pref == 0 && s->tiny_ok && S && s->n_comps) {
+    s->h_small.ensure(256);
+    yd::TinyArgs ta{};
+    memcpy(ta.reqs, reqs, size_t(N) * sizeof(yd_task_req));
+    ta.n = N;
+    ta.now_ns = now_ns;
+    ta.t = MakeTopo(s);
+    ta.sv = s->arrays();
+    ta.ring = s->ring();
+    ta.out = s->h_small.as<yd_grant>();
+    ta.granted_out = reinterpret_cast<unsigned long long*>(s->h_small.as<char>() + yd::kTinyMax * sizeof(yd_grant));
+    ta.counters = s->d_counters.as<Counters>();
+    YD_CUDA_CHECK(cudaEventRecord(s->ev[0], st));
+    yd::k_solve_tiny<<<1, 1024, 0, st>>>(ta);
+    YD_CUDA_CHECK(cudaGetLastError());
+    YD_CUDA_CHECK(cudaEventRecord(s->ev[5], st));
+    YD_CUDA_CHECK(cudaStreamSynchronize(st));
+    memcpy(out, ta.out, size_t(N) * sizeof(yd_grant));
+    const unsigned long long granted = *ta.granted_out;
+    s->next_id += granted;
+    s->staged_n = 0;
+    float ms = 0;
+    cudaEventElapsedTime(&ms, s->ev[0], s->ev[5]);
+    s->stats = yd_solve_stats{};
+    s->stats.total_ms = s->stats.solve_ms = ms;
+    s->stats.decisions = N;
+    s->stats.granted = granted;
+    s->stats.kernel_launches = 1;
+    s->stats.solver = 3;
+    s->stats.h2d_bytes = 0;  // the requests are kernel arguments
+    s->stats.d2h_bytes = size_t(N) * sizeof(yd_grant) + 8;  // written by the kernel into pinned host memory
+    s->have_stats = true;
+    return;
+  }
+
   // Size classes: grids, scratch arrays and memsets are dimensioned for the next power of
   // two; kernels read the exact n from DynParams.
   const uint32_t Nb = (uint32_t)NextPow2(N, 1024);
@@ -1585,28 +1623,6 @@ uint64_t yd_num_tasks(yd_sched* s) {
   return s->h_counters.as<Counters>()->alive;
 }
 
-// DumpInternals summary, cc:540-547,581-584,603-612.
-size_t yd_dump_internals_json(yd_sched* s, char* buf, size_t cap) {
-  const size_t S = s->sv.size();
-  std::vector<yd_servant_state> st(S);
-  yd_get_servant_state(s, st.data(), S);
-  uint64_t capacity = 0, unavailable = 0, running = 0;
-  for (size_t i = 0; i != S; ++i) {
-    running += st[i].running_tasks;
-    capacity += s->sv[i].max_tasks;
-    unavailable += s->sv[i].max_tasks - st[i].capacity_available;
-  }
-  int64_t av = (int64_t)(capacity - running - unavailable);
-  char tmp[512];
-  int len = snprintf(tmp, sizeof(tmp),
-                     "{\"servants_up\":%llu,\"running_tasks\":%llu,\"capacity\":%llu,"
-                     "\"capacity_available\":%llu,\"capacity_unavailable\":%llu}",
-                     (unsigned long long)S, (unsigned long long)running, (unsigned long long)capacity,
-                     (unsigned long long)(av > 0 ? av : 0), (unsigned long long)unavailable);
-  if (buf && cap) snprintf(buf, cap, "%s", tmp);
-  return (size_t)len;
-}
-
 int yd_last_solve_stats(yd_sched* s, yd_solve_stats* out) {
   if (!s->have_stats) return 0;
   *out = s->stats;
@@ -1624,6 +1640,7 @@ void yd_free_host(void* p) {
 
 }  // extern "C"
 #include "ydsched_rpc_impl.inc"
+#include "yddump_impl.inc"
 #include "ydservice_impl.inc"
 #include "ydwire_impl.inc"
 

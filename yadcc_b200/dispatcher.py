@@ -87,6 +87,7 @@ class TaskDispatcher:
         solver: int = 0,
         graphs: bool = True,
         merge_self: bool = True,
+        tiny: bool = True,
         id_stride: int = 0,
         id_offset: int = 0,
     ):
@@ -102,7 +103,8 @@ class TaskDispatcher:
             solver=solver,
             # bit 0: do not capture the solve into a CUDA graph (per-phase timing); bit 1 (test switch): components
             # whose requestors are servants go to the sequential solver instead of the merge solver
-            reserved=(0 if graphs else 1) | (0 if merge_self else 2),
+            # bit 2 (test switch): batches of <= 8 requests take the full pipeline instead of the one-launch path
+            reserved=(0 if graphs else 1) | (0 if merge_self else 2) | (0 if tiny else 4),
             id_stride=id_stride,
             id_offset=id_offset,
         )
@@ -451,7 +453,8 @@ class TaskDispatcher:
         return int(self._lib.yd_num_tasks(self._h))
 
     def dump_internals(self) -> dict:
-        buf = C.create_string_buffer(4096)
+        n = self._lib.yd_dump_internals_json(self._h, None, 0)
+        buf = C.create_string_buffer(n + 1)
         self._lib.yd_dump_internals_json(self._h, buf, len(buf))
         return json.loads(buf.value.decode())
 
