@@ -397,6 +397,7 @@ void yd_sched::SyncTopology() {
     uint32_t c = sv_comp[i];
     if (c == kNone) continue;
     uint32_t l = sv_local[i], T = nwarps[c] * 32;
+    if (l / yd::kK >= T) continue;  // component beyond the row-scan solver's 8192 servants: it never reads these masks
     for (uint32_t e : sv[i].envs) {
       envmask[mask_off[c] + size_t(env_local[e]) * T + l / yd::kK] |= uint8_t(1u << (l % yd::kK));
     }

@@ -290,10 +290,12 @@ class TaskDispatcher:
         """KeepServantAlive for a whole tick's heartbeats in one call (yd_keep_servants_alive)."""
         n = len(servants)
         keep: list = []
-        arr = (_abi.yd_servant * max(n, 1))(*[self._servant_struct(sv, keep) for sv in servants])
+        structs = [self._servant_struct(sv, keep) for sv in servants]  # (they own the byte strings the array points to)
+        arr = (_abi.yd_servant * max(n, 1))(*structs)
         exp = [expires_in] * n if isinstance(expires_in, (int, float)) else list(expires_in)
         ex = (C.c_int64 * max(n, 1))(*[_ns(e) for e in exp])
         self._lib.yd_keep_servants_alive(self._h, _ns(now), arr, ex, n)
+        del structs, keep
 
     def notify_servants_running_tasks(self, batch: Sequence[tuple[str, Sequence[RunningTask]]]) -> list[list[int]]:
         """NotifyServantRunningTasks for many servants in one call: [(location, tasks)] -> unknown ids per item."""
