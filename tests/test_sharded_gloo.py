@@ -134,3 +134,65 @@ def test_two_ranks_equal_one_scheduler(tmp_path, port_lib, id_mode):
                 one.free_tasks(task_id[status == 2][::3])
             else:  # the same requests' grants in the single scheduler's numbering
                 one.free_tasks(g["task_id"][mine][status == 2][::3])
+
+
+def _range_rank_main(rank, world, port, out_dir):
+    import torch.distributed as dist
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from yadcc_b200 import TaskDispatcher
+    from yadcc_b200 import streams as S
+    from yadcc_b200.sharded import RangeShardedDispatcher
+
+    w = S.config3(6000, 120, 6)
+    d = TaskDispatcher(str(PORT_LIB))
+    w.register(d, now=0.0, expires_in=100.0)  # replicated servant table: every rank hears every heartbeat
+    full = w.build_requests(d)
+    cut = [0, 1700, len(full)]  # uneven contiguous ranges of ONE FIFO queue
+    mine = np.ascontiguousarray(full[cut[rank]:cut[rank + 1]])
+    sd = RangeShardedDispatcher(d, rank, world)
+    out = []
+    for rnd in range(2):
+        g = sd.wait_for_starting_new_tasks(mine, 0.5 + rnd)
+        out.append(g.copy())
+        ok = g["status"] == 2
+        sd.free_tasks(g["task_id"][ok][rank::3])  # collective: every rank names some of ITS grants
+        d.on_expiration_timer(now=0.7 + rnd)
+    st = d.servant_state()
+    np.save(Path(out_dir) / f"range{rank}.npy", np.asarray([out[0], out[1], st], dtype=object), allow_pickle=True)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_range_sharded_queue_on_two_gloo_ranks_equals_one_scheduler(tmp_path, port_lib):
+    """The range-sharded scheduler's contract (include/ydshard.h) on CPU: two gloo ranks, each with its contiguous
+    range of one FIFO queue and a replica of the servant table, make together exactly the decisions -- statuses,
+    servants, FIFO task ids, per-servant bookkeeping -- of one TaskDispatcher fed the whole queue, across a
+    collective FreeTask.  (On B200s the exchange is the C++/NCCL path; tests/multi_gpu_check.py checks that one.)"""
+    import torch.multiprocessing as mp
+    from yadcc_b200 import TaskDispatcher
+    from yadcc_b200 import streams as S
+
+    world = 2
+    mp.spawn(_range_rank_main, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    w = S.config3(6000, 120, 6)
+    one = TaskDispatcher(port_lib)
+    w.register(one, now=0.0, expires_in=100.0)
+    full = w.build_requests(one)
+    cut = [0, 1700, len(full)]
+    ranks = [np.load(tmp_path / f"range{r}.npy", allow_pickle=True) for r in range(world)]
+    for rnd in range(2):
+        g = one.wait_for_starting_new_tasks(full, 0.5 + rnd)
+        for r in range(world):
+            part = ranks[r][rnd]
+            ref = g[cut[r]:cut[r + 1]]
+            for k in ("status", "servant_index", "task_id"):
+                assert (np.asarray(part[k]) == ref[k]).all(), (rnd, r, k)
+            ok = ref["status"] == 2
+            one.free_tasks(ref["task_id"][ok][r::3])
+        one.on_expiration_timer(now=0.7 + rnd)
+    st = one.servant_state()
+    for r in range(world):
+        assert (np.asarray(ranks[r][2]["running_tasks"]) == st["running_tasks"]).all()

@@ -184,9 +184,14 @@ class RangeShardedDispatcher:
         from . import _abi
 
         self.local, self.rank, self.world = local, rank, world
+        self.group = group
         lib = local._lib
-        if not hasattr(lib, "yd_shard_init"):
-            raise RuntimeError(f"{lib._yd_path} has no range-sharded path (CUDA library only)")
+        # Libraries without the NCCL path (the CPU oracles in the gloo tests): the same contract -- one queue cut into
+        # per-rank ranges, replicated servant state, FIFO task ids, collective FreeTask -- with the exchange restated
+        # over torch.distributed: the ranges are all-gathered and every rank decides the whole queue on its replica.
+        self.native = hasattr(lib, "yd_shard_init")
+        if not self.native:
+            return
         buf = (C.c_uint8 * _abi.SHARD_UNIQUE_ID_BYTES)()
         if rank == 0 and lib.yd_shard_unique_id(buf) != 0:
             raise RuntimeError("yd_shard_unique_id failed (libnccl.so.2 not loadable?)")
@@ -204,6 +209,14 @@ class RangeShardedDispatcher:
         from .dispatcher import _ns
 
         lib, h = self.local._lib, self.local._h
+        if not self.native:
+            import torch.distributed as dist
+
+            parts: list = [None] * self.world
+            dist.all_gather_object(parts, np.ascontiguousarray(reqs_local), group=self.group)
+            lo = sum(len(p) for p in parts[: self.rank])
+            g = self.local.wait_for_starting_new_tasks(np.concatenate(parts), now)
+            return g[lo:lo + len(reqs_local)].copy()
         if isinstance(reqs_local, (int, np.integer)):
             n, ptr = int(reqs_local), None
         else:
@@ -221,6 +234,13 @@ class RangeShardedDispatcher:
     def free_tasks(self, ids) -> None:
         """Collective FreeTask: every rank passes the ids it wants released (its own grants, typically)."""
         ids = np.ascontiguousarray(np.asarray(ids, dtype=np.uint64))
+        if not self.native:
+            import torch.distributed as dist
+
+            parts: list = [None] * self.world
+            dist.all_gather_object(parts, ids, group=self.group)
+            self.local.free_tasks(np.concatenate(parts))  # every replica holds every lease
+            return
         rc = self.local._lib.yd_shard_free_tasks(self.local._h, ids.ctypes.data if len(ids) else None, len(ids))
         if rc != 0:
             raise RuntimeError(f"yd_shard_free_tasks failed: {rc}")
@@ -230,6 +250,8 @@ class RangeShardedDispatcher:
 
         from . import _abi
 
+        if not self.native:
+            return None
         st = _abi.yd_shard_stats()
         if not self.local._lib.yd_shard_last_stats(self.local._h, C.byref(st)):
             return None
@@ -238,4 +260,5 @@ class RangeShardedDispatcher:
                 "merge_rounds": st.merge_rounds, "kernel_launches": st.kernel_launches}
 
     def close(self) -> None:
-        self.local._lib.yd_shard_finalize(self.local._h)
+        if self.native:
+            self.local._lib.yd_shard_finalize(self.local._h)
