@@ -54,7 +54,7 @@ os.environ["NCCL_DEBUG"] = os.environ.get("YD_NCCL_DEBUG", "WARN")  # (NCCL's ve
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
-from yadcc_b200 import STATUS_GRANTED, TaskDispatcher  # noqa: E402
+from yadcc_b200 import STATUS_GRANTED, TaskDispatcher, pack_requests, unpack_grants  # noqa: E402
 from yadcc_b200 import streams as S  # noqa: E402
 
 METRIC = "task_assignment_decisions_per_sec"
@@ -260,17 +260,24 @@ def measure_workload(name: str, dev_index: int, steps: int, warmup: int, solver:
     reqs = d.alloc_requests(n)  # pinned host memory
     out = d.alloc_grants(n)
     reqs[...] = src
+    reqs16 = d.alloc_requests16(n)  # the packed interface's buffers (16 B up, 8 B down), pinned too
+    out8 = d.alloc_grants8(n)
+    pack_requests(src, reqs16)
+    use_packed = stages is None  # (cfg4's queue is filtered on the way: it goes through the plain call)
 
-    def one_pass(queue, now, staged):
-        """(grants, decisions offered to the solver)"""
+    def one_pass(queue, now, mode):
+        """(grants, decisions offered to the solver); mode: "staged" | "plain" | "packed" """
         if stages is not None:
             queue = stages.filter(queue)
             buf = reqs[: len(queue)]
             buf[...] = queue
             queue = buf
-        if staged:
+        if mode == "staged":
             d.stage_requests(queue)
             return d.wait_for_staged_tasks(len(queue), now, out=out), len(queue)
+        if mode == "packed":
+            g8, ids = d.wait_for_starting_new_tasks_packed(reqs16[: len(queue)], now, out8=out8, unpack=False)
+            return (g8, ids), len(queue)
         return d.wait_for_starting_new_tasks(queue, now, out=out), len(queue)
 
     # ---- parity in this run: the reference on the head of the same queue -------------------------------
@@ -279,17 +286,23 @@ def measure_workload(name: str, dev_index: int, steps: int, warmup: int, solver:
         n_s = min(n, CPU_SAMPLE[name])
         kind, g_cpu, cpu_s, _ = cpu_reference_sample(name, n_s)
         head = src[:n_s].copy()
-        g_gpu, _ = one_pass(head, 1.5, False)
+        g_gpu, _ = one_pass(head, 1.5, "plain")
         parity = grants_equal(g_gpu.copy(), g_cpu)
         d.free_tasks(g_gpu["task_id"][g_gpu["status"] == STATUS_GRANTED].copy())
         d.on_expiration_timer(now=1.6)
+        if use_packed:  # the same head through the packed interface (the call `e2e` is timed on)
+            (g8, ids), _ = one_pass(head, 1.7, "packed")
+            g_gpu = unpack_grants(g8.copy(), ids)
+            parity = parity and grants_equal(g_gpu, g_cpu)
+            d.free_tasks(g_gpu["task_id"][g_gpu["status"] == STATUS_GRANTED].copy())
+            d.on_expiration_timer(now=1.8)
         cpu = {"value": n_s / cpu_s, "unit": UNIT, "cores": 1, "kind": kind,
                "sample": f"the first {n_s} of the queue's {n} requests, once ({cpu_s:.2f} s), single thread; the reference "
                          f"serialises on allocation_lock_ (host has {os.cpu_count()} cores)"}
         reqs[...] = src
 
-    dev_ms, e2e_ms, launches, n_solves = [], [], 0, 0
-    granted = h2d = d2h = solver_used = offered = 0
+    dev_ms, e2e_ms, e2e24_ms, launches, n_solves = [], [], [], 0, 0
+    granted = h2d = d2h = h2d24 = d2h24 = solver_used = offered = 0
     prev_ids = None
     t_wall0 = time.perf_counter()
     for it in range(warmup + steps):
@@ -306,9 +319,11 @@ def measure_workload(name: str, dev_index: int, steps: int, warmup: int, solver:
         torch.cuda.synchronize()
         # -- timed (e2e): HOST buffers --------------------------------------------------------------
         t0 = time.perf_counter()
-        g, offered = one_pass(src if stages is not None else reqs, now, False)
+        g, offered = one_pass(src if stages is not None else reqs, now, "packed" if use_packed else "plain")
         t1 = time.perf_counter()
         st = d.last_solve_stats()
+        if use_packed:
+            g = unpack_grants(g[0], g[1])  # (untimed: the caller's id arithmetic, done here for the FreeTask below)
         ok = g["status"] == STATUS_GRANTED
         prev_ids = g["task_id"][ok].copy()
         granted = int(ok.sum())
@@ -318,13 +333,29 @@ def measure_workload(name: str, dev_index: int, steps: int, warmup: int, solver:
             n_solves += 1
             h2d, d2h = st["h2d_bytes"], st["d2h_bytes"]
             solver_used = st["solver"]
+        if use_packed:
+            # -- timed (e2e, 24-byte requests / 16-byte grants): the plain call, for comparison -----------------
+            d.free_tasks(prev_ids)
+            d.on_expiration_timer(now=now)
+            flush.fill_((it + 7) & 0xFF)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            g, _ = one_pass(reqs, now, "plain")
+            t1 = time.perf_counter()
+            st = d.last_solve_stats()
+            ok = g["status"] == STATUS_GRANTED
+            prev_ids = g["task_id"][ok].copy()
+            assert int(ok.sum()) == granted
+            if it >= warmup:
+                e2e24_ms.append(1e3 * (t1 - t0))
+                h2d24, d2h24 = st["h2d_bytes"], st["d2h_bytes"]
         # -- timed (value): the queue already resident in HBM ---------------------------------------------
         d.free_tasks(prev_ids)
         d.on_expiration_timer(now=now)
         flush.fill_(~it & 0xFF)
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        g, _ = one_pass(src if stages is not None else reqs, now, True)
+        g, _ = one_pass(src if stages is not None else reqs, now, "staged")
         t1 = time.perf_counter()
         st = d.last_solve_stats()
         ok = g["status"] == STATUS_GRANTED
@@ -353,11 +384,18 @@ def measure_workload(name: str, dev_index: int, steps: int, warmup: int, solver:
         "decisions_per_step": decisions, "granted_per_step": granted, "solver_decisions_per_step": offered,
         "value": decisions / (ms_step / 1e3), "unit": UNIT, "ms_per_step": ms_step, "steps": K,
         "e2e": {"value": decisions / (e2e_step / 1e3), "unit": UNIT, "ms_per_step": e2e_step,
-                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                "call": "yd_wait_for_starting_new_tasks_packed (16-byte requests, 8-byte grants)" if use_packed
+                        else "yd_bloom_possibly_contains + yd_running_index_find + yd_wait_for_starting_new_tasks"},
         "gpu_launches_per_step": launches // max(1, n_solves),
         "solver": {1: "row-scan", 2: "slot-stream"}.get(solver_used, str(solver_used)),
         "parity_in_run": parity, "cpu_baseline": cpu,
     }
+    if e2e24_ms:
+        e24 = sum(e2e24_ms) / len(e2e24_ms)
+        rec["e2e_unpacked"] = {"value": decisions / (e24 / 1e3), "unit": UNIT, "ms_per_step": e24,
+                               "h2d_bytes_per_step": int(h2d24), "d2h_bytes_per_step": int(d2h24),
+                               "call": "yd_wait_for_starting_new_tasks (24-byte requests, 16-byte grants)"}
     extra = {"e2e_ms": e2e_ms, "dev_ms": dev_ms, "launches": launches, "n_solves": n_solves, "wall": wall,
              "S": S_count, "n": n, "w": w}
     return rec, extra
@@ -479,6 +517,7 @@ def run_ours(args):
                    "l2": "flushed between steps (256 MiB write)", "solver": rec["solver"],
                    "between_steps_untimed": "FreeTask of the previous grants + OnExpirationTimer tick"},
         "e2e": rec["e2e"],
+        "e2e_unpacked": rec.get("e2e_unpacked"),
         "gpu_launches": int(ex["launches"]),
         "parity_in_run": rec["parity_in_run"],
         "roofline": {

@@ -503,6 +503,19 @@ extern "C" int yd_running_index_entry(yd_sched* s, uint32_t i, yd_running_task* 
 #include "ydservice_impl.inc"
 #include "ydwire_impl.inc"
 
+// ---- packed interface (yd_wait_for_starting_new_tasks_packed): defined as unpack -> the plain call -> pack --------
+extern "C" void yd_wait_for_starting_new_tasks_packed(yd_sched* s, int64_t now_ns, const yd_task_req16* reqs, size_t n,
+                                                      yd_grant8* out, yd_packed_ids* ids) {
+  yd_packed_ids local{yd_next_task_id(s), 1};
+  if (ids) *ids = local;
+  if (n == 0) return;
+  std::vector<yd_task_req> r(n);
+  std::vector<yd_grant> g(n);
+  for (size_t i = 0; i != n; ++i) r[i] = yd_unpack_req(reqs[i]);
+  yd_wait_for_starting_new_tasks(s, now_ns, r.data(), n, g.data());
+  for (size_t i = 0; i != n; ++i) out[i] = yd_pack_grant(g[i], local);
+}
+
 // ---- staged queue (yd_stage_requests / yd_wait_for_staged_tasks): host-side copy ----------
 namespace { std::unordered_map<yd_sched*, std::vector<yd_task_req>> g_staged; }
 extern "C" void yd_stage_requests(yd_sched* s, const yd_task_req* reqs, size_t n) {

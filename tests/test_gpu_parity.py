@@ -47,6 +47,67 @@ def test_fuzz_cuda_equals_oracle(make_dispatcher, seed, solver):
             solver)
 
 
+@pytest.mark.parametrize("seed", range(60))
+def test_fuzz_packed_interface(make_dispatcher, seed):
+    """yd_wait_for_starting_new_tasks_packed (16-byte requests up, 8-byte grants down, unpacked / packed by the
+    fused kernel itself or by the conversion kernels around the pipeline) against the checkers' plain call."""
+    traces = {}
+    for kind in ("cuda", "port"):
+        d = make_dispatcher(kind)
+        st = S.fuzz_stream(d, seed, n_servants=8 + seed % 30, wide=(seed % 5 == 0))
+        traces[kind] = S.Replayer(d, pinned=(kind == "cuda"), packed=(kind == "cuda")).run(st)
+        d.close()
+    assert S.traces_equal(traces["cuda"], traces["port"]), S.first_mismatch(traces["cuda"], traces["port"])
+
+
+@pytest.mark.parametrize("fused", [True, False], ids=["fused", "pipeline"])
+@pytest.mark.parametrize("packed", [True, False], ids=["packed", "plain"])
+@pytest.mark.parametrize("name", ["cfg2-mod-small", "cfg2-random-small", "cfg3-small", "cfg-self-small", "cfg2-mod",
+                                  "cfg2-random", "cfg-self"])
+def test_fused_front_and_packed_interface_match_reference_digest(make_dispatcher, name, packed, fused):
+    """The one-launch solve (fused.cuh; solo for cfg2-mod, fused front + coupled solvers for the others), with and
+    without the packed interface, and the kernel-by-kernel pipeline behind the same interfaces: reference digests."""
+    d = make_dispatcher("cuda", fused=fused)
+    tr = S.Replayer(d, pinned=True, packed=packed).run(S.named_stream(name, d))
+    golden = json.loads((GOLDEN / "digests.json").read_text())["streams"][name]
+    assert S.trace_digest(tr) == golden["sha256"]
+
+
+def _flip_stream(d, seed=7, n_servants=96, n_digests=4):
+    """Batches that alternate between 'data-parallel components only' (the fused kernel finishes the solve alone) and
+    'a requestor is a servant of its component' (it must stand down, flag 4, and the general sequence runs), with
+    frees in between so that slots come back."""
+    rng = np.random.default_rng(seed)
+    w = S.config2(4000, n_servants, n_digests, seed=seed, variant="mod", max_tasks=24, nproc=64)
+    ev = [("hb", 0.0, sv, 100.0) for sv in w.servants]
+    env = np.asarray([d.intern_env(x) for x in w.digests], dtype=np.uint32)
+    outside = np.asarray([d.intern_ip(f"172.16.0.{i}") for i in range(200)], dtype=np.uint32)
+    inside = np.asarray([d.intern_ip(S.servant_ip(i)) for i in range(n_servants)], dtype=np.uint32)
+    now = 0.001
+    for k, kind in enumerate(["dp", "dp", "self", "dp", "dp", "self", "self", "dp", "tiny", "dp"]):
+        n = int(rng.integers(300, 900)) if kind != "tiny" else 5
+        ips = outside[rng.integers(0, len(outside), n)]
+        if kind == "self":
+            ips = np.where(rng.random(n) < 0.3, inside[rng.integers(0, n_servants, n)], ips)
+        ev.append(("wait", now, S._requests(d, env[rng.integers(0, n_digests, n)], ips, 8,
+                                            expires_in_s=float(rng.choice([0.5, 15.0])), prefetch=rng.random(n) < 0.2)))
+        ev.append(("state",))
+        ev.append(("free_frac", seed + k, 0.6))
+        now += 0.01
+    return S.Stream("flip", ev)
+
+
+@pytest.mark.parametrize("packed", [True, False], ids=["packed", "plain"])
+@pytest.mark.parametrize("graphs", [True, False], ids=["graph", "eager"])
+def test_solo_kernel_stands_down_for_coupled_batches(make_dispatcher, packed, graphs):
+    traces = {}
+    for kind in ("cuda", "port"):
+        d = make_dispatcher(kind, graphs=graphs) if kind == "cuda" else make_dispatcher(kind)
+        traces[kind] = S.Replayer(d, pinned=(kind == "cuda"), packed=(packed and kind == "cuda")).run(_flip_stream(d))
+        d.close()
+    assert S.traces_equal(traces["cuda"], traces["port"]), S.first_mismatch(traces["cuda"], traces["port"])
+
+
 @pytest.mark.parametrize("solver", [1, 2], ids=SOLVERS.get)
 @pytest.mark.parametrize("seed", range(1000, 1012))
 def test_fuzz_large_components(make_dispatcher, seed, solver):

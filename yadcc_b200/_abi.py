@@ -54,7 +54,13 @@ RPC_WAIT_DTYPE = np.dtype(
 RUNNING_HIT_DTYPE = np.dtype([("servant_task_id", "<u8"), ("snapshot_index", "<u4"), ("found", "<u4")])
 RPC_RESULT_DTYPE = np.dtype([("status", "<u4"), ("n_grants", "<u4"), ("first_grant", "<u4"), ("reserved", "<u4")])
 RPC_OK, RPC_NO_QUOTA_AVAILABLE, RPC_INVALID_ARGUMENT, RPC_ENVIRONMENT_NOT_AVAILABLE = 0, 1001, 1004, 1006
+# struct yd_task_req16 (16 B) / yd_grant8 (8 B) / yd_packed_ids: the packed interface
+REQ16_DTYPE = np.dtype([("env_id", "<u4"), ("min_version", "<u4"), ("requestor_ip", "<u4"), ("lease", "<u4")])
+GRANT8_DTYPE = np.dtype([("servant_index", "<u4"), ("status_ordinal", "<u4")])
+PACKED_IDS_DTYPE = np.dtype([("first_task_id", "<u8"), ("stride", "<u8")])
+LEASE_PREFETCH = 0x80000000
 assert REQ_DTYPE.itemsize == 24 and GRANT_DTYPE.itemsize == 16 and RPC_WAIT_DTYPE.itemsize == 32
+assert REQ16_DTYPE.itemsize == 16 and GRANT8_DTYPE.itemsize == 8
 
 
 class yd_config(C.Structure):
@@ -187,6 +193,7 @@ PROTOTYPES = [
     ("yd_get_running_tasks", C.c_size_t, [_P, C.POINTER(yd_running_task), C.c_size_t]),
     ("yd_on_expiration_timer", None, [_P, C.c_int64]),
     ("yd_wait_for_starting_new_tasks", None, [_P, C.c_int64, _P, C.c_size_t, _P]),
+    ("yd_wait_for_starting_new_tasks_packed", None, [_P, C.c_int64, _P, C.c_size_t, _P, _P]),
     ("yd_stage_requests", None, [_P, _P, C.c_size_t]),
     ("yd_wait_for_staged_tasks", None, [_P, C.c_int64, C.c_size_t, _P]),
     ("yd_keep_task_alive", None, [_P, C.c_int64, _P, C.c_size_t, C.c_int64, _P]),

@@ -85,15 +85,11 @@ __device__ __forceinline__ bool servant_has_env(const TopoView& t, uint32_t pos,
   return false;
 }
 
-__global__ void __launch_bounds__(256) k_cls_insert(const yd_task_req* __restrict__ reqs,
-                                                    const DynParams* __restrict__ dp, TopoView t, ClassTable ct) {
-  __shared__ unsigned long long s_seen[64];
-  if (threadIdx.x < 64) s_seen[threadIdx.x] = kClsEmpty;
-  __syncthreads();
-  uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
-  if (q >= dp->n) return;
-  const uint2 w0 = __ldg(reinterpret_cast<const uint2*>(reqs + q));
-  const uint32_t env = w0.x, mv = w0.y;
+// One request's contribution: its (digest id, min_version) goes into the class table (deduplicated per block through
+// the 64-entry shared-memory set `s_seen`, which the caller initialises to kClsEmpty), and its component learns whether
+// the requestor's IP belongs to one / several of its servants.
+__device__ __forceinline__ void cls_insert_one(uint32_t env, uint32_t mv, uint32_t ip, const TopoView& t,
+                                               const ClassTable& ct, unsigned long long* s_seen) {
   if (env >= t.n_envs) return;
   const uint32_t comp = t.env_comp[env];
   if (comp == kNone) return;
@@ -123,7 +119,6 @@ __global__ void __launch_bounds__(256) k_cls_insert(const yd_task_req* __restric
     if (!done) atomicExch(&ct.meta[1], 1u);  // table full -> caller falls back to the row-scan solver
   }
   // does the requestor's IP belong to one / several servants of this component?
-  const uint32_t ip = __ldg(reinterpret_cast<const uint2*>(reqs + q) + 1).x;
   if (ip < t.n_ips) {
     uint32_t mine = 0;
     for (uint32_t u = t.ip_off[ip], e = t.ip_off[ip + 1]; u < e && mine < 2; ++u) {
@@ -132,6 +127,18 @@ __global__ void __launch_bounds__(256) k_cls_insert(const yd_task_req* __restric
     const uint32_t bit = mine >= 2 ? 2u : mine;
     if (bit && !(ct.comp_flags[comp] & bit)) atomicOr(&ct.comp_flags[comp], bit);
   }
+}
+
+__global__ void __launch_bounds__(256) k_cls_insert(const yd_task_req* __restrict__ reqs,
+                                                    const DynParams* __restrict__ dp, TopoView t, ClassTable ct) {
+  __shared__ unsigned long long s_seen[64];
+  if (threadIdx.x < 64) s_seen[threadIdx.x] = kClsEmpty;
+  __syncthreads();
+  uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= dp->n) return;
+  const uint2 w0 = __ldg(reinterpret_cast<const uint2*>(reqs + q));
+  const uint32_t ip = __ldg(reinterpret_cast<const uint2*>(reqs + q) + 1).x;
+  cls_insert_one(w0.x, w0.y, ip, t, ct, s_seen);
 }
 
 // The requestor's own servant as the solvers see it: component-local index of the ONE servant of
@@ -192,12 +199,15 @@ __global__ void __launch_bounds__(32) k_cls_merge_tables(const uint32_t* __restr
 // eligible-servant counts, and the solver mode of every component:
 //   comp_mode 1 = data-parallel path (one class, no request from one of its own servants),
 //             0 = sequential slot-stream solver.
-__global__ void __launch_bounds__(1024) k_cls_finalize(TopoView t, ClassTable ct, ServantArrays sv, uint32_t n_comps,
-                                                       uint32_t* __restrict__ comp_mode) {
+// (A block of 1024 threads.  `solo`: the caller can only finish batches made of data-parallel components by itself
+// (fused.cuh); anything else raises flag 4 = "run the general sequence".  meta[4] tells the host either way.)
+__device__ __forceinline__ void cls_finalize_block(const TopoView& t, const ClassTable& ct, uint32_t n_comps,
+                                                   uint32_t* __restrict__ comp_mode, uint32_t solo) {
   __shared__ uint32_t warp_sums[32];
   __shared__ uint32_t carry_s;
+  __shared__ uint32_t s_other;
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid == 0) carry_s = 0;
+  if (tid == 0) { carry_s = 0; s_other = 0; }
   __syncthreads();
   for (uint32_t base = 0; base < kClsTableSize; base += 1024) {
     const uint32_t s = base + tid;
@@ -278,6 +288,7 @@ __global__ void __launch_bounds__(1024) k_cls_finalize(TopoView t, ClassTable ct
     }
     comp_mode[c] = mode;
     ct.comp_midx[c] = midx;
+    if (k >= 1 && mode != 1) s_other = 1;  // requests for a component the data-parallel path cannot decide
   }
   __syncthreads();
   for (uint32_t c = tid; c < ncls; c += 1024) {
@@ -287,15 +298,21 @@ __global__ void __launch_bounds__(1024) k_cls_finalize(TopoView t, ClassTable ct
   if (tid == 0) {
     ct.meta[2] = s_nmerge;
     ct.meta[3] = min(ncls + s_nmerge, ct.cls_bound);  // lists to build: classes + merge pseudo-classes
+    ct.meta[4] = s_other;
+    if (solo && s_other && ct.meta[1] == 0) ct.meta[1] = 4;
   }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(1024) k_cls_finalize(TopoView t, ClassTable ct, ServantArrays sv, uint32_t n_comps,
+                                                       uint32_t* __restrict__ comp_mode) {
+  cls_finalize_block(t, ct, n_comps, comp_mode, 0u);
 }
 
 // Eligible servants per class: max_tasks != 0, digest held, version >= min_version (cc:316-344); 0 => every request
 // of the class is EnvironmentNotFound (cc:105-108).  One block per class, beside the list kernels.
-__global__ void __launch_bounds__(256) k_cls_elig(TopoView t, ClassTable ct, ServantArrays sv) {
+__device__ __forceinline__ void cls_elig_class(uint32_t c, const TopoView& t, const ClassTable& ct, const ServantArrays& sv) {
   __shared__ uint32_t s_sum;
-  const uint32_t c = blockIdx.x;
-  if (c >= min(ct.meta[0], ct.cls_bound)) return;
   if (threadIdx.x == 0) s_sum = 0;
   __syncthreads();
   const uint32_t comp = ct.cls_comp[c], env = ct.cls_env[c], mv = ct.cls_mv[c];
@@ -308,6 +325,13 @@ __global__ void __launch_bounds__(256) k_cls_elig(TopoView t, ClassTable ct, Ser
   if ((threadIdx.x & 31) == 0 && mine) atomicAdd(&s_sum, mine);
   __syncthreads();
   if (threadIdx.x == 0) ct.cls_nelig[c] = s_sum;
+  __syncthreads();  // (s_sum is reused when a block handles several classes)
+}
+
+__global__ void __launch_bounds__(256) k_cls_elig(TopoView t, ClassTable ct, ServantArrays sv) {
+  const uint32_t c = blockIdx.x;
+  if (c >= min(ct.meta[0], ct.cls_bound)) return;
+  cls_elig_class(c, t, ct, sv);
 }
 
 // Per-class sorted slot lists.  A block owns a tile of 1024 SORTED slots, decodes each
@@ -349,19 +373,18 @@ __device__ __forceinline__ bool decode_slot(const SlotDecode& d, const TopoView&
 // barriers per chunk, whatever the number of classes.
 constexpr uint32_t kListChunk = 64;
 
-__global__ void __launch_bounds__(kListTile) k_list_count(const unsigned long long* __restrict__ m_ptr, SlotDecode d,
-                                                          TopoView t, ClassTable ct, ServantArrays sv,
-                                                          uint32_t n_tiles, uint32_t* __restrict__ counts,
-                                                          uint32_t* __restrict__ balg) {
+__device__ __forceinline__ void list_count_tile(uint32_t tile, uint32_t m, const SlotDecode& d, const TopoView& t,
+                                                const ClassTable& ct, const ServantArrays& sv, uint32_t n_tiles,
+                                                uint32_t* __restrict__ counts, uint32_t* __restrict__ balg) {
   __shared__ uint32_t bal[kListChunk][32];
   const uint32_t ncls = min(ct.meta[0], ct.cls_bound);
   const uint32_t nmerge = min(ct.meta[2], ct.cls_bound - ncls);
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   uint32_t pos, r, comp;
-  const bool live = decode_slot(d, t, blockIdx.x * kListTile + tid, (uint32_t)*m_ptr, pos, r, comp);
+  const bool live = decode_slot(d, t, tile * kListTile + tid, m, pos, r, comp);
   const uint32_t ver = live ? (uint32_t)sv.version[pos] : 0u;
   const uint32_t midx = (live && nmerge) ? ct.comp_midx[comp] : kNone;
-  uint32_t* my_row = balg + size_t(blockIdx.x) * ct.cls_bound * 32;
+  uint32_t* my_row = balg + size_t(tile) * ct.cls_bound * 32;
   bool any = false;  // my servant is eligible for some class of its component
   for (uint32_t c0 = 0; c0 < ncls + nmerge; c0 += kListChunk) {
     const uint32_t c1 = min(c0 + kListChunk, ncls + nmerge);
@@ -379,27 +402,33 @@ __global__ void __launch_bounds__(kListTile) k_list_count(const unsigned long lo
     __syncthreads();
     for (uint32_t c = c0 + warp; c < c1; c += 32) {
       const uint32_t cnt = __reduce_add_sync(0xffffffffu, (uint32_t)__popc(bal[c - c0][lane]));
-      if (lane == 0) counts[c * n_tiles + blockIdx.x] = cnt;
+      if (lane == 0) counts[c * n_tiles + tile] = cnt;
     }
     __syncthreads();  // the ballots have been consumed
   }
 }
 
+__global__ void __launch_bounds__(kListTile) k_list_count(const unsigned long long* __restrict__ m_ptr, SlotDecode d,
+                                                          TopoView t, ClassTable ct, ServantArrays sv,
+                                                          uint32_t n_tiles, uint32_t* __restrict__ counts,
+                                                          uint32_t* __restrict__ balg) {
+  list_count_tile(blockIdx.x, (uint32_t)*m_ptr, d, t, ct, sv, n_tiles, counts, balg);
+}
+
 // counts[] has been exclusive-scanned over (class-major, tile-minor).
-__global__ void __launch_bounds__(kListTile) k_list_fill(const unsigned long long* __restrict__ m_ptr, SlotDecode d,
-                                                         TopoView t, ClassTable ct, uint32_t n_tiles,
-                                                         const uint32_t* __restrict__ offs,
-                                                         const uint32_t* __restrict__ balg,
-                                                         uint2* __restrict__ list, uint32_t list_cap) {
+__device__ __forceinline__ void list_fill_tile(uint32_t tile, uint32_t m, const SlotDecode& d, const TopoView& t,
+                                               const ClassTable& ct, uint32_t n_tiles, const uint32_t* __restrict__ offs,
+                                               const uint32_t* __restrict__ balg, uint2* __restrict__ list,
+                                               uint32_t list_cap) {
   __shared__ uint32_t bal[kListChunk][32];
   __shared__ uint16_t pre[kListChunk][32];  // slots of the list in lower warps of this tile
   const uint32_t ncls = min(ct.meta[0], ct.cls_bound);
   const uint32_t nmerge = min(ct.meta[2], ct.cls_bound - ncls);
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   uint32_t pos, r, comp;
-  const bool live = decode_slot(d, t, blockIdx.x * kListTile + tid, (uint32_t)*m_ptr, pos, r, comp);
+  const bool live = decode_slot(d, t, tile * kListTile + tid, m, pos, r, comp);
   const uint32_t local = live ? t.sv_local[pos] : 0u;
-  const uint32_t* my_row = balg + size_t(blockIdx.x) * ct.cls_bound * 32;
+  const uint32_t* my_row = balg + size_t(tile) * ct.cls_bound * 32;
   uint32_t mask = 0;  // bit cls_lbit[c]: my servant is eligible for class c of its component (merge payload)
   for (uint32_t c0 = 0; c0 < ncls + nmerge; c0 += kListChunk) {
     const uint32_t c1 = min(c0 + kListChunk, ncls + nmerge);
@@ -420,7 +449,7 @@ __global__ void __launch_bounds__(kListTile) k_list_fill(const unsigned long lon
       const uint32_t word = bal[c - c0][warp];
       if ((word >> lane) & 1u) {
         if (c < ncls) mask |= 1u << (ct.cls_lbit[c] & 31u);
-        const uint32_t dst = offs[c * n_tiles + blockIdx.x] + pre[c - c0][warp] + __popc(word & ((1u << lane) - 1));
+        const uint32_t dst = offs[c * n_tiles + tile] + pre[c - c0][warp] + __popc(word & ((1u << lane) - 1));
         // class list: (servant, running_tasks value of the slot); pseudo-class: (servant, class mask)
         if (dst < list_cap) list[dst] = make_uint2(local, c < ncls ? r : mask);
         else ct.meta[1] = 1;  // more (class, slot) pairs than provisioned: the host reruns with solver 1
@@ -428,6 +457,14 @@ __global__ void __launch_bounds__(kListTile) k_list_fill(const unsigned long lon
     }
     __syncthreads();  // bal / pre are reused by the next chunk
   }
+}
+
+__global__ void __launch_bounds__(kListTile) k_list_fill(const unsigned long long* __restrict__ m_ptr, SlotDecode d,
+                                                         TopoView t, ClassTable ct, uint32_t n_tiles,
+                                                         const uint32_t* __restrict__ offs,
+                                                         const uint32_t* __restrict__ balg,
+                                                         uint2* __restrict__ list, uint32_t list_cap) {
+  list_fill_tile(blockIdx.x, (uint32_t)*m_ptr, d, t, ct, n_tiles, offs, balg, list, list_cap);
 }
 
 }  // namespace yd

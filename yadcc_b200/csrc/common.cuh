@@ -83,6 +83,32 @@ struct RqLayout {
   __device__ __forceinline__ uint32_t Base(uint32_t c) const { return sharded ? base[c] : rank_off[c * nrt]; }
 };
 
+// The request queue as the kernels read it: the 24-byte records of the C ABI (yd_task_req), or -- inside the one kernel
+// that receives a packed upload (fused.cuh) -- the 16-byte records of yd_task_req16: {env_id, min_version,
+// requestor_ip, lease} with lease = expires_in_ms | prefetch << 31 (the RPC surface counts leases in milliseconds,
+// scheduler.proto next_keep_alive_in_ms).
+struct ReqView {
+  const yd_task_req* r24;
+  const uint4* r16;  // null: read r24
+  __device__ __forceinline__ void head(uint32_t q, uint32_t& env, uint32_t& mv) const {
+    if (r16) { const uint2 w = __ldg(reinterpret_cast<const uint2*>(r16 + q)); env = w.x; mv = w.y; }
+    else { const uint2 w = __ldg(reinterpret_cast<const uint2*>(r24 + q)); env = w.x; mv = w.y; }
+  }
+  __device__ __forceinline__ uint32_t ip(uint32_t q) const {
+    return r16 ? __ldg(reinterpret_cast<const uint2*>(r16 + q) + 1).x : __ldg(reinterpret_cast<const uint2*>(r24 + q) + 1).x;
+  }
+  __device__ __forceinline__ void lease(uint32_t q, uint32_t& flags, long long& expires_in_ns) const {
+    if (r16) {
+      const uint32_t w = __ldg(reinterpret_cast<const uint2*>(r16 + q) + 1).y;
+      flags = (w >> 31) ? YD_REQ_FLAG_PREFETCH : 0u;
+      expires_in_ns = (long long)(w & 0x7fffffffu) * 1000000ll;
+    } else {
+      flags = __ldg(reinterpret_cast<const uint2*>(r24 + q) + 1).y;
+      expires_in_ns = __ldg(reinterpret_cast<const long long*>(r24 + q) + 2);
+    }
+  }
+};
+
 struct ServantArrays {
   uint32_t* nproc;
   uint32_t* load;

@@ -22,29 +22,29 @@ namespace yd {
 
 constexpr int kRankTile = 1024;
 
-__global__ void __launch_bounds__(kRankTile) k_rank_count(const yd_task_req* __restrict__ reqs,
-                                                          const DynParams* __restrict__ dp, TopoView t, ClassTable ct,
-                                                          const uint32_t* __restrict__ comp_mode, uint32_t n_tiles,
-                                                          uint32_t* __restrict__ rcls,   // [n] class or kNone
-                                                          uint32_t* __restrict__ rrank,  // [n] rank inside the tile
-                                                          uint32_t* __restrict__ rself,  // [n] own servant (merge solver)
-                                                          uint32_t* __restrict__ tile_cnt /* [kMaxClasses][n_tiles] */) {
+// One tile of 1024 requests (a block of 1024 threads).  Every (class, tile) cell of tile_cnt below cls_bound is written,
+// so tiles beyond the end of the queue must be run too (their cells are zero).
+__device__ __forceinline__ void rank_count_tile(uint32_t tile, const ReqView& reqs, uint32_t n,
+                                                const TopoView& t, const ClassTable& ct,
+                                                const uint32_t* __restrict__ comp_mode, uint32_t n_tiles,
+                                                uint32_t* __restrict__ rcls, uint32_t* __restrict__ rrank,
+                                                uint32_t* __restrict__ rself, uint32_t* __restrict__ tile_cnt) {
   __shared__ uint16_t wc[32][kMaxClasses];
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   for (uint32_t i = tid; i < 32 * kMaxClasses / 2; i += kRankTile) reinterpret_cast<uint32_t*>(&wc[0][0])[i] = 0;
   __syncthreads();
-  const uint32_t n = dp->n;
-  const uint32_t q = blockIdx.x * kRankTile + tid;
+  const uint32_t q = tile * kRankTile + tid;
   uint32_t cls = kNone, self = kNone;
   if (q < n) {
-    const uint2 w0 = __ldg(reinterpret_cast<const uint2*>(reqs + q));
-    if (w0.x < t.n_envs) {
-      const uint32_t comp = t.env_comp[w0.x];
+    uint32_t env, mv;
+    reqs.head(q, env, mv);
+    if (env < t.n_envs) {
+      const uint32_t comp = t.env_comp[env];
       if (comp != kNone && comp_mode[comp] != 0) {  // data-parallel or merge: both need FIFO ranks
-        const uint32_t slot = cls_find(ct.keys, ((unsigned long long)w0.x << 32) | w0.y);
+        const uint32_t slot = cls_find(ct.keys, ((unsigned long long)env << 32) | mv);
         if (slot != kNone) cls = ct.slot_cls[slot];
         if (cls != kNone && comp_mode[comp] == 2 && (ct.comp_flags[comp] & 1u)) {
-          self = self_servant(t, __ldg(reinterpret_cast<const uint2*>(reqs + q) + 1).x, comp);
+          self = self_servant(t, reqs.ip(q), comp);
         }
       }
     }
@@ -62,15 +62,26 @@ __global__ void __launch_bounds__(kRankTile) k_rank_count(const yd_task_req* __r
       wc[w][tid] = (uint16_t)run;
       run += c;
     }
-    tile_cnt[tid * n_tiles + blockIdx.x] = run;
+    tile_cnt[tid * n_tiles + tile] = run;
   }
-  if (blockIdx.x == 0 && tid == 0) tile_cnt[ct.cls_bound * n_tiles] = 0;  // the scan's end cell
+  if (tile == 0 && tid == 0) tile_cnt[ct.cls_bound * n_tiles] = 0;  // the scan's end cell
   __syncthreads();
   if (q < n) {
     rcls[q] = cls;
     rrank[q] = cls != kNone ? (uint32_t)wc[warp][cls] + wrank : 0u;
     rself[q] = self;
   }
+  __syncthreads();  // (wc is reused when a block handles several tiles)
+}
+
+__global__ void __launch_bounds__(kRankTile) k_rank_count(const yd_task_req* __restrict__ reqs,
+                                                          const DynParams* __restrict__ dp, TopoView t, ClassTable ct,
+                                                          const uint32_t* __restrict__ comp_mode, uint32_t n_tiles,
+                                                          uint32_t* __restrict__ rcls,   // [n] class or kNone
+                                                          uint32_t* __restrict__ rrank,  // [n] rank inside the tile
+                                                          uint32_t* __restrict__ rself,  // [n] own servant (merge solver)
+                                                          uint32_t* __restrict__ tile_cnt /* [kMaxClasses][n_tiles] */) {
+  rank_count_tile(blockIdx.x, ReqView{reqs, nullptr}, dp->n, t, ct, comp_mode, n_tiles, rcls, rrank, rself, tile_cnt);
 }
 
 // Per-class layout of the merge solver's request records (RqLayout) for the range-sharded queue.  (One GPU: class
@@ -117,6 +128,35 @@ __global__ void __launch_bounds__(256) k_rq_layout(ClassTable ct, const uint32_t
 }
 
 // tile_off = exclusive scan of tile_cnt over (class-major, tile-minor).
+// The verdict of request q as far as it is known before the coupled solvers run: false = not ours (the sequential
+// solver -- or nobody -- answers it; res[q] keeps kResEnvNotFound), else `out` = what goes into res[q].  Requests of
+// merge-mode components also publish their FIFO record.
+__device__ __forceinline__ bool rank_assign_one(uint32_t q, uint32_t n_tiles, const TopoView& t, const ClassTable& ct,
+                                                const uint32_t* __restrict__ rcls, const uint32_t* __restrict__ rrank,
+                                                const uint32_t* __restrict__ rself, const uint32_t* __restrict__ tile_off,
+                                                const uint32_t* __restrict__ list_off, uint32_t n_list_tiles,
+                                                const uint2* __restrict__ list, const uint32_t* __restrict__ comp_mode,
+                                                uint2* __restrict__ rq, const RqLayout& L, uint32_t& out) {
+  const uint32_t c = rcls[q];
+  if (c == kNone) return false;  // not ours: the sequential solver (or nobody) answers it
+  if (ct.cls_nelig[c] == 0) { out = kResEnvNotFound; return true; }  // cc:105-108
+  // FIFO rank inside the class, over the whole queue (lower ranks' requests come first)
+  const uint32_t rank = L.Goff(c) + tile_off[c * n_tiles + q / kRankTile] - tile_off[c * n_tiles] + rrank[q];
+  if (comp_mode[ct.cls_comp[c]] == 2) {
+    // merge solver: publish the class's FIFO request list (class c owns rq[tile_off[c][0] ...)) as
+    // (request, its own servant in the component or kNone);
+    // the verdict stays Timeout unless a slot picks this request (solve_merge.cuh)
+    if (rank < L.Win(c)) rq[L.Base(c) + rank] = make_uint2(L.q_base + q, rself[q]);
+    out = kResTimeout;
+    return true;
+  }
+  const uint32_t lb = list_off[c * n_list_tiles], le = list_off[(c + 1) * n_list_tiles];
+  if (rank >= le - lb) { out = kResTimeout; return true; }  // cc:116-118
+  const uint2 e = list[lb + rank];  // (servant local index, running_tasks value of the slot)
+  out = t.comp_sv_off[ct.cls_comp[c]] + e.x;  // (++running_tasks, ++ever_assigned_tasks happen in k_final_write)
+  return true;
+}
+
 __global__ void __launch_bounds__(256) k_rank_assign(const DynParams* __restrict__ dp, uint32_t n_tiles, TopoView t,
                                                      ClassTable ct,
                                                      const uint32_t* __restrict__ rcls,
@@ -132,24 +172,8 @@ __global__ void __launch_bounds__(256) k_rank_assign(const DynParams* __restrict
   // Overflow flagged by the class table or the list builder: the host reruns this batch (bigger
   // class bound or the row-scan solver), so nothing may be decided -- or counted -- now.
   if (ct.meta[1]) return;
-  const uint32_t c = rcls[q];
-  if (c == kNone) return;  // not ours: the sequential solver (or nobody) answers it
-  if (ct.cls_nelig[c] == 0) { res[q] = kResEnvNotFound; return; }  // cc:105-108
-  // FIFO rank inside the class, over the whole queue (lower ranks' requests come first)
-  const uint32_t rank = L.Goff(c) + tile_off[c * n_tiles + q / kRankTile] - tile_off[c * n_tiles] + rrank[q];
-  if (comp_mode[ct.cls_comp[c]] == 2) {
-    // merge solver: publish the class's FIFO request list (class c owns rq[tile_off[c][0] ...)) as
-    // (request, its own servant in the component or kNone);
-    // the verdict stays Timeout unless a slot picks this request (solve_merge.cuh)
-    if (rank < L.Win(c)) rq[L.Base(c) + rank] = make_uint2(L.q_base + q, rself[q]);
-    res[q] = kResTimeout;
-    return;
-  }
-  const uint32_t lb = list_off[c * n_list_tiles], le = list_off[(c + 1) * n_list_tiles];
-  if (rank >= le - lb) { res[q] = kResTimeout; return; }  // cc:116-118
-  const uint2 e = list[lb + rank];  // (servant local index, running_tasks value of the slot)
-  const uint32_t li = t.comp_sv_off[ct.cls_comp[c]] + e.x;
-  res[q] = li;  // (++running_tasks, ++ever_assigned_tasks happen in k_final_write)
+  uint32_t v;
+  if (rank_assign_one(q, n_tiles, t, ct, rcls, rrank, rself, tile_off, list_off, n_list_tiles, list, comp_mode, rq, L, v)) res[q] = v;
 }
 
 }  // namespace yd

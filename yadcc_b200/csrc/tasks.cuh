@@ -136,27 +136,20 @@ __global__ void __launch_bounds__(1024) k_final_write(const uint32_t* __restrict
 // predecessors are running or done), publishes its count, sums its predecessors' published counts back to the nearest
 // one that already knows its inclusive prefix, and publishes its own.  `look` = one zeroed 64-bit word per block
 // (bits 63..62: 1 = count, 2 = inclusive prefix; low bits: the value) + the ticket counter behind them.
-__global__ void __launch_bounds__(1024) k_final_fused(const uint32_t* __restrict__ res,
-                                                      const yd_task_req* __restrict__ reqs,
-                                                      const DynParams* __restrict__ dp,
-                                                      unsigned long long* __restrict__ look, uint32_t nb,
-                                                      const uint32_t* __restrict__ comp_sv, TaskRing ring,
-                                                      yd_grant* __restrict__ out, Counters* __restrict__ counters,
-                                                      const uint32_t* __restrict__ abort_flag,
-                                                      uint32_t* __restrict__ run, unsigned long long* __restrict__ ever) {
-  if (abort_flag && *abort_flag) return;
+//
+// final_tile: tile `vb` of 1024 requests, r = the solver's verdict for request vb * 1024 + tid (kResEnvNotFound beyond
+// the queue's end).  Tiles below vb must be running or done.  kPacked: 8-byte grants {servant_index, status << 30 |
+// FIFO ordinal of the grant}, see yd_grant8 in ydsched.h.
+template <bool kPacked>
+__device__ __forceinline__ void final_tile(uint32_t vb, uint32_t last_vb, uint32_t r, uint32_t n, long long now_ns,
+                                           const ReqView& reqs, unsigned long long* __restrict__ look,
+                                           const uint32_t* __restrict__ comp_sv, const TaskRing& ring,
+                                           void* __restrict__ out, Counters* __restrict__ counters,
+                                           uint32_t* __restrict__ run, unsigned long long* __restrict__ ever) {
   __shared__ uint32_t warp_cnt[32];
-  __shared__ uint32_t s_vb;
   __shared__ unsigned long long s_excl;
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid == 0) s_vb = (uint32_t)atomicAdd(&look[nb], 1ull);
-  __syncthreads();
-  const uint32_t vb = s_vb;
-  const uint32_t n = dp->n;
-  const long long now_ns = dp->now_ns;
-  ring.next = dp->ring_next;
   const uint32_t q = vb * 1024 + tid;
-  uint32_t r = q < n ? res[q] : kResEnvNotFound;
   const bool granted = r < kResTimeout;
   if (granted) r = comp_sv[r];  // solver results index the component-ordered servant list
   const uint32_t bal = __ballot_sync(0xffffffffu, granted);
@@ -194,33 +187,64 @@ __global__ void __launch_bounds__(1024) k_final_fused(const uint32_t* __restrict
       __threadfence();
       vl[vb] = (2ull << 62) | (excl + mine);
       s_excl = excl;
-      if (vb == nb - 1) {  // the last block knows the batch's total
+      if (vb == last_vb) {  // the last block knows the batch's total
         counters->granted = excl + mine;
         counters->alive += excl + mine;
       }
     }
   }
   __syncthreads();
-  if (q >= n) return;
-  uint32_t before = 0;
-  for (uint32_t w = 0; w < warp; ++w) before += warp_cnt[w];
-  before += __popc(bal & ((1u << lane) - 1));
-  uint4 g;  // {task_id lo, task_id hi, servant_index, status} == yd_grant
-  if (granted) {
-    const uint64_t id = ring.next + s_excl + before;
-    const unsigned long long xid = ring.ext(id);
-    g = make_uint4((uint32_t)xid, (uint32_t)(xid >> 32), r, YD_STATUS_GRANTED);
-    const uint64_t slot = id & ring.mask;
-    const yd_task_req rq = reqs[q];
-    ring.exp[slot] = now_ns + rq.expires_in_ns;
-    ring.srv[slot] = r;
-    ring.flags[slot] = kTaskAlive | ((rq.flags & YD_REQ_FLAG_PREFETCH) ? kTaskPrefetch : 0u);
-    atomicAdd(&run[r], 1u);  // ++running_tasks, ++ever_assigned_tasks (cc:123-124)
-    atomicAdd(&ever[r], 1ull);
-  } else {
-    g = make_uint4(0u, 0u, YD_NO_SERVANT, (r == kResTimeout) ? YD_STATUS_TIMEOUT : YD_STATUS_ENVIRONMENT_NOT_FOUND);
+  if (q < n) {
+    uint32_t before = 0;
+    for (uint32_t w = 0; w < warp; ++w) before += warp_cnt[w];
+    before += __popc(bal & ((1u << lane) - 1));
+    const uint64_t ordinal = s_excl + before;
+    uint32_t status;
+    if (granted) {
+      status = YD_STATUS_GRANTED;
+      const uint64_t id = ring.next + ordinal;
+      const uint64_t slot = id & ring.mask;
+      uint32_t rflags;
+      long long expires_in_ns;
+      reqs.lease(q, rflags, expires_in_ns);
+      ring.exp[slot] = now_ns + expires_in_ns;
+      ring.srv[slot] = r;
+      ring.flags[slot] = kTaskAlive | ((rflags & YD_REQ_FLAG_PREFETCH) ? kTaskPrefetch : 0u);
+      atomicAdd(&run[r], 1u);  // ++running_tasks, ++ever_assigned_tasks (cc:123-124)
+      atomicAdd(&ever[r], 1ull);
+    } else {
+      status = (r == kResTimeout) ? YD_STATUS_TIMEOUT : YD_STATUS_ENVIRONMENT_NOT_FOUND;
+      r = YD_NO_SERVANT;
+    }
+    if (kPacked) {
+      reinterpret_cast<uint2*>(out)[q] = make_uint2(r, (status << 30) | (granted ? (uint32_t)ordinal : 0u));
+    } else {
+      const unsigned long long xid = granted ? ring.ext(ring.next + ordinal) : 0ull;
+      // {task_id lo, task_id hi, servant_index, status} == yd_grant, one 16-byte store
+      reinterpret_cast<uint4*>(out)[q] = make_uint4((uint32_t)xid, (uint32_t)(xid >> 32), r, status);
+    }
   }
-  *reinterpret_cast<uint4*>(out + q) = g;  // one 16-byte store
+  __syncthreads();  // (warp_cnt / s_excl are reused when a block handles several tiles)
+}
+
+__global__ void __launch_bounds__(1024) k_final_fused(const uint32_t* __restrict__ res,
+                                                      const yd_task_req* __restrict__ reqs,
+                                                      const DynParams* __restrict__ dp,
+                                                      unsigned long long* __restrict__ look, uint32_t nb,
+                                                      const uint32_t* __restrict__ comp_sv, TaskRing ring,
+                                                      yd_grant* __restrict__ out, Counters* __restrict__ counters,
+                                                      const uint32_t* __restrict__ abort_flag,
+                                                      uint32_t* __restrict__ run, unsigned long long* __restrict__ ever) {
+  if (abort_flag && *abort_flag) return;
+  __shared__ uint32_t s_vb;
+  if (threadIdx.x == 0) s_vb = (uint32_t)atomicAdd(&look[nb], 1ull);
+  __syncthreads();
+  const uint32_t vb = s_vb;
+  const uint32_t n = dp->n;
+  ring.next = dp->ring_next;
+  const uint32_t q = vb * 1024 + threadIdx.x;
+  final_tile<false>(vb, nb - 1, q < n ? res[q] : kResEnvNotFound, n, dp->now_ns, ReqView{reqs, nullptr}, look, comp_sv, ring, out, counters,
+                    run, ever);
 }
 
 // run[] += claims, ever[] += claims: the all-reduced per-servant slot claims of a range-sharded solve.

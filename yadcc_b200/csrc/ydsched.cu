@@ -33,6 +33,7 @@
 #include "running_index.cuh"
 #include "tasks.cuh"
 #include "tiny.cuh"
+#include "fused.cuh"
 
 namespace {
 
@@ -189,6 +190,13 @@ struct yd_sched {
   uint32_t force_stream = 0;   // yd_config.reserved bit 1 / YDSCHED_FORCE_STREAM: no merge solver for self-requests
   bool dump_env = false, debug_env = false, tiny_ok = true;
   bool stream_attr_set = false;
+  // fused front kernel (fused.cuh): one persistent launch for the class / rank / list phases and -- `solo` -- the grants
+  bool fused_cfg = true;       // yd_config.reserved bit 3 / YDSCHED_NO_FUSED switch it off
+  bool solo_hint = true;       // the last batch consisted of data-parallel components only
+  uint32_t fused_grid = 0;     // blocks of the fused kernel: one per SM
+  uint32_t fused_max_nb = 262144;  // largest batch size class that takes it (YDSCHED_FUSED_MAX_N)
+  size_t z_fbar_off = 0;
+  DevBuf d_reqs16, d_out8;     // packed upload / download (yd_task_req16, yd_grant8)
   size_t res_words = 0;  // u32 words of res[] in d_res (the class-table keys follow)
   size_t staged_n = 0;   // requests placed in d_reqs by yd_stage_requests
 
@@ -213,7 +221,7 @@ struct yd_sched {
   // captured solve graphs, keyed by size class
   struct GraphKey {
     uint32_t Nb = 0, S = 0, n_comps = 0, max_comp = 0, cls_bound = 0, solver = 0, wide = 0, merge_rounds = 0, force_stream = 0,
-             order_static = 0;
+             order_static = 0, variant = 0, packed = 0;
     size_t slot_b = 0;
     unsigned long long gen = 0, topo_gen = 0;  // buffer reallocations; topology rebuilds (n_envs, n_ips, ... are baked in)
     uint64_t ring_cap = 0;
@@ -221,7 +229,7 @@ struct yd_sched {
       return Nb == o.Nb && S == o.S && n_comps == o.n_comps && max_comp == o.max_comp && cls_bound == o.cls_bound &&
              merge_rounds == o.merge_rounds && force_stream == o.force_stream && order_static == o.order_static &&
              solver == o.solver && wide == o.wide && slot_b == o.slot_b && gen == o.gen && topo_gen == o.topo_gen &&
-             ring_cap == o.ring_cap;
+             ring_cap == o.ring_cap && variant == o.variant && packed == o.packed;
     }
   };
   struct GraphEntry { GraphKey key; cudaGraphExec_t exec = nullptr; uint32_t launches = 0; };
@@ -522,6 +530,14 @@ yd_sched* yd_create(const yd_config* cfg) {
   if (const char* e = getenv("YDSCHED_MERGE_CHUNK")) s->merge_chunk = std::max(32u, (uint32_t)atoi(e) & ~31u);
   if (const char* e = getenv("YDSCHED_MERGE_ROUNDS")) s->merge_rounds = std::max(2u, (uint32_t)atoi(e));
   s->tiny_ok = !(cfg->reserved & 4u) && !getenv("YDSCHED_NO_TINY");
+  s->fused_cfg = !(cfg->reserved & 8u) && !getenv("YDSCHED_NO_FUSED");
+  if (const char* e = getenv("YDSCHED_FUSED_MAX_N")) s->fused_max_nb = (uint32_t)std::max(1024, atoi(e));
+  {
+    int sms = 0, per_sm = 0;
+    YD_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg->device));
+    YD_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, yd::k_fused_front, 1024, 0));
+    s->fused_grid = per_sm >= 1 ? (uint32_t)sms : 0u;  // (0: the kernel does not fit an SM -- never on sm_100a; the pipeline is used)
+  }
   s->dump_env = getenv("YDSCHED_DUMP") != nullptr;
   s->debug_env = getenv("YDSCHED_DEBUG") != nullptr;
   YD_CUDA_CHECK(cudaStreamCreateWithFlags(&s->st, cudaStreamNonBlocking));
@@ -560,7 +576,7 @@ void yd_destroy(yd_sched* s) {
                     &s->d_codes, &s->d_ids, &s->d_ok, &s->d_counters, &s->d_sv_env_off, &s->d_sv_envs,
                     &s->d_comp_mode, &s->d_slot_owner, &s->d_sort_k[0], &s->d_sort_k[1], &s->d_sort_v[0],
                     &s->d_sort_v[1], &s->d_zero, &s->d_list, &s->d_list_bal, &s->d_rcls, &s->d_rrank, &s->d_rank_cnt, &s->d_rq, &s->d_rself,
-                    &s->d_slot_pick, &s->d_mst_in, &s->d_mst_out, &s->d_stream_scratch, &s->d_bloom,
+                    &s->d_slot_pick, &s->d_mst_in, &s->d_mst_out, &s->d_stream_scratch, &s->d_reqs16, &s->d_out8, &s->d_bloom,
                     &s->d_bloom_keys, &s->d_bloom_out, &s->d_rt_bytes, &s->d_rt_off, &s->d_rt_len, &s->d_rt_ids,
                     &s->d_rt_slots, &s->d_rt_keys, &s->d_rt_out}) {
     b->release();
@@ -806,6 +822,8 @@ void PrepareStreamBuffers(yd_sched* s, uint32_t Nb, size_t slot_b) {
   off += 2 * (yd::kMaxClasses + 1) * 8;
   s->z_final_off = off;
   off += (size_t(Nb + 1023) / 1024 + 2) * 8;
+  s->z_fbar_off = off;
+  off += 8 * 4;
   const uint32_t n_tiles = (uint32_t)((slot_b + yd::kListTile - 1) / yd::kListTile);
   s->z_listcnt_off = off;
   off += (size_t(s->cls_bound) * n_tiles + 1) * 4;
@@ -878,6 +896,60 @@ uint32_t RebuildSlotOrder(yd_sched* s, size_t slot_b) {
   return l;
 }
 
+// The solvers for everything the data-parallel path does not decide: the merge solver (all components but those with
+// several servants behind one requestor IP), then the sequential slot-stream walk for the rest.
+uint32_t LaunchCoupledSolvers(yd_sched* s, uint32_t N, size_t slot_b, const yd::RqLayout& L) {
+  cudaStream_t st = s->st;
+  uint32_t launches = 0;
+  yd::TopoView t = MakeTopo(s);
+  yd::ClassTable ct = MakeClassTable(s);
+  yd::ServantArrays arr = s->arrays();
+  const yd::DynParams* dp = s->d_dyn.as<yd::DynParams>();
+  uint32_t* list_cnt = reinterpret_cast<uint32_t*>(static_cast<char*>(s->d_zero.p) + s->z_listcnt_off);
+  const uint32_t n_tiles = (uint32_t)((slot_b + yd::kListTile - 1) / yd::kListTile);
+  const uint32_t n_rtiles = (N + yd::kRankTile - 1) / yd::kRankTile;
+  // ---- merge solver: everything but components with several servants behind one requestor IP -------
+  yd::MergePlan mp = MakeMergePlan(s);
+  {
+    yd::MergeArgs m{};
+    m.t = t; m.ct = ct; m.mp = mp; m.sv = arr; m.dp = dp;
+    m.comp_mode = s->d_comp_mode.as<uint32_t>();
+    m.list_off = list_cnt; m.n_list_tiles = n_tiles; m.list = s->d_list.as<uint2>();
+    m.rank_off = s->d_rank_cnt.as<uint32_t>(); m.n_rank_tiles = n_rtiles;
+    m.rq = s->d_rq.as<uint2>(); m.rcls = s->d_rcls.as<uint32_t>(); m.rself = s->d_rself.as<uint32_t>();
+    m.slot_pick = s->d_slot_pick.as<uint32_t>();
+    m.st_in = s->d_mst_in.as<uint32_t>(); m.st_out = s->d_mst_out.as<uint32_t>();
+    m.res = s->d_res.as<uint32_t>();
+    m.L = L;
+    launches += LaunchMerge(s, m, st);
+  }
+
+  // ---- sequential decisions for everything else ---------------------------------------------
+  yd::StreamArgs a{};
+  a.reqs = s->d_reqs.as<yd_task_req>();
+  a.dp = dp;
+  a.res = s->d_res.as<uint32_t>();
+  a.t = t;
+  a.ct = ct;
+  a.sv = arr;
+  a.row_len = s->d_row_len.as<uint32_t>();
+  a.static_rows = s->order_static ? 1u : 0u;
+  a.list_off = list_cnt;
+  a.n_list_tiles = n_tiles;
+  a.list = s->d_list.as<uint2>();
+  a.max_comp_servants = (uint32_t)std::min<size_t>(s->max_comp_servants, kStreamMaxComponent);
+  a.gscratch = s->d_stream_scratch.as<uint32_t>();
+  a.n_servants = (uint32_t)s->sv.size();
+  a.comp_mode = s->d_comp_mode.as<uint32_t>();
+  a.viol = mp.viol;
+  a.counters = s->d_counters.as<Counters>();
+  a.debug = s->stream_debug;
+  const size_t dyn = size_t(a.max_comp_servants) * 8;
+  yd::k_solve_stream<<<s->n_comps, (yd::kStreamProducers + 1) * 32, dyn, st>>>(a);
+  launches += 1;
+  return launches;
+}
+
 // Solver 2: sorted slot streams.  Two concurrent branches:
 //   st  : slot table (+ first histogram) -> radix passes
 //   st2 : [wait for the request upload] class table -> finalize -> FIFO ranks -> scan
@@ -941,45 +1013,57 @@ uint32_t LaunchStream(yd_sched* s, uint32_t N, size_t slot_b, bool capturing) {
                                                      s->d_rq.as<uint2>(), s->d_res.as<uint32_t>(), L);
   launches += 1;
 
-  // ---- merge solver: everything but components with several servants behind one requestor IP -------
-  yd::MergePlan mp = MakeMergePlan(s);
-  {
-    yd::MergeArgs m{};
-    m.t = t; m.ct = ct; m.mp = mp; m.sv = arr; m.dp = dp;
-    m.comp_mode = s->d_comp_mode.as<uint32_t>();
-    m.list_off = list_cnt; m.n_list_tiles = n_tiles; m.list = s->d_list.as<uint2>();
-    m.rank_off = s->d_rank_cnt.as<uint32_t>(); m.n_rank_tiles = n_rtiles;
-    m.rq = s->d_rq.as<uint2>(); m.rcls = s->d_rcls.as<uint32_t>(); m.rself = s->d_rself.as<uint32_t>();
-    m.slot_pick = s->d_slot_pick.as<uint32_t>();
-    m.st_in = s->d_mst_in.as<uint32_t>(); m.st_out = s->d_mst_out.as<uint32_t>();
-    m.res = s->d_res.as<uint32_t>();
-    m.L = L;
-    launches += LaunchMerge(s, m, st);
-  }
+  launches += LaunchCoupledSolvers(s, N, slot_b, L);
+  return launches;
+}
 
-  // ---- sequential decisions for everything else ---------------------------------------------
-  yd::StreamArgs a{};
+// The fused front (fused.cuh): classes, ranks, lists and the data-parallel verdicts in ONE persistent launch on `st`;
+// `solo`: grants, task ids and leases too (batches made of data-parallel components only), else the coupled solvers
+// follow.  Needs the kept slot order.
+uint32_t LaunchFused(yd_sched* s, uint32_t N, size_t slot_b, bool capturing, bool solo, bool packed_in, bool packed_out) {
+  cudaStream_t st = s->st;
+  uint32_t launches = 0;
+  const uint32_t n_tiles = (uint32_t)((slot_b + yd::kListTile - 1) / yd::kListTile);
+  const uint32_t n_rtiles = (N + yd::kRankTile - 1) / yd::kRankTile;
+  yd::FusedArgs a{};
   a.reqs = s->d_reqs.as<yd_task_req>();
-  a.dp = dp;
-  a.res = s->d_res.as<uint32_t>();
-  a.t = t;
-  a.ct = ct;
-  a.sv = arr;
-  a.row_len = s->d_row_len.as<uint32_t>();
-  a.static_rows = s->order_static ? 1u : 0u;
-  a.list_off = list_cnt;
-  a.n_list_tiles = n_tiles;
-  a.list = s->d_list.as<uint2>();
-  a.max_comp_servants = (uint32_t)std::min<size_t>(s->max_comp_servants, kStreamMaxComponent);
-  a.gscratch = s->d_stream_scratch.as<uint32_t>();
-  a.n_servants = (uint32_t)s->sv.size();
+  a.reqs16 = packed_in ? s->d_reqs16.as<uint4>() : nullptr;
+  a.reqs_w = (packed_in && !solo) ? s->d_reqs.as<yd_task_req>() : nullptr;
+  a.dp = s->d_dyn.as<yd::DynParams>();
+  a.t = MakeTopo(s);
+  a.ct = MakeClassTable(s);
+  a.sv = s->arrays();
+  a.dec = yd::SlotDecode{s->d_sort_v[0].as<uint32_t>(), s->d_slot_owner.as<uint32_t>(), s->d_row_off.as<uint32_t>(),
+                         s->d_row_len.as<uint32_t>(), s->d_run.as<uint32_t>(), 1u};
+  a.m_ptr = &s->d_counters.as<Counters>()->slots;
   a.comp_mode = s->d_comp_mode.as<uint32_t>();
-  a.viol = mp.viol;
+  a.n_comps = s->n_comps;
+  a.n_rtiles = n_rtiles;
+  a.n_ltiles = n_tiles;
+  a.rcls = s->d_rcls.as<uint32_t>();
+  a.rrank = s->d_rrank.as<uint32_t>();
+  a.rself = s->d_rself.as<uint32_t>();
+  a.rank_cnt = s->d_rank_cnt.as<uint32_t>();
+  a.list_cnt = reinterpret_cast<uint32_t*>(static_cast<char*>(s->d_zero.p) + s->z_listcnt_off);
+  a.list_bal = s->d_list_bal.as<uint32_t>();
+  a.list = s->d_list.as<uint2>();
+  a.list_cap = (uint32_t)(slot_b * 4);
+  a.rq = s->d_rq.as<uint2>();
+  a.res = s->d_res.as<uint32_t>();
+  a.L = MakeRqLayout(s, 0, N, false);
+  a.bar = reinterpret_cast<uint32_t*>(static_cast<char*>(s->d_zero.p) + s->z_fbar_off);
+  a.solo = solo ? 1u : 0u;
+  a.packed_out = packed_out ? 1u : 0u;
+  a.look = reinterpret_cast<unsigned long long*>(static_cast<char*>(s->d_zero.p) + s->z_final_off);
+  a.comp_sv = s->d_comp_sv.as<uint32_t>();
+  a.ring = s->ring();
+  a.out = packed_out ? s->d_out8.p : s->d_out.p;
   a.counters = s->d_counters.as<Counters>();
-  a.debug = s->stream_debug;
-  const size_t dyn = size_t(a.max_comp_servants) * 8;
-  yd::k_solve_stream<<<s->n_comps, (yd::kStreamProducers + 1) * 32, dyn, st>>>(a);
+  YD_CUDA_CHECK(cudaStreamWaitEvent(st, s->ev_h2d, capturing ? cudaEventWaitExternal : 0));
+  const uint32_t grid = std::min(s->fused_grid, std::max(n_rtiles, n_tiles));
+  yd::k_fused_front<<<grid, 1024, 0, st>>>(a);
   launches += 1;
+  if (!solo) launches += LaunchCoupledSolvers(s, N, slot_b, a.L);
   return launches;
 }
 
@@ -997,22 +1081,38 @@ uint64_t NextPow2(uint64_t v, uint64_t lo) {
 
 // Everything between the request upload and the grant download, for size class
 // (Nb, slot_b): the sequence that is captured into a CUDA graph.
-uint32_t EnqueueSolve(yd_sched* s, uint32_t Nb, size_t slot_b, uint32_t solver, bool record_events, bool capturing) {
+// variant: 0 = the kernel-by-kernel pipeline, 1 = fused front + coupled solvers + final, 2 = fused front alone (solo).
+// packed bit 0: the upload is 16-byte records in d_reqs16; bit 1: the download is 8-byte grants from d_out8.
+uint32_t EnqueueSolve(yd_sched* s, uint32_t Nb, size_t slot_b, uint32_t solver, bool record_events, bool capturing,
+                      uint32_t variant = 0, uint32_t packed = 0) {
   cudaStream_t st = s->st;
   const uint32_t S = (uint32_t)s->sv.size();
   const bool have_work = S && s->n_comps;
   const uint32_t nb = (Nb + 1023) / 1024;
+  const bool packed_in = packed & 1u, packed_out = packed & 2u;
   uint32_t launches = 0;
   const yd::DynParams* dp = s->d_dyn.as<yd::DynParams>();
   YD_CUDA_CHECK(cudaMemcpyAsync(s->d_dyn.p, s->h_dyn.p, sizeof(yd::DynParams), cudaMemcpyHostToDevice, st));
-  // res[] = kResEnvNotFound, and (slot-stream) the class-table keys behind it = empty
-  YD_CUDA_CHECK(cudaMemsetAsync(s->d_res.p, 0xFF, size_t(Nb) * 4 + (solver == 2 ? yd::kClsTableSize * 8 : 0), st));
+  if (variant == 2) {
+    // the solo kernel keeps the verdicts in registers: only the class-table keys behind res[] are initialised
+    YD_CUDA_CHECK(cudaMemsetAsync(s->d_res.as<uint32_t>() + s->res_words, 0xFF, yd::kClsTableSize * 8, st));
+  } else {
+    // res[] = kResEnvNotFound, and (slot-stream) the class-table keys behind it = empty
+    YD_CUDA_CHECK(cudaMemsetAsync(s->d_res.p, 0xFF, size_t(Nb) * 4 + (solver == 2 ? yd::kClsTableSize * 8 : 0), st));
+  }
   if (solver == 2 && have_work) YD_CUDA_CHECK(cudaMemsetAsync(s->d_zero.p, 0, s->z_bytes, st));
   if (record_events) YD_CUDA_CHECK(cudaEventRecord(s->ev[1], st));
   const uint32_t* abort_flag = nullptr;
+  if (packed_in && !(variant && have_work && solver == 2)) {
+    // 16-byte upload -> the 24-byte queue the pipeline kernels read
+    YD_CUDA_CHECK(cudaStreamWaitEvent(st, s->ev_h2d, capturing ? cudaEventWaitExternal : 0));
+    yd::k_unpack_reqs<<<(Nb + 255) / 256, 256, 0, st>>>(s->d_reqs16.as<uint4>(), dp, s->d_reqs.as<yd_task_req>());
+    launches += 1;
+  }
   if (have_work && solver == 2) {
     if (record_events) YD_CUDA_CHECK(cudaEventRecord(s->ev[2], st));
-    launches += LaunchStream(s, Nb, slot_b, capturing);
+    if (variant) launches += LaunchFused(s, Nb, slot_b, capturing, variant == 2, packed_in, packed_out);
+    else launches += LaunchStream(s, Nb, slot_b, capturing);
     abort_flag = MakeClassTable(s).meta + 1;
   } else {
     if (have_work) launches += LaunchSlotTable(s, false);
@@ -1022,7 +1122,9 @@ uint32_t EnqueueSolve(yd_sched* s, uint32_t Nb, size_t slot_b, uint32_t solver, 
     if (have_work) launches += LaunchRowscan(s);
   }
   if (record_events) YD_CUDA_CHECK(cudaEventRecord(s->ev[3], st));
-  if (solver == 2 && have_work && nb <= 2048) {
+  if (variant == 2 && have_work && solver == 2) {
+    // grants, ids and leases were written by the fused kernel
+  } else if (solver == 2 && have_work && nb <= 2048) {
     // grants, task ids (single-pass scan with look-back), leases, ++running_tasks: one launch (beyond ~2 M requests the
     // look-back chain of 1024-thread blocks is slower than three plain passes)
     unsigned long long* look = reinterpret_cast<unsigned long long*>(static_cast<char*>(s->d_zero.p) + s->z_final_off);
@@ -1042,11 +1144,15 @@ uint32_t EnqueueSolve(yd_sched* s, uint32_t Nb, size_t slot_b, uint32_t solver, 
                                            s->d_ever.as<unsigned long long>());
     launches += 3;
   }
+  if (packed_out && !(variant == 2 && have_work && solver == 2)) {
+    yd::k_pack_grants<<<(Nb + 255) / 256, 256, 0, st>>>(s->d_out.as<uint4>(), dp, s->ring(), s->d_out8.as<uint2>());
+    launches += 1;
+  }
   YD_CUDA_CHECK(cudaGetLastError());
   if (record_events) YD_CUDA_CHECK(cudaEventRecord(s->ev[4], st));
   YD_CUDA_CHECK(cudaMemcpyAsync(s->h_counters.p, s->d_counters.p, sizeof(Counters), cudaMemcpyDeviceToHost, st));
   if (abort_flag) {
-    YD_CUDA_CHECK(cudaMemcpyAsync(s->h_meta.p, abort_flag - 1, 16, cudaMemcpyDeviceToHost, st));  // meta[0..3]
+    YD_CUDA_CHECK(cudaMemcpyAsync(s->h_meta.p, abort_flag - 1, 32, cudaMemcpyDeviceToHost, st));  // meta[0..7]
   }
   return launches;
 }
@@ -1138,26 +1244,33 @@ void yd_wait_for_staged_tasks(yd_sched* s, int64_t now_ns, size_t n, yd_grant* o
   yd_wait_for_starting_new_tasks(s, now_ns, nullptr, n, out);
 }
 
-// `reqs` == NULL: the first n staged requests (yd_stage_requests) are already in HBM.
-void yd_wait_for_starting_new_tasks(yd_sched* s, int64_t now_ns, const yd_task_req* reqs, size_t n,
-                                    yd_grant* out) {
+extern "C++" {
+namespace {
+// The solve behind yd_wait_for_starting_new_tasks and its packed twin.  Requests: `reqs` (24-byte records), or `reqs16`
+// (16-byte records), or neither = the first n staged requests (yd_stage_requests) are already in HBM.  Grants: `out`
+// (16-byte records) or `out8` (8-byte records, ids = ids_out->first_task_id + ordinal * stride).
+void WaitImpl(yd_sched* s, int64_t now_ns, const yd_task_req* reqs, const yd_task_req16* reqs16, size_t n, yd_grant* out,
+              yd_grant8* out8, yd_packed_ids* ids_out) {
+  if (ids_out) { ids_out->first_task_id = s->next_id * s->id_stride + s->id_offset; ids_out->stride = s->id_stride; }
   if (n == 0) return;
-  if (!reqs && n > s->staged_n) { fprintf(stderr, "ydsched: NULL request array and nothing staged\n"); abort(); }
+  if (!reqs && !reqs16 && n > s->staged_n) { fprintf(stderr, "ydsched: NULL request array and nothing staged\n"); abort(); }
   if (n > 0x40000000ull) { fprintf(stderr, "ydsched: batch too large\n"); abort(); }
   YD_CUDA_CHECK(cudaSetDevice(s->device));
   cudaStream_t st = s->st;
   const uint32_t N = (uint32_t)n;
   const uint32_t S = (uint32_t)s->sv.size();
+  const uint32_t packed = (reqs16 ? 1u : 0u) | (out8 ? 2u : 0u);
   s->SyncServantState();
   s->SyncFacts();
   s->SyncTopology();
   s->EnsureRing(N);
 
   // ---- a handful of requests: one launch, arguments in, pinned memory out (tiny.cuh) ------------------------------
-  if (reqs && N <= yd::kTinyMax && s->solver_pref == 0 && s->tiny_ok && S && s->n_comps) {
+  if ((reqs || reqs16) && N <= yd::kTinyMax && s->solver_pref == 0 && s->tiny_ok && S && s->n_comps) {
     s->h_small.ensure(256);
     yd::TinyArgs ta{};
-    memcpy(ta.reqs, reqs, size_t(N) * sizeof(yd_task_req));
+    if (reqs) memcpy(ta.reqs, reqs, size_t(N) * sizeof(yd_task_req));
+    else for (uint32_t i = 0; i != N; ++i) ta.reqs[i] = yd_unpack_req(reqs16[i]);
     ta.n = N;
     ta.now_ns = now_ns;
     ta.t = MakeTopo(s);
@@ -1171,7 +1284,8 @@ void yd_wait_for_starting_new_tasks(yd_sched* s, int64_t now_ns, const yd_task_r
     YD_CUDA_CHECK(cudaGetLastError());
     YD_CUDA_CHECK(cudaEventRecord(s->ev[5], st));
     YD_CUDA_CHECK(cudaStreamSynchronize(st));
-    memcpy(out, ta.out, size_t(N) * sizeof(yd_grant));
+    if (out) memcpy(out, ta.out, size_t(N) * sizeof(yd_grant));
+    else for (uint32_t i = 0; i != N; ++i) out8[i] = yd_pack_grant(ta.out[i], *ids_out);
     const unsigned long long granted = *ta.granted_out;
     s->next_id += granted;
     s->staged_n = 0;
@@ -1209,6 +1323,8 @@ void yd_wait_for_starting_new_tasks(yd_sched* s, int64_t now_ns, const yd_task_r
   s->res_words = Nb;
   s->d_res.ensure(size_t(Nb) * 4 + yd::kClsTableSize * 8);
   s->d_out.ensure(size_t(Nb) * sizeof(yd_grant));
+  if (reqs16) s->d_reqs16.ensure(size_t(Nb) * sizeof(yd_task_req16));
+  if (out8) s->d_out8.ensure(size_t(Nb) * sizeof(yd_grant8));
   s->d_blk.ensure(size_t(nb) * 4);
   s->d_row_off.ensure(size_t(S + 1) * 4);
   s->d_row_len.ensure(size_t(S + 1) * 4);
@@ -1236,14 +1352,27 @@ void yd_wait_for_starting_new_tasks(yd_sched* s, int64_t now_ns, const yd_task_r
     YD_CUDA_CHECK(cudaMemcpyAsync(s->d_reqs.p, reqs, size_t(N) * sizeof(yd_task_req), cudaMemcpyHostToDevice,
                                   s->st_copy));
     s->staged_n = 0;  // the staging area now holds this batch
+  } else if (reqs16) {
+    YD_CUDA_CHECK(cudaMemcpyAsync(s->d_reqs16.p, reqs16, size_t(N) * sizeof(yd_task_req16), cudaMemcpyHostToDevice,
+                                  s->st_copy));
+    s->staged_n = 0;
   }
   YD_CUDA_CHECK(cudaEventRecord(s->ev_h2d, s->st_copy));
   bool graphed = false;
   const uint32_t merge_rounds_cfg = s->merge_rounds, force_stream_cfg = s->force_stream;
-  int merge_retry = 0;
-  for (int attempt = 0;; ++attempt) {
-    memset(s->h_meta.p, 0, 16);
+  int merge_retry = 0, grow_attempts = 0;
+  for (;;) {
+    memset(s->h_meta.p, 0, 32);
     graphed = false;
+    // The fused front kernel takes batches in the latency-bound regime whose (class, tile) count matrices one block
+    // scans in a few rounds; it needs the kept slot order.  solo = it also writes the grants (no coupled component
+    // had requests last time; if one has now, the kernel raises flag 4 and the batch is replayed with variant 1).
+    uint32_t variant = 0;
+    if (s->fused_cfg && s->fused_grid && s->solver_pref == 0 && solver == 2 && want_static && S && s->n_comps && Nb <= s->fused_max_nb &&
+        size_t(s->cls_bound) * ((Nb + yd::kRankTile - 1) / yd::kRankTile) <= 32768 &&
+        size_t(s->cls_bound) * ((slot_b + yd::kListTile - 1) / yd::kListTile) <= 32768) {
+      variant = s->solo_hint ? 2u : 1u;
+    }
     if (s->use_graphs) {
       // make sure every buffer the sequence touches exists BEFORE capturing (no allocation
       // inside a capture), then look the size class up
@@ -1257,12 +1386,13 @@ void yd_wait_for_starting_new_tasks(yd_sched* s, int64_t now_ns, const yd_task_r
       key.gen = g_buf_generation; key.topo_gen = s->topo_gen; key.ring_cap = s->ring_cap;
       key.merge_rounds = s->merge_rounds; key.force_stream = s->force_stream;
       key.order_static = (solver == 2 && s->order_static) ? 1u : 0u;
+      key.variant = variant; key.packed = packed;
       yd_sched::GraphEntry* hit = nullptr;
       for (auto& g : s->graphs) if (g.key == key) { hit = &g; break; }
       if (!hit) {
         cudaGraph_t graph = nullptr;
         YD_CUDA_CHECK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-        uint32_t l = EnqueueSolve(s, Nb, slot_b, solver, false, true);
+        uint32_t l = EnqueueSolve(s, Nb, slot_b, solver, false, true, variant, packed);
         YD_CUDA_CHECK(cudaStreamEndCapture(st, &graph));
         cudaGraphExec_t exec = nullptr;
         YD_CUDA_CHECK(cudaGraphInstantiate(&exec, graph, 0));
@@ -1284,17 +1414,20 @@ void yd_wait_for_starting_new_tasks(yd_sched* s, int64_t now_ns, const yd_task_r
       if (solver == 2 && want_static && S && s->n_comps && (s->order_dirty || !s->order_static || s->order_slot_b != slot_b)) {
         launches += RebuildSlotOrder(s, slot_b);
       }
-      launches += EnqueueSolve(s, Nb, slot_b, solver, true, false);
+      launches += EnqueueSolve(s, Nb, slot_b, solver, true, false, variant, packed);
     }
     if (solver == 1) { s->order_dirty = true; s->order_static = false; }  // the row-scan solver's table overwrote the kept one
-    YD_CUDA_CHECK(cudaMemcpyAsync(out, s->d_out.p, size_t(N) * sizeof(yd_grant), cudaMemcpyDeviceToHost, st));
+    if (out8) YD_CUDA_CHECK(cudaMemcpyAsync(out8, s->d_out8.p, size_t(N) * sizeof(yd_grant8), cudaMemcpyDeviceToHost, st));
+    else YD_CUDA_CHECK(cudaMemcpyAsync(out, s->d_out.p, size_t(N) * sizeof(yd_grant), cudaMemcpyDeviceToHost, st));
     YD_CUDA_CHECK(cudaEventRecord(s->ev[5], st));
     YD_CUDA_CHECK(cudaStreamSynchronize(st));
     if (s->dump_env && solver == 2 && S && s->n_comps) DumpStreamState(s, Nb, slot_b);
     if (solver == 2 && S && s->n_comps && s->h_meta.as<uint32_t>()[1] != 0) {
       // Nothing was decided (the stream solver and the final kernels all stood down).
       const uint32_t flag = s->h_meta.as<uint32_t>()[1], ncls = s->h_meta.as<uint32_t>()[0];
-      if (flag == 2 && attempt < 3 && s->cls_bound < yd::kMaxClasses) {  // more lists than provisioned: grow and go again
+      if (flag == 4) {  // the solo kernel met a component it cannot decide: the general sequence, now and next time
+        s->solo_hint = false;
+      } else if (flag == 2 && grow_attempts++ < 3 && s->cls_bound < yd::kMaxClasses) {  // more lists than provisioned: grow and go again
         // one list per class plus one pseudo-class list per merge-mode component
         const uint32_t want = ncls + s->h_meta.as<uint32_t>()[2] + 1;
         s->cls_bound *= 2;
@@ -1314,6 +1447,7 @@ void yd_wait_for_starting_new_tasks(yd_sched* s, int64_t now_ns, const yd_task_r
       }
       continue;
     }
+    if (variant == 1) s->solo_hint = s->h_meta.as<uint32_t>()[4] == 0;  // back to one launch when nothing is coupled any more
     break;
   }
   const Counters* c = s->h_counters.as<Counters>();
@@ -1337,13 +1471,28 @@ void yd_wait_for_starting_new_tasks(yd_sched* s, int64_t now_ns, const yd_task_r
   stt.granted = c->granted;
   stt.kernel_launches = launches;
   stt.solver = solver;
-  stt.h2d_bytes = (reqs ? size_t(N) * sizeof(yd_task_req) : 0) + sizeof(yd::DynParams);
-  stt.d2h_bytes = size_t(N) * sizeof(yd_grant) + sizeof(Counters) + 8;
+  stt.h2d_bytes = (reqs ? size_t(N) * sizeof(yd_task_req) : reqs16 ? size_t(N) * sizeof(yd_task_req16) : 0) + sizeof(yd::DynParams);
+  stt.d2h_bytes = size_t(N) * (out8 ? sizeof(yd_grant8) : sizeof(yd_grant)) + sizeof(Counters) + 32;
   s->have_stats = true;
   if (s->debug_env) {
     fprintf(stderr, "ydsched: solver %u graph %d merge_rounds %llu merge_chunks %llu walks %llu windows %llu solve_ms %.3f\n",
             solver, (int)graphed, c->pad[0], c->pad[1], c->pad[2], c->pad[3], stt.solve_ms);
   }
+}
+}  // namespace
+}  // extern "C++"
+
+// `reqs` == NULL: the first n staged requests (yd_stage_requests) are already in HBM.
+void yd_wait_for_starting_new_tasks(yd_sched* s, int64_t now_ns, const yd_task_req* reqs, size_t n,
+                                    yd_grant* out) {
+  WaitImpl(s, now_ns, reqs, nullptr, n, out, nullptr, nullptr);
+}
+
+// The same decisions with 16-byte requests up and 8-byte grants down (ydsched.h: yd_task_req16, yd_grant8).
+void yd_wait_for_starting_new_tasks_packed(yd_sched* s, int64_t now_ns, const yd_task_req16* reqs, size_t n,
+                                           yd_grant8* out, yd_packed_ids* ids) {
+  yd_packed_ids local;
+  WaitImpl(s, now_ns, nullptr, reqs, n, nullptr, out, ids ? ids : &local);
 }
 
 // KeepTaskAlive x n, cc:142-165.

@@ -77,6 +77,33 @@ def _ns(seconds: float | int) -> int:
     return int(round(seconds * 1_000_000_000))
 
 
+def pack_requests(reqs: np.ndarray, out: np.ndarray | None = None) -> np.ndarray:
+    """REQ_DTYPE -> REQ16_DTYPE (yd_task_req16).  Leases must be whole milliseconds below 2^31 ms -- the RPC
+    surface's unit (scheduler.proto next_keep_alive_in_ms)."""
+    ns = reqs["expires_in_ns"]
+    assert (ns % 1_000_000 == 0).all() and (ns >= 0).all() and (ns < (1 << 31) * 1_000_000).all()
+    if out is None:
+        out = np.empty(reqs.shape[0], dtype=_abi.REQ16_DTYPE)
+    out["env_id"] = reqs["env_id"]
+    out["min_version"] = reqs["min_version"]
+    out["requestor_ip"] = reqs["requestor_ip"]
+    out["lease"] = (ns // 1_000_000).astype(np.uint32) | np.where(
+        reqs["flags"] & _abi.REQ_FLAG_PREFETCH, np.uint32(_abi.LEASE_PREFETCH), np.uint32(0))
+    return out
+
+
+def unpack_grants(g8: np.ndarray, ids) -> np.ndarray:
+    """GRANT8 + PACKED_IDS -> GRANT_DTYPE (yd_unpack_grant)."""
+    out = np.zeros(g8.shape[0], dtype=GRANT_DTYPE)
+    so = g8["status_ordinal"]
+    out["status"] = so >> 30
+    out["servant_index"] = g8["servant_index"]
+    granted = out["status"] == _abi.STATUS_GRANTED
+    out["task_id"] = np.where(
+        granted, np.uint64(ids["first_task_id"]) + (so & 0x3FFFFFFF).astype(np.uint64) * np.uint64(ids["stride"]), np.uint64(0))
+    return out
+
+
 class TaskDispatcher:
     def __init__(
         self,
@@ -88,6 +115,7 @@ class TaskDispatcher:
         graphs: bool = True,
         merge_self: bool = True,
         tiny: bool = True,
+        fused: bool = True,
         id_stride: int = 0,
         id_offset: int = 0,
     ):
@@ -104,7 +132,8 @@ class TaskDispatcher:
             # bit 0: do not capture the solve into a CUDA graph (per-phase timing); bit 1 (test switch): components
             # whose requestors are servants go to the sequential solver instead of the merge solver
             # bit 2 (test switch): batches of <= 8 requests take the full pipeline instead of the one-launch path
-            reserved=(0 if graphs else 1) | (0 if merge_self else 2) | (0 if tiny else 4),
+            # bit 3 (test switch): no fused front kernel (fused.cuh) -- the kernel-by-kernel pipeline at every size
+            reserved=(0 if graphs else 1) | (0 if merge_self else 2) | (0 if tiny else 4) | (0 if fused else 8),
             id_stride=id_stride,
             id_offset=id_offset,
         )
@@ -172,6 +201,26 @@ class TaskDispatcher:
             self._h, now_ns if now_ns is not None else _ns(now), reqs.ctypes.data, n, out.ctypes.data
         )
         return out[:n]
+
+    def wait_for_starting_new_tasks_packed(
+        self, reqs16: np.ndarray, now: float = 0.0, *, now_ns: int | None = None, out8: np.ndarray | None = None,
+        unpack: bool = True,
+    ) -> np.ndarray | tuple[np.ndarray, np.ndarray]:
+        """The same decisions through the packed interface (yd_wait_for_starting_new_tasks_packed): 16-byte
+        requests (`pack_requests`), 8-byte grants.  unpack=True returns a GRANT_DTYPE array like
+        wait_for_starting_new_tasks; unpack=False returns (GRANT8 array, PACKED_IDS record)."""
+        assert reqs16.dtype == _abi.REQ16_DTYPE and reqs16.flags.c_contiguous
+        n = reqs16.shape[0]
+        if out8 is None:
+            out8 = np.empty(n, dtype=_abi.GRANT8_DTYPE)
+        assert out8.dtype == _abi.GRANT8_DTYPE and out8.shape[0] >= n and out8.flags.c_contiguous
+        ids = np.zeros(1, dtype=_abi.PACKED_IDS_DTYPE)
+        self._lib.yd_wait_for_starting_new_tasks_packed(
+            self._h, now_ns if now_ns is not None else _ns(now), reqs16.ctypes.data, n, out8.ctypes.data, ids.ctypes.data
+        )
+        if not unpack:
+            return out8[:n], ids[0]
+        return unpack_grants(out8[:n], ids[0])
 
     def make_requests(
         self,
@@ -491,3 +540,9 @@ class TaskDispatcher:
 
     def alloc_grants(self, n: int) -> np.ndarray:
         return self._alloc(n, GRANT_DTYPE)
+
+    def alloc_requests16(self, n: int) -> np.ndarray:
+        return self._alloc(n, _abi.REQ16_DTYPE)
+
+    def alloc_grants8(self, n: int) -> np.ndarray:
+        return self._alloc(n, _abi.GRANT8_DTYPE)

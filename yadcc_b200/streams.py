@@ -67,12 +67,13 @@ class Replayer:
     """Drives a TaskDispatcher with a Stream and records everything it returns."""
 
     def __init__(self, dispatcher: TaskDispatcher, *, pinned: bool = False, on_solve: Callable | None = None,
-                 batch_heartbeats: bool = False):
+                 batch_heartbeats: bool = False, packed: bool = False):
         """`batch_heartbeats`: runs of consecutive "hb" events with one timestamp go through
         keep_servants_alive, runs of consecutive "notify"/"notify_own" events through
         notify_servants_running_tasks (one call each); the trace is the same by definition."""
         self.d = dispatcher
         self.batch_heartbeats = batch_heartbeats
+        self.packed = packed  # solves go through yd_wait_for_starting_new_tasks_packed (16-byte requests, 8-byte grants)
         self.pinned = pinned
         self.on_solve = on_solve
         self.pending = np.zeros(0, dtype=REQ_DTYPE)
@@ -82,7 +83,14 @@ class Replayer:
         self.solve_calls = 0
 
     def _wait(self, now: float, reqs: np.ndarray) -> np.ndarray:
-        if self.pinned:
+        if self.packed:
+            from .dispatcher import pack_requests
+            if self.pinned:
+                buf = pack_requests(reqs, self.d.alloc_requests16(len(reqs)))
+                g = self.d.wait_for_starting_new_tasks_packed(buf, now, out8=self.d.alloc_grants8(len(reqs)))
+            else:
+                g = self.d.wait_for_starting_new_tasks_packed(pack_requests(reqs), now)
+        elif self.pinned:
             buf = self.d.alloc_requests(len(reqs))
             buf[...] = reqs
             out = self.d.alloc_grants(len(reqs))
