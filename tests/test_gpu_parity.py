@@ -404,6 +404,34 @@ def test_many_classes(make_dispatcher, n_classes):
     assert (results[1] == results[3]).all()
 
 
+@pytest.mark.parametrize("packed", [False, True], ids=["plain", "packed"])
+def test_many_classes_on_a_component_beyond_the_rowscan_solver(make_dispatcher, packed):
+    """300 (digest, min_version) classes overflow the class table while one component has 9000 servants, more than
+    the row-scan fallback holds: the batch is decided as consecutive halves (sequential decisions compose)."""
+    import numpy as np
+    from yadcc_b200 import Servant, PRIORITY_USER, pack_requests
+
+    dg = "ab" * 32
+    results = []
+    for kind in ("cuda", "port"):
+        d = make_dispatcher(kind)
+        r = np.random.default_rng(3)
+        d.keep_servants_alive(
+            [Servant(f"10.{i >> 16}.{(i >> 8) & 255}.{i & 255}:8335", None, [dg], int(r.integers(1, 300)), 8, int(r.integers(0, 4)),
+                     0, 64 << 30, int(r.integers(0, 3)), PRIORITY_USER) for i in range(9000)], 10.0, now=0.0)
+        n = 3000
+        reqs = d.make_requests(n, dg, [f"10.0.{j >> 8}.{j & 255}" if k % 7 == 0 else "172.16.0.9"
+                                       for k, j in enumerate(r.integers(0, 9000, n))],
+                               r.integers(1, 301, n).astype(np.uint32))
+        if packed and kind == "cuda":
+            results.append(d.wait_for_starting_new_tasks_packed(pack_requests(reqs), 0.5).copy())
+        else:
+            results.append(d.wait_for_starting_new_tasks(reqs, 0.5).copy())
+        results.append(d.servant_state()["running_tasks"].copy())
+    assert (results[0] == results[2]).all()
+    assert (results[1] == results[3]).all()
+
+
 @pytest.mark.parametrize("seed", range(8))
 def test_merge_solver_coupled_no_self(make_dispatcher, seed):
     """Coupled components whose requestors are NOT servants take the merge solver

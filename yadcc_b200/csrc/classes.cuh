@@ -57,6 +57,10 @@ struct TopoView {  // the parts of the topology the class kernels need
   const uint32_t* sv_envs;
   const uint32_t* comp_sv_off;
   const uint32_t* comp_sv;
+  // digest membership as one 64-bit word per servant (bit = the digest's index inside its component, env_local), or
+  // null when some component holds more than 64 digests (the CSR above is walked instead)
+  const unsigned long long* sv_emask;
+  const uint32_t* env_local;
 };
 
 __device__ __forceinline__ uint32_t cls_hash(unsigned long long key) {
@@ -79,6 +83,7 @@ __device__ __forceinline__ uint32_t cls_find(const unsigned long long* __restric
 }
 
 __device__ __forceinline__ bool servant_has_env(const TopoView& t, uint32_t pos, uint32_t env) {
+  if (t.sv_emask) return (t.sv_emask[pos] >> (t.env_local[env] & 63u)) & 1ull;
   for (uint32_t u = t.sv_env_off[pos], e = t.sv_env_off[pos + 1]; u < e; ++u) {
     if (t.sv_envs[u] == env) return true;
   }
@@ -346,12 +351,21 @@ struct SlotDecode {
   const uint32_t* row_len;
   const uint32_t* run;
   uint32_t static_rows;  // rows hold every running_tasks value from 0 (table kept across solves): slot k of a row IS r = k
+  const uint2* rec;      // kept order only (else null): sorted position -> (registry position, r), k_slot_records
 };
 
 __device__ __forceinline__ bool decode_slot(const SlotDecode& d, const TopoView& t, uint32_t i, uint32_t m,
                                             uint32_t& pos, uint32_t& r, uint32_t& comp) {
   pos = 0; r = 0; comp = kNone;
   if (i >= m) return false;
+  if (d.rec) {  // one load instead of the four dependent ones below
+    const uint2 w = d.rec[i];
+    if (w.x == kNone) return false;
+    pos = w.x; r = w.y;
+    if (r < d.run[pos]) return false;  // the servant has filled that slot already
+    comp = t.sv_comp[pos];
+    return comp != kNone;
+  }
   const uint32_t orig = d.sorted_orig[i];
   pos = d.slot_owner[orig];
   const uint32_t k = orig - d.row_off[pos];
@@ -364,6 +378,18 @@ __device__ __forceinline__ bool decode_slot(const SlotDecode& d, const TopoView&
   }
   comp = t.sv_comp[pos];
   return comp != kNone;
+}
+
+// The kept order's decode, materialised once per rebuild: rec[i] = (registry position, running_tasks value) of sorted
+// slot i, or (kNone, 0) for a slot outside its row.
+__global__ void __launch_bounds__(256) k_slot_records(const unsigned long long* __restrict__ m_ptr, SlotDecode d,
+                                                      uint2* __restrict__ rec) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (uint32_t)*m_ptr) return;
+  const uint32_t orig = d.sorted_orig[i];
+  const uint32_t pos = d.slot_owner[orig];
+  const uint32_t k = orig - d.row_off[pos];
+  rec[i] = k < d.row_len[pos] ? make_uint2(pos, k) : make_uint2(kNone, 0u);
 }
 
 // "Slot i belongs to list c" is evaluated ONCE, by the count kernel, as ballots: one 32-bit

@@ -91,20 +91,20 @@ struct ReqView {
   const yd_task_req* r24;
   const uint4* r16;  // null: read r24
   __device__ __forceinline__ void head(uint32_t q, uint32_t& env, uint32_t& mv) const {
-    if (r16) { const uint2 w = __ldg(reinterpret_cast<const uint2*>(r16 + q)); env = w.x; mv = w.y; }
-    else { const uint2 w = __ldg(reinterpret_cast<const uint2*>(r24 + q)); env = w.x; mv = w.y; }
+    const uint2 w = r16 ? reinterpret_cast<const uint2*>(r16 + q)[0] : reinterpret_cast<const uint2*>(r24 + q)[0];
+    env = w.x; mv = w.y;
   }
   __device__ __forceinline__ uint32_t ip(uint32_t q) const {
-    return r16 ? __ldg(reinterpret_cast<const uint2*>(r16 + q) + 1).x : __ldg(reinterpret_cast<const uint2*>(r24 + q) + 1).x;
+    return r16 ? reinterpret_cast<const uint2*>(r16 + q)[1].x : reinterpret_cast<const uint2*>(r24 + q)[1].x;
   }
   __device__ __forceinline__ void lease(uint32_t q, uint32_t& flags, long long& expires_in_ns) const {
     if (r16) {
-      const uint32_t w = __ldg(reinterpret_cast<const uint2*>(r16 + q) + 1).y;
+      const uint32_t w = reinterpret_cast<const uint2*>(r16 + q)[1].y;
       flags = (w >> 31) ? YD_REQ_FLAG_PREFETCH : 0u;
       expires_in_ns = (long long)(w & 0x7fffffffu) * 1000000ll;
     } else {
-      flags = __ldg(reinterpret_cast<const uint2*>(r24 + q) + 1).y;
-      expires_in_ns = __ldg(reinterpret_cast<const long long*>(r24 + q) + 2);
+      flags = reinterpret_cast<const uint2*>(r24 + q)[1].y;
+      expires_in_ns = reinterpret_cast<const long long*>(r24 + q)[2];
     }
   }
 };

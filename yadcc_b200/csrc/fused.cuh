@@ -25,15 +25,44 @@
 // first only delays the barrier.
 #pragma once
 #include "parallel.cuh"
+#include <cstddef>
 #include "tasks.cuh"
 
 namespace yd {
 
+// The per-call scalars.  A solo solve is ONE plain kernel launch and gets them by value (kernel parameters); the graphed
+// general sequence reads them from HBM, where the graph's first node copies them.  (They are NOT read from mapped host
+// memory: a dependent load over PCIe at the top of the kernel cost ~70 us apiece on the measured boxes.)
+struct FusedScalars {
+  DynParams dyn;
+  unsigned long long seq;  // launch counter, echoed in the report
+  // Zero-copy I/O, when the caller's arrays are page-locked (yd_alloc_host): device-visible addresses of the caller's
+  // request array (read once, by the first phase, which leaves a copy in HBM for the later ones) and grant array
+  // (written by the last phase of a solo solve) -- no copy-engine transfer before or after the kernel.  Else null.
+  const void* zc_in;
+  void* zc_out;
+};
+
+// The solo kernel's result, in MAPPED pinned host memory (posted writes; the host reads it after the stream has drained):
+// no copy node after the kernel either.
+struct FusedHostIO {
+  unsigned long long done_seq;   // = the launch's seq once the record below is complete (written last)
+  unsigned long long granted;    // grants of the batch
+  uint32_t meta[8];              // the class table's meta words (meta[1] != 0: nothing was decided, see ClassTable)
+};
+
 struct FusedArgs {
+  FusedScalars sc;              // by value ...
+  const FusedScalars* sc_dev;   // ... or, if not null, in HBM
+  FusedHostIO* hio;         // device-side address of the mapped result record (solo)
+  DynParams* dyn_out;       // device copy of the scalars for the kernels that follow (not solo)
+  unsigned long long* clean_keys;  // solo: what the last block re-initialises for the next solve: the class-table keys ...
+  uint4* clean_zero;               // ... and the zeroed scratch region
+  uint32_t clean_zero_vec;         //     (16-byte words)
   const yd_task_req* reqs;  // the 24-byte queue in HBM
   yd_task_req* reqs_w;      // packed upload, not solo: the 24-byte records are written here for the kernels that follow
   const uint4* reqs16;      // packed upload (yd_task_req16), or null
-  const DynParams* dp;
+  uint4* reqs16_w;          // where a zero-copy read of packed requests leaves its HBM copy (= reqs16)
   TopoView t;
   ClassTable ct;
   ServantArrays sv;
@@ -53,7 +82,7 @@ struct FusedArgs {
   uint2* rq;
   uint32_t* res;
   RqLayout L;
-  uint32_t* bar;  // [2], zeroed per solve: arrivals, release epoch
+  uint32_t* bar;  // [3], zeroed per solve: arrivals, release epoch, blocks that are done
   // solo
   uint32_t solo, packed_out;
   unsigned long long* look;
@@ -61,37 +90,81 @@ struct FusedArgs {
   TaskRing ring;
   void* out;
   Counters* counters;
+  uint32_t n_servants;
+  unsigned long long* prof;  // debug (YDSCHED_FUSED_PROF): block 0 stamps %globaltimer at every phase boundary, else null
 };
+
+__device__ __forceinline__ unsigned long long fused_now() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void fused_stamp(const FusedArgs& a, int k) {
+  if (a.prof && blockIdx.x == 0 && threadIdx.x == 0) a.prof[k] = fused_now();
+}
+
+// Pull a table into L2 while the first phase streams the requests: the bench flushes L2 between solves and a scheduler
+// that has been idle finds it cold too; the later phases chase indices through these tables and would pay one DRAM
+// round trip per dependent load.  One 128-byte line per thread and step, spread over the whole grid.
+__device__ __forceinline__ void fused_prefetch(const void* p, size_t bytes) {
+  const char* base = static_cast<const char*>(p);
+  for (size_t off = (size_t(blockIdx.x) * 1024 + threadIdx.x) * 128; off < bytes; off += size_t(gridDim.x) * 1024 * 128) {
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(base + off));
+  }
+}
+
+__device__ __forceinline__ uint32_t fused_atom_add_acq_rel(uint32_t* p, uint32_t v) {
+  uint32_t old;
+  asm volatile("atom.add.acq_rel.gpu.global.u32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");
+  return old;
+}
+__device__ __forceinline__ uint32_t fused_ld_acquire(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void fused_st_release(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 
 // Arrive at barrier episode `epoch` (1, 2, ...).  Returns true in exactly one block: the last one to arrive, which has
 // already acquired everybody's writes and must call fused_release after its leader work; the others call fused_wait.
+// (bar.sync orders the block's accesses before thread 0's release / after its acquire: the cooperative-groups grid
+// barrier with release / acquire accesses instead of full fences.)
 __device__ __forceinline__ bool fused_arrive(uint32_t* bar, uint32_t epoch) {
   __shared__ uint32_t s_last;
   __syncthreads();
-  if (threadIdx.x == 0) {
-    __threadfence();
-    const uint32_t old = atomicAdd(&bar[0], 1u);
-    const uint32_t last = (old + 1 == epoch * gridDim.x) ? 1u : 0u;
-    if (last) __threadfence();
-    s_last = last;
-  }
+  if (threadIdx.x == 0) s_last = (fused_atom_add_acq_rel(&bar[0], 1u) + 1 == epoch * gridDim.x) ? 1u : 0u;
   __syncthreads();
   return s_last != 0;
 }
 __device__ __forceinline__ void fused_release(uint32_t* bar, uint32_t epoch) {
   __syncthreads();
-  if (threadIdx.x == 0) {
-    __threadfence();
-    atomicExch(&bar[1], epoch);
-  }
-  __syncthreads();
+  if (threadIdx.x == 0) fused_st_release(&bar[1], epoch);
 }
 __device__ __forceinline__ void fused_wait(uint32_t* bar, uint32_t epoch) {
   if (threadIdx.x == 0) {
-    while (*reinterpret_cast<volatile uint32_t*>(&bar[1]) < epoch) __nanosleep(20);
-    __threadfence();
+    while (fused_ld_acquire(&bar[1]) < epoch) {}
   }
   __syncthreads();
+}
+// "I am done": true in the block that finishes last -- it has acquired everything the grid wrote.
+__device__ __forceinline__ bool fused_done_last(uint32_t* bar) {
+  __shared__ uint32_t s_fin;
+  __syncthreads();
+  if (threadIdx.x == 0) s_fin = (fused_atom_add_acq_rel(&bar[2], 1u) + 1 == gridDim.x) ? 1u : 0u;
+  __syncthreads();
+  return s_fin != 0;
+}
+
+// The result record for the host (threads 0..8 of one block): the class table's meta words and the grant count, as
+// posted writes into mapped host memory -- or, `report_dev`, into HBM for a copy node to fetch.  The host reads it after
+// the stream has drained, so no ordering is needed among the writes.
+__device__ __forceinline__ void fused_report(const FusedArgs& a, unsigned long long seq, unsigned long long granted) {
+  FusedHostIO* h = a.hio;
+  const uint32_t k = threadIdx.x;
+  if (k < 8) h->meta[k] = a.ct.meta[k];
+  else if (k == 8) { h->granted = granted; h->done_seq = seq; }
 }
 
 // In-place exclusive scan of data[0 .. cells) by one block of 1024 threads (8 values per thread and round).
@@ -142,22 +215,63 @@ __device__ __forceinline__ void fused_scan_flat(uint32_t* __restrict__ data, uin
 
 __global__ void __launch_bounds__(1024, 1) k_fused_front(FusedArgs a) {
   __shared__ unsigned long long s_seen[64];
+  __shared__ DynParams s_dyn;
+  __shared__ unsigned long long s_seq, s_zc_in, s_zc_out;
   const uint32_t tid = threadIdx.x, G = gridDim.x;
-  const uint32_t n = a.dp->n;
+  if (tid == 0) {
+    const FusedScalars sc = a.sc_dev ? *a.sc_dev : a.sc;
+    s_dyn = sc.dyn;
+    s_seq = sc.seq;
+    s_zc_in = reinterpret_cast<unsigned long long>(sc.zc_in);
+    s_zc_out = reinterpret_cast<unsigned long long>(sc.zc_out);
+    if (blockIdx.x == 0 && a.dyn_out) *a.dyn_out = sc.dyn;
+  }
+  __syncthreads();
+  const uint32_t n = s_dyn.n;
   const uint32_t nb_live = (n + 1023) / 1024;            // request tiles that hold requests
   const uint32_t m = (uint32_t)*a.m_ptr;
   const uint32_t lt_live = min((m + kListTile - 1) / kListTile, a.n_ltiles);  // slot tiles that hold slots
   const ReqView rv{a.reqs, a.reqs16};
 
+  fused_stamp(a, 0);
   // ---- P1: classes ---------------------------------------------------------------------------------------------
   if (tid < 64) s_seen[tid] = kClsEmpty;
   __syncthreads();
+  {
+    const size_t S4 = size_t(a.n_servants) * 4;
+    fused_prefetch(a.dec.rec, size_t(m) * 8);
+    fused_prefetch(a.sv.run, S4);
+    fused_prefetch(a.sv.version, S4);
+    fused_prefetch(a.sv.max_tasks, S4);
+    fused_prefetch(a.t.sv_comp, S4);
+    fused_prefetch(a.t.sv_local, S4);
+    fused_prefetch(a.t.comp_sv, S4);
+    if (a.t.sv_emask) fused_prefetch(a.t.sv_emask, S4 * 2);
+    else { fused_prefetch(a.t.sv_env_off, S4 + 4); }
+  }
+  const char* zc_in = reinterpret_cast<const char*>(s_zc_in);
   for (uint32_t tile = blockIdx.x; tile < nb_live; tile += G) {
     const uint32_t q = tile * 1024 + tid;
+    if (zc_in) {
+      // this tile of the caller's page-locked array -> HBM, 16 bytes per thread and step (coalesced reads over PCIe);
+      // every later read of the requests, here and in the kernels that follow, hits the copy
+      if (a.reqs16) {
+        if (q < n) a.reqs16_w[q] = reinterpret_cast<const uint4*>(zc_in)[q];
+      } else {
+        const uint32_t bytes = min(n - tile * 1024, 1024u) * (uint32_t)sizeof(yd_task_req);  // a multiple of 8
+        const char* src = zc_in + size_t(tile) * 1024 * sizeof(yd_task_req);
+        char* dst = reinterpret_cast<char*>(const_cast<yd_task_req*>(a.reqs)) + size_t(tile) * 1024 * sizeof(yd_task_req);
+        for (uint32_t o = tid * 16; o < bytes; o += 1024 * 16) {
+          if (o + 16 <= bytes) *reinterpret_cast<uint4*>(dst + o) = *reinterpret_cast<const uint4*>(src + o);
+          else *reinterpret_cast<uint2*>(dst + o) = *reinterpret_cast<const uint2*>(src + o);
+        }
+      }
+      __syncthreads();
+    }
     if (q < n) {
       uint32_t env, mv, ip;
       if (a.reqs16) {
-        const uint4 w = __ldg(a.reqs16 + q);
+        const uint4 w = a.reqs16[q];
         env = w.x; mv = w.y; ip = w.z;
         if (a.reqs_w) {  // the kernels after this one read 24-byte records
           uint2* dst = reinterpret_cast<uint2*>(a.reqs_w + q);
@@ -174,6 +288,7 @@ __global__ void __launch_bounds__(1024, 1) k_fused_front(FusedArgs a) {
     }
   }
 
+  fused_stamp(a, 1);
   // ---- E1: class numbering and solver modes, by the last block to arrive ------------------------------------------
   if (fused_arrive(a.bar, 1)) {
     cls_finalize_block(a.t, a.ct, a.n_comps, a.comp_mode, a.solo);
@@ -184,9 +299,13 @@ __global__ void __launch_bounds__(1024, 1) k_fused_front(FusedArgs a) {
   // Overflow (1, 2) or a solo kernel facing a coupled component (4): nothing is decided, the host replays the batch.
   // Every block reads the same value: nobody writes the flag between E1's release and the next barrier's arrival
   // ... except list_fill_tile (P5), which is behind E2; the check is repeated after B3.
-  if (*reinterpret_cast<volatile uint32_t*>(&a.ct.meta[1]) != 0) return;
+  if (*reinterpret_cast<volatile uint32_t*>(&a.ct.meta[1]) != 0) {
+    if (a.solo && blockIdx.x == 0) fused_report(a, s_seq, 0);
+    return;
+  }
   const uint32_t ncls = min(a.ct.meta[0], a.ct.cls_bound);
   const uint32_t nlists = min(a.ct.meta[3], a.ct.cls_bound);
+  fused_stamp(a, 2);
 
   // ---- P3: rank counts, list ballots and counts, eligible servants per class ---------------------------------------
   {
@@ -207,6 +326,7 @@ __global__ void __launch_bounds__(1024, 1) k_fused_front(FusedArgs a) {
     }
   }
 
+  fused_stamp(a, 3);
   // ---- E2: both count matrices -> offsets (class-major, tile-minor, + the end cell) -------------------------------
   if (fused_arrive(a.bar, 2)) {
     fused_scan_flat(a.rank_cnt, ncls * a.n_rtiles + 1);
@@ -216,20 +336,27 @@ __global__ void __launch_bounds__(1024, 1) k_fused_front(FusedArgs a) {
     fused_wait(a.bar, 2);
   }
 
+  fused_stamp(a, 4);
   // ---- P5: per-class sorted slot lists ------------------------------------------------------------------------------
   for (uint32_t tile = blockIdx.x; tile < lt_live; tile += G) {
     list_fill_tile(tile, m, a.dec, a.t, a.ct, a.n_ltiles, a.list_cnt, a.list_bal, a.list, a.list_cap);
   }
 
+  fused_stamp(a, 5);
   // ---- B3 ---------------------------------------------------------------------------------------------------------
   if (fused_arrive(a.bar, 3)) fused_release(a.bar, 3);
   else fused_wait(a.bar, 3);
-  if (*reinterpret_cast<volatile uint32_t*>(&a.ct.meta[1]) != 0) return;  // a list outgrew its buffer: nothing is decided
+  if (*reinterpret_cast<volatile uint32_t*>(&a.ct.meta[1]) != 0) {  // a list outgrew its buffer: nothing is decided
+    if (a.solo && blockIdx.x == 0) fused_report(a, s_seq, 0);
+    return;
+  }
 
+  fused_stamp(a, 6);
   // ---- P6: verdicts (+ solo: ids, grants, leases) -----------------------------------------------------------------
-  const long long now_ns = a.dp->now_ns;
+  const long long now_ns = s_dyn.now_ns;
   TaskRing ring = a.ring;
-  ring.next = a.dp->ring_next;
+  ring.next = s_dyn.ring_next;
+  void* const out = s_zc_out ? reinterpret_cast<void*>(s_zc_out) : a.out;
   for (uint32_t tile = blockIdx.x; tile < nb_live; tile += G) {
     const uint32_t q = tile * 1024 + tid;
     uint32_t r = kResEnvNotFound;
@@ -242,9 +369,18 @@ __global__ void __launch_bounds__(1024, 1) k_fused_front(FusedArgs a) {
       }
     }
     if (a.solo) {
-      if (a.packed_out) final_tile<true>(tile, nb_live - 1, r, n, now_ns, rv, a.look, a.comp_sv, ring, a.out, a.counters, a.sv.run, a.sv.ever);
-      else final_tile<false>(tile, nb_live - 1, r, n, now_ns, rv, a.look, a.comp_sv, ring, a.out, a.counters, a.sv.run, a.sv.ever);
+      if (a.packed_out) final_tile<true>(tile, nb_live - 1, r, n, now_ns, rv, a.look, a.comp_sv, ring, out, a.counters, a.sv.run, a.sv.ever);
+      else final_tile<false>(tile, nb_live - 1, r, n, now_ns, rv, a.look, a.comp_sv, ring, out, a.counters, a.sv.run, a.sv.ever);
     }
+  }
+  fused_stamp(a, 7);
+  // ---- solo: the block that finishes last reports to the host and leaves the scratch as the next solve expects it ----
+  if (a.solo && fused_done_last(a.bar)) {
+    fused_report(a, s_seq, a.counters->granted);
+    __syncthreads();  // (the report reads meta[], which lies in the region zeroed below)
+    for (uint32_t i = tid; i < kClsTableSize; i += 1024) a.clean_keys[i] = kClsEmpty;
+    for (uint32_t i = tid; i < a.clean_zero_vec; i += 1024) a.clean_zero[i] = make_uint4(0u, 0u, 0u, 0u);
+    if (a.prof && tid == 0) a.prof[8] = fused_now();
   }
 }
 

@@ -171,7 +171,8 @@ struct yd_sched {
   PinBuf h_topo;
 
   // slot-stream solver state
-  DevBuf d_sv_env_off, d_sv_envs, d_comp_mode;
+  DevBuf d_sv_env_off, d_sv_envs, d_comp_mode, d_sv_emask, d_slot_rec;
+  bool emask_ok = false;  // every component holds <= 64 digests: d_sv_emask is valid
   DevBuf d_slot_owner, d_sort_k[2], d_sort_v[2];
   // one zero-filled scratch region per solve: radix histograms (one per pass), the class
   // table's u32 arrays, the per-(class, tile) list counts -- a single memset node
@@ -197,6 +198,20 @@ struct yd_sched {
   uint32_t fused_max_nb = 262144;  // largest batch size class that takes it (YDSCHED_FUSED_MAX_N)
   size_t z_fbar_off = 0;
   DevBuf d_reqs16, d_out8;     // packed upload / download (yd_task_req16, yd_grant8)
+  yd::FusedHostIO* h_fio = nullptr;  // mapped pinned record: the solo kernel's result (no copy nodes after it)
+  yd::FusedHostIO* d_fio = nullptr;  // its device-side address
+  yd::FusedScalars fsc{};            // the call's scalars: kernel parameters of a solo launch ...
+  PinBuf h_fsc;                      // ... or (graphed general sequence) copied into d_fsc by the graph's first node
+  DevBuf d_fsc;
+  // The solo kernel re-initialises the scratch it dirtied (class-table keys, zeroed region) before it ends; while this
+  // signature matches the current buffers and layout the next solo solve needs no memset nodes either.
+  struct CleanSig { unsigned long long gen = ~0ull; size_t z_cls_off = 0, z_bytes = 0, res_words = 0; const void* zero = nullptr; const void* res = nullptr;
+    bool operator==(const CleanSig& o) const { return gen == o.gen && z_cls_off == o.z_cls_off && z_bytes == o.z_bytes && res_words == o.res_words && zero == o.zero && res == o.res; } };
+  CleanSig clean_sig;
+  bool clean_valid = false;
+  bool zero_copy = true;       // YDSCHED_NO_ZEROCOPY: page-locked caller arrays are copied like pageable ones
+  bool fused_prof = false;     // YDSCHED_FUSED_PROF: phase stamps of the fused kernel, printed after every solve
+  DevBuf d_fused_prof;
   size_t res_words = 0;  // u32 words of res[] in d_res (the class-table keys follow)
   size_t staged_n = 0;   // requests placed in d_reqs by yd_stage_requests
 
@@ -232,7 +247,21 @@ struct yd_sched {
              ring_cap == o.ring_cap && variant == o.variant && packed == o.packed;
     }
   };
-  struct GraphEntry { GraphKey key; cudaGraphExec_t exec = nullptr; uint32_t launches = 0; };
+  struct GraphEntry {
+    GraphKey key;
+    cudaGraphExec_t exec = nullptr;
+    uint32_t launches = 0;
+    // solo graphs (one kernel node): the per-call scalars are kernel parameters, patched before every launch
+    cudaGraph_t graph = nullptr;
+    cudaGraphNode_t knode = nullptr;
+    yd::FusedArgs fargs{};
+    uint32_t fgrid = 0;
+  };
+  yd::FusedArgs last_fused{};  // what LaunchFused passed last (picked up right after a capture)
+  uint32_t last_fused_grid = 0;
+  bool report_dev = false;     // YDSCHED_REPORT_DEV: the solo kernel's report goes to HBM + a copy node (comparison)
+  bool host_prof = false;      // YDSCHED_HOST_PROF: host-side timestamps of a solve, printed
+  DevBuf d_report;
   std::vector<GraphEntry> graphs;
   unsigned long long topo_gen = 0;
   bool use_graphs = true;
@@ -253,6 +282,8 @@ struct yd_sched {
   cudaEvent_t ev[6] = {};
   yd_solve_stats stats{};
   bool have_stats = false;
+  int stats_times_pending = 0;  // 1: events of an eager solve, 2: of a graphed one, not yet turned into milliseconds
+  size_t static_bound_cache = 0;  // StaticSlotBound() of the current facts
 
   yd::ServantArrays arrays() const {
     return yd::ServantArrays{d_nproc.as<uint32_t>(), d_load.as<uint32_t>(), d_maxt.as<uint32_t>(),
@@ -325,6 +356,8 @@ void yd_sched::SyncFacts() {
       h[4 * S + i] = (uint32_t)s.version;
       maxcap = std::max(maxcap, std::min(s.nproc, s.max_tasks));
     }
+    static_bound_cache = 0;
+    for (uint32_t i = 0; i != S; ++i) static_bound_cache += size_t(std::min(sv[i].nproc, sv[i].max_tasks)) + 1;
     if (wide != (maxcap > yd::kNarrowCapLimit)) order_dirty = true;
     wide = maxcap > yd::kNarrowCapLimit;
     d_nproc.ensure(size_t(S) * 4); d_load.ensure(size_t(S) * 4); d_maxt.ensure(size_t(S) * 4);
@@ -454,6 +487,14 @@ void yd_sched::SyncTopology() {
   env_off[S] = (uint32_t)env_flat.size();
   up(d_sv_env_off, env_off.data(), size_t(S + 1) * 4);
   up(d_sv_envs, env_flat.data(), env_flat.size() * 4);
+  // digest membership as a 64-bit word per servant, when every component's digests fit
+  emask_ok = true;
+  for (uint32_t c = 0; c != C; ++c) emask_ok = emask_ok && comp_envs[c].size() <= 64;
+  std::vector<unsigned long long> emask(std::max(S, 1u), 0ull);
+  if (emask_ok) {
+    for (uint32_t i = 0; i != S; ++i) for (uint32_t e : sv[i].envs) emask[i] |= 1ull << env_local[e];
+  }
+  up(d_sv_emask, emask.data(), emask.size() * 8);
   std::vector<uint32_t> comp_mode(std::max(C, 1u), 0);
   up(d_comp_mode, comp_mode.data(), comp_mode.size() * 4);
   max_comp_servants = 0;
@@ -532,6 +573,16 @@ yd_sched* yd_create(const yd_config* cfg) {
   s->tiny_ok = !(cfg->reserved & 4u) && !getenv("YDSCHED_NO_TINY");
   s->fused_cfg = !(cfg->reserved & 8u) && !getenv("YDSCHED_NO_FUSED");
   if (const char* e = getenv("YDSCHED_FUSED_MAX_N")) s->fused_max_nb = (uint32_t)std::max(1024, atoi(e));
+  YD_CUDA_CHECK(cudaHostAlloc(reinterpret_cast<void**>(&s->h_fio), sizeof(yd::FusedHostIO), cudaHostAllocMapped));
+  memset(s->h_fio, 0, sizeof(yd::FusedHostIO));
+  YD_CUDA_CHECK(cudaHostGetDevicePointer(reinterpret_cast<void**>(&s->d_fio), s->h_fio, 0));
+  s->zero_copy = getenv("YDSCHED_NO_ZEROCOPY") == nullptr;
+  s->report_dev = getenv("YDSCHED_REPORT_DEV") != nullptr;
+  s->host_prof = getenv("YDSCHED_HOST_PROF") != nullptr;
+  s->d_report.ensure(sizeof(yd::FusedHostIO));
+  s->fused_prof = getenv("YDSCHED_FUSED_PROF") != nullptr;
+  s->d_fused_prof.ensure(128);
+  YD_CUDA_CHECK(cudaMemset(s->d_fused_prof.p, 0, 128));
   {
     int sms = 0, per_sm = 0;
     YD_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg->device));
@@ -556,6 +607,8 @@ yd_sched* yd_create(const yd_config* cfg) {
   s->h_small.ensure(1 << 16);
   s->d_dyn.ensure(sizeof(yd::DynParams));
   s->h_dyn.ensure(sizeof(yd::DynParams));
+  s->h_fsc.ensure(sizeof(yd::FusedScalars));
+  s->d_fsc.ensure(sizeof(yd::FusedScalars));
   s->h_meta.ensure(64);
   s->EnsureRing(0);
   return s;
@@ -574,16 +627,18 @@ void yd_destroy(yd_sched* s) {
                     &s->d_sv_comp, &s->d_sv_local, &s->d_ip_off, &s->d_ip_sv, &s->d_t_exp, &s->d_t_srv,
                     &s->d_t_flags, &s->d_reqs, &s->d_res, &s->d_out, &s->d_blk, &s->d_row_off, &s->d_row_len,
                     &s->d_codes, &s->d_ids, &s->d_ok, &s->d_counters, &s->d_sv_env_off, &s->d_sv_envs,
-                    &s->d_comp_mode, &s->d_slot_owner, &s->d_sort_k[0], &s->d_sort_k[1], &s->d_sort_v[0],
+                    &s->d_comp_mode, &s->d_sv_emask, &s->d_slot_rec, &s->d_slot_owner, &s->d_sort_k[0], &s->d_sort_k[1], &s->d_sort_v[0],
                     &s->d_sort_v[1], &s->d_zero, &s->d_list, &s->d_list_bal, &s->d_rcls, &s->d_rrank, &s->d_rank_cnt, &s->d_rq, &s->d_rself,
-                    &s->d_slot_pick, &s->d_mst_in, &s->d_mst_out, &s->d_stream_scratch, &s->d_reqs16, &s->d_out8, &s->d_bloom,
+                    &s->d_slot_pick, &s->d_mst_in, &s->d_mst_out, &s->d_stream_scratch, &s->d_reqs16, &s->d_out8, &s->d_fused_prof, &s->d_report, &s->d_bloom,
                     &s->d_bloom_keys, &s->d_bloom_out, &s->d_rt_bytes, &s->d_rt_off, &s->d_rt_len, &s->d_rt_ids,
                     &s->d_rt_slots, &s->d_rt_keys, &s->d_rt_out}) {
     b->release();
   }
-  for (auto& g : s->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
+  for (auto& g : s->graphs) { if (g.exec) cudaGraphExecDestroy(g.exec); if (g.graph) cudaGraphDestroy(g.graph); }
+  if (s->h_fio) cudaFreeHost(s->h_fio);
   s->d_dyn.release();
-  for (PinBuf* b : {&s->h_facts, &s->h_topo, &s->h_counters, &s->h_small, &s->h_dyn, &s->h_meta}) b->release();
+  s->d_fsc.release();
+  for (PinBuf* b : {&s->h_facts, &s->h_topo, &s->h_counters, &s->h_small, &s->h_dyn, &s->h_meta, &s->h_fsc}) b->release();
   for (auto& e : s->ev) cudaEventDestroy(e);
   cudaEventDestroy(s->ev_fork); cudaEventDestroy(s->ev_join); cudaEventDestroy(s->ev_h2d); cudaEventDestroy(s->ev_fin);
   cudaStreamDestroy(s->st2); cudaStreamDestroy(s->st_copy);
@@ -657,6 +712,8 @@ yd::TopoView MakeTopo(yd_sched* s) {
   t.sv_envs = s->d_sv_envs.as<uint32_t>();
   t.comp_sv_off = s->d_comp_sv_off.as<uint32_t>();
   t.comp_sv = s->d_comp_sv.as<uint32_t>();
+  t.sv_emask = s->emask_ok ? s->d_sv_emask.as<unsigned long long>() : nullptr;
+  t.env_local = s->d_env_local.as<uint32_t>();
   return t;
 }
 
@@ -807,6 +864,7 @@ uint32_t LaunchSort(yd_sched* s, int first_bit, int last_bit) {
 void PrepareStreamBuffers(yd_sched* s, uint32_t Nb, size_t slot_b) {
   const size_t ksz = s->wide ? 8 : 4;
   for (int b = 0; b < 2; ++b) { s->d_sort_k[b].ensure(slot_b * ksz); s->d_sort_v[b].ensure(slot_b * 4); }
+  s->d_slot_rec.ensure(slot_b * 8);
   s->sort_nb = (uint32_t)((slot_b + yd::kRsTile - 1) / yd::kRsTile);
   const int passes = s->wide ? 9 : 4;
   size_t off = 0;
@@ -872,13 +930,6 @@ uint32_t LaunchMerge(yd_sched* s, yd::MergeArgs& m, cudaStream_t st) {
 
 constexpr size_t kStaticSlotLimit = size_t(1) << 26;
 
-// Slots of every servant for running_tasks = 0 .. free_end - 1 (+1 spare per servant), whatever the batch.
-size_t StaticSlotBound(yd_sched* s) {
-  size_t b = 0;
-  for (auto&& v : s->sv) b += size_t(std::min(v.nproc, v.max_tasks)) + 1;
-  return b;
-}
-
 // (Re)builds the kept slot order: slot table over ALL running_tasks values + its sort, outside any graph.
 // Buffers must exist (PrepareStreamBuffers).  Returns the number of kernels launched.
 uint32_t RebuildSlotOrder(yd_sched* s, size_t slot_b) {
@@ -888,6 +939,13 @@ uint32_t RebuildSlotOrder(yd_sched* s, size_t slot_b) {
   uint32_t l = LaunchSlotTable(s, true, true);
   if (s->wide) l += LaunchSort<unsigned long long>(s, 0, 62);
   else l += LaunchSort<uint32_t>(s, 3, 30);
+  {
+    yd::SlotDecode dec{s->d_sort_v[0].as<uint32_t>(), s->d_slot_owner.as<uint32_t>(), s->d_row_off.as<uint32_t>(),
+                       s->d_row_len.as<uint32_t>(), s->d_run.as<uint32_t>(), 1u, nullptr};
+    yd::k_slot_records<<<(unsigned)((slot_b + 255) / 256), 256, 0, st>>>(&s->d_counters.as<Counters>()->slots, dec,
+                                                                          s->d_slot_rec.as<uint2>());
+    l += 1;
+  }
   YD_CUDA_CHECK(cudaGetLastError());
   s->order_dirty = false;
   s->order_static = true;
@@ -993,7 +1051,8 @@ uint32_t LaunchStream(yd_sched* s, uint32_t N, size_t slot_b, bool capturing) {
   // ---- per-class sorted slot lists ----------------------------------------------------
   const unsigned long long* m_ptr = &s->d_counters.as<Counters>()->slots;
   yd::SlotDecode dec{s->d_sort_v[0].as<uint32_t>(), s->d_slot_owner.as<uint32_t>(), s->d_row_off.as<uint32_t>(),
-                     s->d_row_len.as<uint32_t>(), s->d_run.as<uint32_t>(), s->order_static ? 1u : 0u};
+                     s->d_row_len.as<uint32_t>(), s->d_run.as<uint32_t>(), s->order_static ? 1u : 0u,
+                     s->order_static ? s->d_slot_rec.as<uint2>() : nullptr};
   yd::k_list_count<<<n_tiles, yd::kListTile, 0, st>>>(m_ptr, dec, t, ct, arr, n_tiles, list_cnt,
                                                       s->d_list_bal.as<uint32_t>());
   yd::k_scan_rows<<<ct.cls_bound, 1024, 0, st>>>(list_cnt, ct.meta + 3, n_tiles, ScanPub(s, 1));
@@ -1026,15 +1085,24 @@ uint32_t LaunchFused(yd_sched* s, uint32_t N, size_t slot_b, bool capturing, boo
   const uint32_t n_tiles = (uint32_t)((slot_b + yd::kListTile - 1) / yd::kListTile);
   const uint32_t n_rtiles = (N + yd::kRankTile - 1) / yd::kRankTile;
   yd::FusedArgs a{};
+  a.sc = s->fsc;
+  // graphed general sequence: the scalars come through a copy node; a solo graph gets them as (patched) kernel parameters
+  a.sc_dev = (capturing && !solo) ? s->d_fsc.as<yd::FusedScalars>() : nullptr;
+  if (a.sc_dev) YD_CUDA_CHECK(cudaMemcpyAsync(s->d_fsc.p, s->h_fsc.p, sizeof(yd::FusedScalars), cudaMemcpyHostToDevice, st));
+  a.hio = s->report_dev ? s->d_report.as<yd::FusedHostIO>() : s->d_fio;
+  a.dyn_out = solo ? nullptr : s->d_dyn.as<yd::DynParams>();
+  a.clean_keys = reinterpret_cast<unsigned long long*>(s->d_res.as<uint32_t>() + s->res_words);
+  a.clean_zero = reinterpret_cast<uint4*>(static_cast<char*>(s->d_zero.p) + s->z_cls_off);
+  a.clean_zero_vec = (uint32_t)((s->z_bytes - s->z_cls_off) / 16);
   a.reqs = s->d_reqs.as<yd_task_req>();
   a.reqs16 = packed_in ? s->d_reqs16.as<uint4>() : nullptr;
+  a.reqs16_w = packed_in ? s->d_reqs16.as<uint4>() : nullptr;
   a.reqs_w = (packed_in && !solo) ? s->d_reqs.as<yd_task_req>() : nullptr;
-  a.dp = s->d_dyn.as<yd::DynParams>();
   a.t = MakeTopo(s);
   a.ct = MakeClassTable(s);
   a.sv = s->arrays();
   a.dec = yd::SlotDecode{s->d_sort_v[0].as<uint32_t>(), s->d_slot_owner.as<uint32_t>(), s->d_row_off.as<uint32_t>(),
-                         s->d_row_len.as<uint32_t>(), s->d_run.as<uint32_t>(), 1u};
+                         s->d_row_len.as<uint32_t>(), s->d_run.as<uint32_t>(), 1u, s->d_slot_rec.as<uint2>()};
   a.m_ptr = &s->d_counters.as<Counters>()->slots;
   a.comp_mode = s->d_comp_mode.as<uint32_t>();
   a.n_comps = s->n_comps;
@@ -1059,9 +1127,16 @@ uint32_t LaunchFused(yd_sched* s, uint32_t N, size_t slot_b, bool capturing, boo
   a.ring = s->ring();
   a.out = packed_out ? s->d_out8.p : s->d_out.p;
   a.counters = s->d_counters.as<Counters>();
+  a.n_servants = (uint32_t)s->sv.size();
+  a.prof = s->fused_prof ? s->d_fused_prof.as<unsigned long long>() : nullptr;
   YD_CUDA_CHECK(cudaStreamWaitEvent(st, s->ev_h2d, capturing ? cudaEventWaitExternal : 0));
   const uint32_t grid = std::min(s->fused_grid, std::max(n_rtiles, n_tiles));
   yd::k_fused_front<<<grid, 1024, 0, st>>>(a);
+  s->last_fused = a;
+  s->last_fused_grid = grid;
+  if (solo && s->report_dev) {
+    YD_CUDA_CHECK(cudaMemcpyAsync(s->h_fio, s->d_report.p, sizeof(yd::FusedHostIO), cudaMemcpyDeviceToHost, st));
+  }
   launches += 1;
   if (!solo) launches += LaunchCoupledSolvers(s, N, slot_b, a.L);
   return launches;
@@ -1092,15 +1167,22 @@ uint32_t EnqueueSolve(yd_sched* s, uint32_t Nb, size_t slot_b, uint32_t solver, 
   const bool packed_in = packed & 1u, packed_out = packed & 2u;
   uint32_t launches = 0;
   const yd::DynParams* dp = s->d_dyn.as<yd::DynParams>();
-  YD_CUDA_CHECK(cudaMemcpyAsync(s->d_dyn.p, s->h_dyn.p, sizeof(yd::DynParams), cudaMemcpyHostToDevice, st));
-  if (variant == 2) {
-    // the solo kernel keeps the verdicts in registers: only the class-table keys behind res[] are initialised
-    YD_CUDA_CHECK(cudaMemsetAsync(s->d_res.as<uint32_t>() + s->res_words, 0xFF, yd::kClsTableSize * 8, st));
+  const bool fused = variant && have_work && solver == 2;
+  const bool solo = fused && variant >= 2;
+  // (the fused kernel reads the call's scalars from the mapped host record and -- not solo -- stores them in d_dyn itself)
+  if (!fused) YD_CUDA_CHECK(cudaMemcpyAsync(s->d_dyn.p, s->h_dyn.p, sizeof(yd::DynParams), cudaMemcpyHostToDevice, st));
+  if (solo) {
+    // the solo kernel keeps the verdicts in registers: only the class-table keys behind res[] are initialised -- and
+    // not even those (variant 3) when the previous solo solve left the scratch clean
+    if (variant == 2) {
+      YD_CUDA_CHECK(cudaMemsetAsync(s->d_res.as<uint32_t>() + s->res_words, 0xFF, yd::kClsTableSize * 8, st));
+      YD_CUDA_CHECK(cudaMemsetAsync(static_cast<char*>(s->d_zero.p) + s->z_cls_off, 0, s->z_bytes - s->z_cls_off, st));
+    }
   } else {
     // res[] = kResEnvNotFound, and (slot-stream) the class-table keys behind it = empty
     YD_CUDA_CHECK(cudaMemsetAsync(s->d_res.p, 0xFF, size_t(Nb) * 4 + (solver == 2 ? yd::kClsTableSize * 8 : 0), st));
+    if (solver == 2 && have_work) YD_CUDA_CHECK(cudaMemsetAsync(s->d_zero.p, 0, s->z_bytes, st));
   }
-  if (solver == 2 && have_work) YD_CUDA_CHECK(cudaMemsetAsync(s->d_zero.p, 0, s->z_bytes, st));
   if (record_events) YD_CUDA_CHECK(cudaEventRecord(s->ev[1], st));
   const uint32_t* abort_flag = nullptr;
   if (packed_in && !(variant && have_work && solver == 2)) {
@@ -1111,7 +1193,7 @@ uint32_t EnqueueSolve(yd_sched* s, uint32_t Nb, size_t slot_b, uint32_t solver, 
   }
   if (have_work && solver == 2) {
     if (record_events) YD_CUDA_CHECK(cudaEventRecord(s->ev[2], st));
-    if (variant) launches += LaunchFused(s, Nb, slot_b, capturing, variant == 2, packed_in, packed_out);
+    if (variant) launches += LaunchFused(s, Nb, slot_b, capturing, variant >= 2, packed_in, packed_out);
     else launches += LaunchStream(s, Nb, slot_b, capturing);
     abort_flag = MakeClassTable(s).meta + 1;
   } else {
@@ -1122,7 +1204,7 @@ uint32_t EnqueueSolve(yd_sched* s, uint32_t Nb, size_t slot_b, uint32_t solver, 
     if (have_work) launches += LaunchRowscan(s);
   }
   if (record_events) YD_CUDA_CHECK(cudaEventRecord(s->ev[3], st));
-  if (variant == 2 && have_work && solver == 2) {
+  if (solo) {
     // grants, ids and leases were written by the fused kernel
   } else if (solver == 2 && have_work && nb <= 2048) {
     // grants, task ids (single-pass scan with look-back), leases, ++running_tasks: one launch (beyond ~2 M requests the
@@ -1144,12 +1226,13 @@ uint32_t EnqueueSolve(yd_sched* s, uint32_t Nb, size_t slot_b, uint32_t solver, 
                                            s->d_ever.as<unsigned long long>());
     launches += 3;
   }
-  if (packed_out && !(variant == 2 && have_work && solver == 2)) {
+  if (packed_out && !solo) {
     yd::k_pack_grants<<<(Nb + 255) / 256, 256, 0, st>>>(s->d_out.as<uint4>(), dp, s->ring(), s->d_out8.as<uint2>());
     launches += 1;
   }
   YD_CUDA_CHECK(cudaGetLastError());
   if (record_events) YD_CUDA_CHECK(cudaEventRecord(s->ev[4], st));
+  if (solo) return launches;  // the kernel left grant count and flags in the mapped host record
   YD_CUDA_CHECK(cudaMemcpyAsync(s->h_counters.p, s->d_counters.p, sizeof(Counters), cudaMemcpyDeviceToHost, st));
   if (abort_flag) {
     YD_CUDA_CHECK(cudaMemcpyAsync(s->h_meta.p, abort_flag - 1, 32, cudaMemcpyDeviceToHost, st));  // meta[0..7]
@@ -1253,6 +1336,9 @@ void WaitImpl(yd_sched* s, int64_t now_ns, const yd_task_req* reqs, const yd_tas
               yd_grant8* out8, yd_packed_ids* ids_out) {
   if (ids_out) { ids_out->first_task_id = s->next_id * s->id_stride + s->id_offset; ids_out->stride = s->id_stride; }
   if (n == 0) return;
+  double hp[8] = {};
+  auto hp_now = [&]() { return s->host_prof ? std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count() : 0.0; };
+  hp[0] = hp_now();
   if (!reqs && !reqs16 && n > s->staged_n) { fprintf(stderr, "ydsched: NULL request array and nothing staged\n"); abort(); }
   if (n > 0x40000000ull) { fprintf(stderr, "ydsched: batch too large\n"); abort(); }
   YD_CUDA_CHECK(cudaSetDevice(s->device));
@@ -1292,6 +1378,7 @@ void WaitImpl(yd_sched* s, int64_t now_ns, const yd_task_req* reqs, const yd_tas
     float ms = 0;
     cudaEventElapsedTime(&ms, s->ev[0], s->ev[5]);
     s->stats = yd_solve_stats{};
+    s->stats_times_pending = 0;
     s->stats.total_ms = s->stats.solve_ms = ms;
     s->stats.decisions = N;
     s->stats.granted = granted;
@@ -1308,7 +1395,7 @@ void WaitImpl(yd_sched* s, int64_t now_ns, const yd_task_req* reqs, const yd_tas
   const uint32_t Nb = (uint32_t)NextPow2(N, 1024);
   // The slot table: kept across solves (all running_tasks values of every servant) while it is small enough,
   // else rebuilt per solve and clamped to the batch size.
-  const size_t static_bound = StaticSlotBound(s);
+  const size_t static_bound = S ? s->static_bound_cache : 0;  // (= StaticSlotBound(s), kept by SyncFacts)
   const bool want_static = s->solver_pref != 1 && static_bound <= kStaticSlotLimit;
   size_t slot_bound = static_bound;
   if (!want_static) {
@@ -1343,21 +1430,35 @@ void WaitImpl(yd_sched* s, int64_t now_ns, const yd_task_req* reqs, const yd_tas
   hd->now_ns = now_ns;
   hd->ring_lo = s->lo;
   hd->ring_next = s->next_id;
+  s->fsc.dyn = *hd;
 
   uint32_t launches = 0;
+  hp[1] = hp_now();
   YD_CUDA_CHECK(cudaEventRecord(s->ev[0], st));
   // The request upload runs on its own stream so that the slot table and its sort (which
   // do not read the requests) overlap it; consumers wait on ev_h2d.
-  if (reqs) {
-    YD_CUDA_CHECK(cudaMemcpyAsync(s->d_reqs.p, reqs, size_t(N) * sizeof(yd_task_req), cudaMemcpyHostToDevice,
-                                  s->st_copy));
-    s->staged_n = 0;  // the staging area now holds this batch
-  } else if (reqs16) {
-    YD_CUDA_CHECK(cudaMemcpyAsync(s->d_reqs16.p, reqs16, size_t(N) * sizeof(yd_task_req16), cudaMemcpyHostToDevice,
-                                  s->st_copy));
-    s->staged_n = 0;
-  }
-  YD_CUDA_CHECK(cudaEventRecord(s->ev_h2d, s->st_copy));
+  // (Page-locked caller arrays -- yd_alloc_host -- are not copied at all when the fused kernel runs: its first phase
+  // reads the requests over PCIe itself and, solo, its last phase writes the grants straight into the caller's array.)
+  bool uploaded = false;
+  auto upload = [&]() {
+    if (uploaded) return;
+    if (reqs) {
+      YD_CUDA_CHECK(cudaMemcpyAsync(s->d_reqs.p, reqs, size_t(N) * sizeof(yd_task_req), cudaMemcpyHostToDevice, s->st_copy));
+    } else if (reqs16) {
+      YD_CUDA_CHECK(cudaMemcpyAsync(s->d_reqs16.p, reqs16, size_t(N) * sizeof(yd_task_req16), cudaMemcpyHostToDevice, s->st_copy));
+    }
+    uploaded = true;
+  };
+  auto mapped_address = [&](const void* p) -> void* {
+    if (!p || !s->zero_copy || (reinterpret_cast<uintptr_t>(p) & 15u)) return nullptr;  // (16-byte vector accesses)
+    cudaPointerAttributes at{};
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return at.type == cudaMemoryTypeHost ? at.devicePointer : nullptr;
+  };
+  const void* in_host = reqs ? static_cast<const void*>(reqs) : static_cast<const void*>(reqs16);
+  void* const in_dev = mapped_address(in_host);
+  void* const out_dev = mapped_address(out ? static_cast<void*>(out) : static_cast<void*>(out8));
+  if (in_host) s->staged_n = 0;  // the staging area now holds this batch
   bool graphed = false;
   const uint32_t merge_rounds_cfg = s->merge_rounds, force_stream_cfg = s->force_stream;
   int merge_retry = 0, grow_attempts = 0;
@@ -1373,6 +1474,24 @@ void WaitImpl(yd_sched* s, int64_t now_ns, const yd_task_req* reqs, const yd_tas
         size_t(s->cls_bound) * ((slot_b + yd::kListTile - 1) / yd::kListTile) <= 32768) {
       variant = s->solo_hint ? 2u : 1u;
     }
+    yd_sched::CleanSig sig_now;
+    if (variant == 2) {
+      if (solver == 2) PrepareStreamBuffers(s, Nb, slot_b);  // (fixes the scratch layout the signature describes)
+      sig_now = yd_sched::CleanSig{g_buf_generation, s->z_cls_off, s->z_bytes, s->res_words, s->d_zero.p, s->d_res.p};
+      if (s->clean_valid && s->clean_sig == sig_now) variant = 3;  // no memset nodes: the graph is the kernel alone
+    }
+    s->clean_valid = false;  // (whatever runs now dirties the scratch; a completed solo solve says otherwise below)
+    // (a staged solve -- no request array in this call -- leaves its grants in HBM and copies them afterwards, so that
+    // the device-side events around it time the solve alone)
+    const bool zc_in = variant >= 1 && in_dev, zc_out = variant >= 2 && out_dev && in_host;
+    hp[2] = hp_now();
+    if (!zc_in) upload();
+    YD_CUDA_CHECK(cudaEventRecord(s->ev_h2d, s->st_copy));
+    s->fsc.zc_in = zc_in ? in_dev : nullptr;
+    s->fsc.zc_out = zc_out ? out_dev : nullptr;
+    s->fsc.seq += 1;
+    *s->h_fsc.as<yd::FusedScalars>() = s->fsc;
+    s->h_fio->done_seq = 0;
     if (s->use_graphs) {
       // make sure every buffer the sequence touches exists BEFORE capturing (no allocation
       // inside a capture), then look the size class up
@@ -1396,17 +1515,51 @@ void WaitImpl(yd_sched* s, int64_t now_ns, const yd_task_req* reqs, const yd_tas
         YD_CUDA_CHECK(cudaStreamEndCapture(st, &graph));
         cudaGraphExec_t exec = nullptr;
         YD_CUDA_CHECK(cudaGraphInstantiate(&exec, graph, 0));
-        YD_CUDA_CHECK(cudaGraphDestroy(graph));
+        yd_sched::GraphEntry ge;
+        ge.key = key; ge.exec = exec; ge.launches = l;
+        if (variant >= 2) {
+          // keep the graph: its kernel node is the handle through which the scalars are patched
+          size_t nn = 0;
+          YD_CUDA_CHECK(cudaGraphGetNodes(graph, nullptr, &nn));
+          std::vector<cudaGraphNode_t> nodes(nn);
+          YD_CUDA_CHECK(cudaGraphGetNodes(graph, nodes.data(), &nn));
+          for (cudaGraphNode_t nd : nodes) {
+            cudaGraphNodeType ty;
+            YD_CUDA_CHECK(cudaGraphNodeGetType(nd, &ty));
+            if (ty == cudaGraphNodeTypeKernel) ge.knode = nd;
+          }
+          if (!ge.knode) { fprintf(stderr, "ydsched: no kernel node in the solo graph\n"); abort(); }
+          ge.graph = graph;
+          ge.fargs = s->last_fused;
+          ge.fgrid = s->last_fused_grid;
+        } else {
+          YD_CUDA_CHECK(cudaGraphDestroy(graph));
+        }
         if (s->graphs.size() >= 16) {  // drop the oldest size class
           cudaGraphExecDestroy(s->graphs.front().exec);
+          if (s->graphs.front().graph) cudaGraphDestroy(s->graphs.front().graph);
           s->graphs.erase(s->graphs.begin());
         }
-        s->graphs.push_back({key, exec, l});
+        s->graphs.push_back(ge);
         hit = &s->graphs.back();
       }
+      if (variant >= 2) {  // this call's scalars -> the kernel node's parameters
+        hit->fargs.sc = s->fsc;
+        void* kp[1] = {&hit->fargs};
+        cudaKernelNodeParams np{};
+        np.func = reinterpret_cast<void*>(yd::k_fused_front);
+        np.gridDim = dim3(hit->fgrid);
+        np.blockDim = dim3(1024);
+        np.sharedMemBytes = 0;
+        np.kernelParams = kp;
+        np.extra = nullptr;
+        YD_CUDA_CHECK(cudaGraphExecKernelNodeSetParams(hit->exec, hit->knode, &np));
+      }
+      hp[3] = hp_now();
       YD_CUDA_CHECK(cudaEventRecord(s->ev[1], st));
       YD_CUDA_CHECK(cudaGraphLaunch(hit->exec, st));
       YD_CUDA_CHECK(cudaEventRecord(s->ev[4], st));
+      hp[4] = hp_now();
       launches += hit->launches;
       graphed = true;
     } else {
@@ -1417,11 +1570,25 @@ void WaitImpl(yd_sched* s, int64_t now_ns, const yd_task_req* reqs, const yd_tas
       launches += EnqueueSolve(s, Nb, slot_b, solver, true, false, variant, packed);
     }
     if (solver == 1) { s->order_dirty = true; s->order_static = false; }  // the row-scan solver's table overwrote the kept one
-    if (out8) YD_CUDA_CHECK(cudaMemcpyAsync(out8, s->d_out8.p, size_t(N) * sizeof(yd_grant8), cudaMemcpyDeviceToHost, st));
+    if (zc_out) {}  // the kernel wrote the grants into the caller's page-locked array
+    else if (out8) YD_CUDA_CHECK(cudaMemcpyAsync(out8, s->d_out8.p, size_t(N) * sizeof(yd_grant8), cudaMemcpyDeviceToHost, st));
     else YD_CUDA_CHECK(cudaMemcpyAsync(out, s->d_out.p, size_t(N) * sizeof(yd_grant), cudaMemcpyDeviceToHost, st));
     YD_CUDA_CHECK(cudaEventRecord(s->ev[5], st));
+    hp[5] = hp_now();
     YD_CUDA_CHECK(cudaStreamSynchronize(st));
+    hp[6] = hp_now();
+    if (variant >= 2) {  // the solo kernel's report: flags and grant count (there are no copy nodes in its graph)
+      if (s->h_fio->done_seq != s->fsc.seq) { fprintf(stderr, "ydsched: the fused kernel left no report\n"); abort(); }
+      memcpy(s->h_meta.p, const_cast<const uint32_t*>(s->h_fio->meta), 32);
+      s->h_counters.as<Counters>()->granted = s->h_fio->granted;
+    }
     if (s->dump_env && solver == 2 && S && s->n_comps) DumpStreamState(s, Nb, slot_b);
+    if (s->fused_prof && variant) {
+      unsigned long long t[9];
+      YD_CUDA_CHECK(cudaMemcpy(t, s->d_fused_prof.p, sizeof t, cudaMemcpyDeviceToHost));
+      fprintf(stderr, "ydsched: fused variant %u n %u ns: P1 %llu E1 %llu P3 %llu E2 %llu P5 %llu B3 %llu P6 %llu total %llu (+report/clean %lld)\n", variant, N,
+              t[1] - t[0], t[2] - t[1], t[3] - t[2], t[4] - t[3], t[5] - t[4], t[6] - t[5], t[7] - t[6], t[7] - t[0], (long long)(t[8] - t[7]));
+    }
     if (solver == 2 && S && s->n_comps && s->h_meta.as<uint32_t>()[1] != 0) {
       // Nothing was decided (the stream solver and the final kernels all stood down).
       const uint32_t flag = s->h_meta.as<uint32_t>()[1], ncls = s->h_meta.as<uint32_t>()[0];
@@ -1440,14 +1607,35 @@ void WaitImpl(yd_sched* s, int64_t now_ns, const yd_task_req* reqs, const yd_tas
         ++merge_retry;
       } else {
         if (s->max_comp_servants > kRowscanMaxComponent) {
-          fprintf(stderr, "ydsched: class table overflow and components too large for the row-scan solver\n");
-          abort();
+          // More classes than the class table holds AND a component beyond the row-scan solver's reach.  n sequential
+          // decisions are the first half's followed by the second half's: decide the batch as two consecutive halves
+          // (each with half the requests, hence -- eventually -- few enough classes).
+          if (N < 2) { fprintf(stderr, "ydsched: class table overflow on a single request\n"); abort(); }
+          s->merge_rounds = merge_rounds_cfg;
+          s->force_stream = force_stream_cfg;
+          std::vector<yd_task_req> r(N);
+          if (reqs) memcpy(r.data(), reqs, size_t(N) * sizeof(yd_task_req));
+          else if (reqs16) for (uint32_t i = 0; i != N; ++i) r[i] = yd_unpack_req(reqs16[i]);
+          else YD_CUDA_CHECK(cudaMemcpy(r.data(), s->d_reqs.p, size_t(N) * sizeof(yd_task_req), cudaMemcpyDeviceToHost));
+          std::vector<yd_grant> g(N);
+          const uint32_t h = N / 2;
+          WaitImpl(s, now_ns, r.data(), nullptr, h, g.data(), nullptr, nullptr);
+          WaitImpl(s, now_ns, r.data() + h, nullptr, N - h, g.data() + h, nullptr, nullptr);
+          if (out) memcpy(out, g.data(), size_t(N) * sizeof(yd_grant));
+          else for (uint32_t i = 0; i != N; ++i) out8[i] = yd_pack_grant(g[i], *ids_out);
+          s->stats.decisions = N;
+          return;
         }
         solver = 1;
       }
       continue;
     }
     if (variant == 1) s->solo_hint = s->h_meta.as<uint32_t>()[4] == 0;  // back to one launch when nothing is coupled any more
+    if (variant >= 2) {  // completed: the kernel's last block has re-initialised the scratch
+      if (variant == 2) sig_now = yd_sched::CleanSig{g_buf_generation, s->z_cls_off, s->z_bytes, s->res_words, s->d_zero.p, s->d_res.p};
+      s->clean_sig = sig_now;
+      s->clean_valid = true;
+    }
     break;
   }
   const Counters* c = s->h_counters.as<Counters>();
@@ -1455,18 +1643,10 @@ void WaitImpl(yd_sched* s, int64_t now_ns, const yd_task_req* reqs, const yd_tas
   s->merge_rounds = merge_rounds_cfg;
   s->force_stream = force_stream_cfg;
 
-  float ms = 0;
   yd_solve_stats& stt = s->stats;
   stt = yd_solve_stats{};
-  cudaEventElapsedTime(&ms, s->ev[0], s->ev[5]); stt.total_ms = ms;
-  if (graphed) {
-    // inside a graph the phases are not separable: solve_ms is the whole device pipeline
-    cudaEventElapsedTime(&ms, s->ev[1], s->ev[4]); stt.solve_ms = ms;
-  } else {
-    cudaEventElapsedTime(&ms, s->ev[1], s->ev[2]); stt.prep_ms = ms;
-    cudaEventElapsedTime(&ms, s->ev[2], s->ev[3]); stt.solve_ms = ms;
-    cudaEventElapsedTime(&ms, s->ev[3], s->ev[4]); stt.final_ms = ms;
-  }
+  // (the event arithmetic costs a driver call apiece: done when yd_last_solve_stats asks, the events stay valid until the next solve)
+  s->stats_times_pending = graphed ? 2 : 1;
   stt.decisions = N;
   stt.granted = c->granted;
   stt.kernel_launches = launches;
@@ -1474,6 +1654,11 @@ void WaitImpl(yd_sched* s, int64_t now_ns, const yd_task_req* reqs, const yd_tas
   stt.h2d_bytes = (reqs ? size_t(N) * sizeof(yd_task_req) : reqs16 ? size_t(N) * sizeof(yd_task_req16) : 0) + sizeof(yd::DynParams);
   stt.d2h_bytes = size_t(N) * (out8 ? sizeof(yd_grant8) : sizeof(yd_grant)) + sizeof(Counters) + 32;
   s->have_stats = true;
+  if (s->host_prof) {
+    hp[7] = hp_now();
+    fprintf(stderr, "ydsched: host us: prep %.1f (attrs+variant %.1f) upload+event+setparams %.1f launch %.1f d2h-enqueue %.1f sync-wait %.1f stats %.1f total %.1f\n",
+            hp[1] - hp[0], hp[2] - hp[1], hp[3] - hp[2], hp[4] - hp[3], hp[5] - hp[4], hp[6] - hp[5], hp[7] - hp[6], hp[7] - hp[0]);
+  }
   if (s->debug_env) {
     fprintf(stderr, "ydsched: solver %u graph %d merge_rounds %llu merge_chunks %llu walks %llu windows %llu solve_ms %.3f\n",
             solver, (int)graphed, c->pad[0], c->pad[1], c->pad[2], c->pad[3], stt.solve_ms);
@@ -1775,13 +1960,28 @@ uint64_t yd_num_tasks(yd_sched* s) {
 
 int yd_last_solve_stats(yd_sched* s, yd_solve_stats* out) {
   if (!s->have_stats) return 0;
+  if (s->stats_times_pending) {
+    float ms = 0;
+    yd_solve_stats& stt = s->stats;
+    cudaEventElapsedTime(&ms, s->ev[0], s->ev[5]); stt.total_ms = ms;
+    if (s->stats_times_pending == 2) {
+      // inside a graph the phases are not separable: solve_ms is the whole device pipeline
+      cudaEventElapsedTime(&ms, s->ev[1], s->ev[4]); stt.solve_ms = ms;
+    } else {
+      cudaEventElapsedTime(&ms, s->ev[1], s->ev[2]); stt.prep_ms = ms;
+      cudaEventElapsedTime(&ms, s->ev[2], s->ev[3]); stt.solve_ms = ms;
+      cudaEventElapsedTime(&ms, s->ev[3], s->ev[4]); stt.final_ms = ms;
+    }
+    s->stats_times_pending = 0;
+  }
   *out = s->stats;
   return 1;
 }
 
 void* yd_alloc_host(size_t bytes) {
   void* p = nullptr;
-  if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+  // (mapped + portable: the fused kernel reads requests from / writes grants to such arrays directly)
+  if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) return nullptr;
   return p;
 }
 void yd_free_host(void* p) {
