@@ -1,13 +1,13 @@
 #!/usr/bin/env python
 """Per-solve kernel time and DRAM traffic of the solve pipeline, measured with ncu (run on the GPU box).
 
-    python tools/ncu_traffic.py cfg2-mod cfg2-random ... > gpurun_out/r2_dram_traffic.json
+    python tools/ncu_traffic.py cfg2-mod cfg2-random ... > gpurun_out/r2f_dram_traffic.json
 
 For every workload: `ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum` over
 tools/one_solve.py, once with ncu's default cache control (every kernel starts COLD: all caches flushed) and once
 with --cache-control none (WARM: caches as the previous kernel left them, which is how the timed loop runs).  The
 last solve's kernels (from its k_cls_insert to the next lease-maintenance kernel) are summed.  Also writes the
-per-launch list of the last solve to gpurun_out/r2_launches_<workload>.csv.
+per-launch list of the last solve to gpurun_out/r2f_launches_<workload>.csv.
 """
 import csv
 import json
@@ -35,7 +35,8 @@ def run(workload: str, warm: bool):
         d[r[12]] = float(r[14].replace(",", ""))
         d[r[12] + ".unit"] = r[13]
     seq = [launches[k] for k in sorted(launches)]
-    start = max(i for i, d in enumerate(seq) if d["name"].endswith("k_cls_insert"))
+    # a solve starts with the fused front kernel, or (kernel-by-kernel pipeline) with k_cls_insert
+    start = max(i for i, d in enumerate(seq) if d["name"].endswith("k_cls_insert") or d["name"].endswith("k_fused_front"))
     solve = []
     for d in seq[start:]:
         if any(x in d["name"] for x in ("k_free", "k_tick", "k_keep_alive")):
@@ -68,10 +69,10 @@ def main():
             "warm_bytes": sum(k["dram_read"] + k["dram_write"] for k in warm),
             "sum_kernel_us": round(sum(k["us"] for k in warm), 1),
             "sum_kernel_us_cold": round(sum(k["us"] for k in cold), 1),
-            "source": "profiles/r2_dram_traffic.json (tools/ncu_traffic.py on a B200)",
+            "source": "profiles/r2f_dram_traffic.json (tools/ncu_traffic.py on a B200)",
             "launches_warm": warm, "launches_cold": cold,
         }
-        with open(OUT / f"r2_launches_{w}.csv", "w") as f:
+        with open(OUT / f"r2f_launches_{w}.csv", "w") as f:
             f.write("kernel,grid,block,us_warm,dram_read_warm,dram_write_warm,us_cold,dram_read_cold,dram_write_cold\n")
             for a, b in zip(warm, cold):
                 f.write(f"{a['kernel']},\"{a['grid']}\",\"{a['block']}\",{a['us']},{a['dram_read']},{a['dram_write']},{b['us']},{b['dram_read']},{b['dram_write']}\n")

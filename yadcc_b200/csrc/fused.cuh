@@ -91,6 +91,7 @@ struct FusedArgs {
   void* out;
   Counters* counters;
   uint32_t n_servants;
+  uint32_t loff_cache_words;  // dynamic shared memory of the launch, in words
   unsigned long long* prof;  // debug (YDSCHED_FUSED_PROF): block 0 stamps %globaltimer at every phase boundary, else null
 };
 
@@ -213,7 +214,47 @@ __device__ __forceinline__ void fused_scan_flat(uint32_t* __restrict__ data, uin
   }
 }
 
+// Solo solves skip the compacted lists: the request with FIFO rank k in class c takes the k-th member of c's list, and
+// that member is found straight from what the count phase left behind -- the scanned (class, tile) offsets (`loff`, in
+// shared memory when they fit) name the slot tile, the tile's membership ballot (32 words) names the slot, the kept
+// order's record names the servant.  Returns the verdict: a REGISTRY POSITION, kResTimeout or kResEnvNotFound.
+__device__ __forceinline__ uint32_t fused_select(uint32_t q, const FusedArgs& a, const uint32_t* __restrict__ loff) {
+  const uint32_t c = a.rcls[q];
+  if (c == kNone) return kResEnvNotFound;           // unknown digest, or one nobody holds
+  if (a.ct.cls_nelig[c] == 0) return kResEnvNotFound;  // cc:105-108
+  const uint32_t rank = a.rank_cnt[c * a.n_rtiles + q / kRankTile] - a.rank_cnt[c * a.n_rtiles] + a.rrank[q];
+  const uint32_t* row = loff + c * a.n_ltiles;
+  const uint32_t lb = row[0], le = row[a.n_ltiles];
+  if (rank >= le - lb) return kResTimeout;            // cc:116-118
+  const uint32_t target = lb + rank;
+  uint32_t lo = 0, hi = a.n_ltiles;                   // the last tile whose offset is <= target holds it
+  while (hi - lo > 1) {
+    const uint32_t mid = (lo + hi) >> 1;
+    if (row[mid] <= target) lo = mid; else hi = mid;
+  }
+  uint32_t j = target - row[lo];                      // the j-th member inside tile lo
+  const uint4* words = reinterpret_cast<const uint4*>(a.list_bal + (size_t(lo) * a.ct.cls_bound + c) * 32);
+  uint32_t w = 0, word = 0;
+  bool found = false;
+#pragma unroll 1
+  for (uint32_t v = 0; v < 8 && !found; ++v) {
+    const uint4 x = words[v];
+    const uint32_t xs[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (!found) {
+        const uint32_t p = __popc(xs[k]);
+        if (j < p) { found = true; w = v * 4 + k; word = xs[k]; }
+        else j -= p;
+      }
+    }
+  }
+  const uint32_t bit = __fns(word, 0, (int)j + 1);
+  return a.dec.rec[lo * kListTile + w * 32 + bit].x;
+}
+
 __global__ void __launch_bounds__(1024, 1) k_fused_front(FusedArgs a) {
+  extern __shared__ uint32_t s_loff[];  // solo: the scanned list offsets, when a.loff_cache_words holds them
   __shared__ unsigned long long s_seen[64];
   __shared__ DynParams s_dyn;
   __shared__ unsigned long long s_seq, s_zc_in, s_zc_out;
@@ -337,7 +378,8 @@ __global__ void __launch_bounds__(1024, 1) k_fused_front(FusedArgs a) {
   }
 
   fused_stamp(a, 4);
-  // ---- P5: per-class sorted slot lists ------------------------------------------------------------------------------
+  if (!a.solo) {
+  // ---- P5: per-class sorted slot lists (the coupled solvers read them) -------------------------------------------
   for (uint32_t tile = blockIdx.x; tile < lt_live; tile += G) {
     list_fill_tile(tile, m, a.dec, a.t, a.ct, a.n_ltiles, a.list_cnt, a.list_bal, a.list, a.list_cap);
   }
@@ -346,9 +388,7 @@ __global__ void __launch_bounds__(1024, 1) k_fused_front(FusedArgs a) {
   // ---- B3 ---------------------------------------------------------------------------------------------------------
   if (fused_arrive(a.bar, 3)) fused_release(a.bar, 3);
   else fused_wait(a.bar, 3);
-  if (*reinterpret_cast<volatile uint32_t*>(&a.ct.meta[1]) != 0) {  // a list outgrew its buffer: nothing is decided
-    if (a.solo && blockIdx.x == 0) fused_report(a, s_seq, 0);
-    return;
+  if (*reinterpret_cast<volatile uint32_t*>(&a.ct.meta[1]) != 0) return;  // a list outgrew its buffer: nothing is decided
   }
 
   fused_stamp(a, 6);
@@ -357,20 +397,29 @@ __global__ void __launch_bounds__(1024, 1) k_fused_front(FusedArgs a) {
   TaskRing ring = a.ring;
   ring.next = s_dyn.ring_next;
   void* const out = s_zc_out ? reinterpret_cast<void*>(s_zc_out) : a.out;
-  for (uint32_t tile = blockIdx.x; tile < nb_live; tile += G) {
-    const uint32_t q = tile * 1024 + tid;
-    uint32_t r = kResEnvNotFound;
-    if (q < n) {
-      uint32_t v;
-      if (rank_assign_one(q, a.n_rtiles, a.t, a.ct, a.rcls, a.rrank, a.rself, a.rank_cnt, a.list_cnt, a.n_ltiles, a.list,
-                          a.comp_mode, a.rq, a.L, v)) {
-        r = v;
-        if (!a.solo) a.res[q] = v;
-      }
+  if (a.solo) {
+    // every component with requests is data-parallel: no lists, the members are selected from the ballots
+    const uint32_t cells = nlists * a.n_ltiles + 1;
+    const uint32_t* loff = a.list_cnt;
+    if (cells <= a.loff_cache_words) {
+      for (uint32_t i = tid; i < cells; i += 1024) s_loff[i] = a.list_cnt[i];
+      __syncthreads();
+      loff = s_loff;
     }
-    if (a.solo) {
-      if (a.packed_out) final_tile<true>(tile, nb_live - 1, r, n, now_ns, rv, a.look, a.comp_sv, ring, out, a.counters, a.sv.run, a.sv.ever);
-      else final_tile<false>(tile, nb_live - 1, r, n, now_ns, rv, a.look, a.comp_sv, ring, out, a.counters, a.sv.run, a.sv.ever);
+    for (uint32_t tile = blockIdx.x; tile < nb_live; tile += G) {
+      const uint32_t q = tile * 1024 + tid;
+      const uint32_t r = q < n ? fused_select(q, a, loff) : kResEnvNotFound;
+      if (a.packed_out) final_tile<true, true>(tile, nb_live - 1, r, n, now_ns, rv, a.look, a.comp_sv, ring, out, a.counters, a.sv.run, a.sv.ever);
+      else final_tile<false, true>(tile, nb_live - 1, r, n, now_ns, rv, a.look, a.comp_sv, ring, out, a.counters, a.sv.run, a.sv.ever);
+    }
+  } else {
+    for (uint32_t tile = blockIdx.x; tile < nb_live; tile += G) {
+      const uint32_t q = tile * 1024 + tid;
+      uint32_t v;
+      if (q < n && rank_assign_one(q, a.n_rtiles, a.t, a.ct, a.rcls, a.rrank, a.rself, a.rank_cnt, a.list_cnt, a.n_ltiles,
+                                   a.list, a.comp_mode, a.rq, a.L, v)) {
+        a.res[q] = v;
+      }
     }
   }
   fused_stamp(a, 7);

@@ -140,7 +140,7 @@ __global__ void __launch_bounds__(1024) k_final_write(const uint32_t* __restrict
 // final_tile: tile `vb` of 1024 requests, r = the solver's verdict for request vb * 1024 + tid (kResEnvNotFound beyond
 // the queue's end).  Tiles below vb must be running or done.  kPacked: 8-byte grants {servant_index, status << 30 |
 // FIFO ordinal of the grant}, see yd_grant8 in ydsched.h.
-template <bool kPacked>
+template <bool kPacked, bool kPos = false>  // kPos: r is already a registry position (else an index into comp_sv)
 __device__ __forceinline__ void final_tile(uint32_t vb, uint32_t last_vb, uint32_t r, uint32_t n, long long now_ns,
                                            const ReqView& reqs, unsigned long long* __restrict__ look,
                                            const uint32_t* __restrict__ comp_sv, const TaskRing& ring,
@@ -151,7 +151,7 @@ __device__ __forceinline__ void final_tile(uint32_t vb, uint32_t last_vb, uint32
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t q = vb * 1024 + tid;
   const bool granted = r < kResTimeout;
-  if (granted) r = comp_sv[r];  // solver results index the component-ordered servant list
+  if (granted && !kPos) r = comp_sv[r];  // solver results index the component-ordered servant list
   const uint32_t bal = __ballot_sync(0xffffffffu, granted);
   if (lane == 0) warp_cnt[warp] = __popc(bal);
   __syncthreads();

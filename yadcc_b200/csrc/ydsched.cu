@@ -256,9 +256,11 @@ struct yd_sched {
     cudaGraphNode_t knode = nullptr;
     yd::FusedArgs fargs{};
     uint32_t fgrid = 0;
+    size_t fdyn = 0;
   };
   yd::FusedArgs last_fused{};  // what LaunchFused passed last (picked up right after a capture)
   uint32_t last_fused_grid = 0;
+  size_t last_fused_dyn = 0;
   bool report_dev = false;     // YDSCHED_REPORT_DEV: the solo kernel's report goes to HBM + a copy node (comparison)
   bool host_prof = false;      // YDSCHED_HOST_PROF: host-side timestamps of a solve, printed
   DevBuf d_report;
@@ -586,7 +588,8 @@ yd_sched* yd_create(const yd_config* cfg) {
   {
     int sms = 0, per_sm = 0;
     YD_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg->device));
-    YD_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, yd::k_fused_front, 1024, 0));
+    YD_CUDA_CHECK(cudaFuncSetAttribute(yd::k_fused_front, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    YD_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, yd::k_fused_front, 1024, 64 * 1024));
     s->fused_grid = per_sm >= 1 ? (uint32_t)sms : 0u;  // (0: the kernel does not fit an SM -- never on sm_100a; the pipeline is used)
   }
   s->dump_env = getenv("YDSCHED_DUMP") != nullptr;
@@ -1076,6 +1079,8 @@ uint32_t LaunchStream(yd_sched* s, uint32_t N, size_t slot_b, bool capturing) {
   return launches;
 }
 
+constexpr size_t kFusedLoffCacheWords = 16384;  // 64 KB of dynamic shared memory at most
+
 // The fused front (fused.cuh): classes, ranks, lists and the data-parallel verdicts in ONE persistent launch on `st`;
 // `solo`: grants, task ids and leases too (batches made of data-parallel components only), else the coupled solvers
 // follow.  Needs the kept slot order.
@@ -1131,9 +1136,14 @@ uint32_t LaunchFused(yd_sched* s, uint32_t N, size_t slot_b, bool capturing, boo
   a.prof = s->fused_prof ? s->d_fused_prof.as<unsigned long long>() : nullptr;
   YD_CUDA_CHECK(cudaStreamWaitEvent(st, s->ev_h2d, capturing ? cudaEventWaitExternal : 0));
   const uint32_t grid = std::min(s->fused_grid, std::max(n_rtiles, n_tiles));
-  yd::k_fused_front<<<grid, 1024, 0, st>>>(a);
+  // solo: the scanned list offsets are searched once per request -- from shared memory when they fit
+  const size_t cells = size_t(s->cls_bound) * n_tiles + 1;
+  const size_t dyn = solo && cells <= kFusedLoffCacheWords ? cells * 4 : 0;
+  a.loff_cache_words = (uint32_t)(dyn / 4);
+  yd::k_fused_front<<<grid, 1024, dyn, st>>>(a);
   s->last_fused = a;
   s->last_fused_grid = grid;
+  s->last_fused_dyn = dyn;
   if (solo && s->report_dev) {
     YD_CUDA_CHECK(cudaMemcpyAsync(s->h_fio, s->d_report.p, sizeof(yd::FusedHostIO), cudaMemcpyDeviceToHost, st));
   }
@@ -1532,6 +1542,7 @@ void WaitImpl(yd_sched* s, int64_t now_ns, const yd_task_req* reqs, const yd_tas
           ge.graph = graph;
           ge.fargs = s->last_fused;
           ge.fgrid = s->last_fused_grid;
+          ge.fdyn = s->last_fused_dyn;
         } else {
           YD_CUDA_CHECK(cudaGraphDestroy(graph));
         }
@@ -1550,7 +1561,7 @@ void WaitImpl(yd_sched* s, int64_t now_ns, const yd_task_req* reqs, const yd_tas
         np.func = reinterpret_cast<void*>(yd::k_fused_front);
         np.gridDim = dim3(hit->fgrid);
         np.blockDim = dim3(1024);
-        np.sharedMemBytes = 0;
+        np.sharedMemBytes = (unsigned)hit->fdyn;
         np.kernelParams = kp;
         np.extra = nullptr;
         YD_CUDA_CHECK(cudaGraphExecKernelNodeSetParams(hit->exec, hit->knode, &np));
