@@ -383,6 +383,31 @@ void yd_running_index_find(yd_sched* s, const char* keys, size_t n, size_t key_l
  * stay valid until the next yd_running_index_refresh. */
 int yd_running_index_entry(yd_sched* s, uint32_t snapshot_index, yd_running_task* out);
 
+/* ---- BASELINE configs[3] as one call: pre-filters + solve ------------------------------- */
+
+/* What a delegate daemon does for every task before a grant is asked, for a whole queue at once:
+ * (1) the compilation cache's bloom filter (yd_bloom_possibly_contains; a possible hit is served
+ * from the cache, distributed_cache_reader.cc:70-77), (2) the in-flight task index
+ * (yd_running_index_find; an identical task already running is joined,
+ * distributed_task_dispatcher.cc:257) and (3) yd_wait_for_starting_new_tasks over what is left,
+ * FIFO order kept.  Either filter stage is skipped when its key array is NULL. */
+typedef struct yd_prefilter {
+  const char* cache_keys; /* n fixed-length records like the bloom calls, or NULL */
+  size_t cache_key_len, cache_key_stride;
+  const char* task_digests; /* n fixed-length records like yd_running_index_find, or NULL */
+  size_t task_digest_len, task_digest_stride;
+} yd_prefilter;
+#define YD_FILTER_OFFERED 0u   /* went to the scheduler: its grant is the next unread entry of grants_out */
+#define YD_FILTER_CACHE_HIT 1u /* BloomFilter::PossiblyContains(cache key) */
+#define YD_FILTER_JOINED 2u    /* TryFindTask(task digest).has_value(), and no cache hit */
+/* verdict_out[i] (n bytes) = YD_FILTER_*; hits_out (n entries, may be NULL) = what
+ * yd_running_index_find reports for request i; grants_out (capacity n): the decisions for the
+ * OFFERED requests, in order.  Returns how many requests were offered.  Defined as the three calls
+ * above applied in that order; the CUDA backend keeps the queue in HBM between the stages. */
+size_t yd_filter_and_wait_for_starting_new_tasks(yd_sched* s, int64_t now_ns, const yd_task_req* reqs, size_t n,
+                                                 const yd_prefilter* filter, uint8_t* verdict_out,
+                                                 yd_running_hit* hits_out, yd_grant* grants_out);
+
 /* ---- introspection ------------------------------------------------------ */
 
 size_t yd_num_servants(yd_sched* s);

@@ -503,6 +503,8 @@ extern "C" int yd_running_index_entry(yd_sched* s, uint32_t i, yd_running_task* 
 #include "ydservice_impl.inc"
 #include "ydwire_impl.inc"
 
+#include "ydsched_filter_impl.inc"
+
 // ---- packed interface (yd_wait_for_starting_new_tasks_packed): defined as unpack -> the plain call -> pack --------
 extern "C" void yd_wait_for_starting_new_tasks_packed(yd_sched* s, int64_t now_ns, const yd_task_req16* reqs, size_t n,
                                                       yd_grant8* out, yd_packed_ids* ids) {

@@ -598,6 +598,49 @@ def test_cfg4_trace_with_bloom_prefilter(make_dispatcher):
     assert 0.15 < results[0][1]["found"].mean() < 0.35
 
 
+@pytest.mark.parametrize("stages", ["both", "bloom", "dedupe", "none"])
+def test_cfg4_prefiltered_solve_in_one_call(make_dispatcher, stages):
+    """yd_filter_and_wait_for_starting_new_tasks (bloom probes, in-flight index probes, compaction and solve with the
+    queue resident in HBM) against the checker, whose version of the call is its definition: the three calls in order."""
+    import numpy as np
+    from bloom_cases import tu_keys
+    from running_index_cases import task_digests
+    from yadcc_b200 import RunningTask
+
+    keys = tu_keys(6124)
+    digests = task_digests(6124, 11)
+    rng = np.random.default_rng(4)
+    cached = [k for k, m in zip(keys, rng.random(len(keys)) < 0.3) if m]
+    n = 30_000
+    tu = np.arange(n) % len(keys)
+    trace = [keys[i] for i in tu] if stages in ("both", "bloom") else None
+    trace_digests = [digests[i] for i in tu] if stages in ("both", "dedupe") else None
+    results = []
+    for kind in ("cuda", "port"):
+        d = make_dispatcher(kind)
+        w = S.config2(n, 600, 8, variant="mod", max_tasks=24)
+        w.register(d)
+        d.bloom_reset()
+        d.bloom_add(cached)
+        all_reqs = w.build_requests(d)
+        early = d.wait_for_starting_new_tasks(all_reqs[:900].copy(), 0.25)
+        locs = [d.servant_location(i) for i in range(600)]
+        by_servant = {}
+        for j, gr in enumerate(early):
+            by_servant.setdefault(int(gr["servant_index"]), []).append(
+                RunningTask(j + 1, int(gr["task_id"]), locs[int(gr["servant_index"])], digests[5000 - j]))
+        d.notify_servants_running_tasks([(locs[si], tasks) for si, tasks in by_servant.items()])
+        d.running_index_refresh()
+        verdict, hits, g = d.filter_and_wait_for_starting_new_tasks(all_reqs, trace, trace_digests, 0.5)
+        results.append((verdict.copy(), hits.copy(), g.copy(), d.servant_state()["running_tasks"].copy()))
+    for a, b in zip(results[0], results[1]):
+        assert a.shape == b.shape and (a == b).all()
+    v = results[0][0]
+    assert (v == 0).sum() == len(results[0][2])
+    if stages == "both":
+        assert (v == 1).any() and (v == 2).any()
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("seed", range(3))
 def test_running_index_matches_oracle(make_dispatcher, seed):

@@ -42,3 +42,40 @@ def test_packed_equals_plain_on_checkers(make_dispatcher, kind, name):
         d.close()
     assert S.traces_equal(*traces), S.first_mismatch(*traces)
     assert any((t["status"] == STATUS_GRANTED).any() for t in traces[1] if t.dtype == _abi.GRANT_DTYPE)
+
+
+def test_prefiltered_solve_is_the_three_calls_in_order(make_dispatcher):
+    """The checkers' yd_filter_and_wait_for_starting_new_tasks against the calls it is defined by."""
+    from bloom_cases import tu_keys
+    from running_index_cases import task_digests
+    from yadcc_b200 import RunningTask
+
+    keys, digests = tu_keys(400), task_digests(400, 11)
+    n = 2000
+    tu = np.arange(n) % len(keys)
+    trace, trace_digests = [keys[i] for i in tu], [digests[i] for i in tu]
+    out = []
+    for fused in (True, False):
+        d = make_dispatcher("port")
+        w = S.config2(n, 64, 4, variant="mod", max_tasks=16)
+        w.register(d)
+        d.bloom_reset()
+        d.bloom_add(keys[::3])
+        reqs = w.build_requests(d)
+        early = d.wait_for_starting_new_tasks(reqs[:100].copy(), 0.25)
+        locs = [d.servant_location(i) for i in range(64)]
+        for j, gr in enumerate(early):
+            if gr["status"] == STATUS_GRANTED:
+                d.notify_servant_running_tasks(locs[int(gr["servant_index"])],
+                                               [RunningTask(j + 1, int(gr["task_id"]), locs[int(gr["servant_index"])], digests[399 - j])])
+        d.running_index_refresh()
+        if fused:
+            verdict, hits, g = d.filter_and_wait_for_starting_new_tasks(reqs, trace, trace_digests, 0.5)
+        else:
+            hit = d.bloom_possibly_contains(trace)
+            hits = d.find_running_tasks(trace_digests)
+            verdict = np.where(hit, 1, np.where(hits["found"] != 0, 2, 0)).astype(np.uint8)
+            g = d.wait_for_starting_new_tasks(reqs[verdict == 0], 0.5)
+        out.append((verdict.copy(), hits.copy(), g.copy()))
+    for a, b in zip(*out):
+        assert a.shape == b.shape and (a == b).all()

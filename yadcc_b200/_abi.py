@@ -63,6 +63,14 @@ assert REQ_DTYPE.itemsize == 24 and GRANT_DTYPE.itemsize == 16 and RPC_WAIT_DTYP
 assert REQ16_DTYPE.itemsize == 16 and GRANT8_DTYPE.itemsize == 8
 
 
+class yd_prefilter(C.Structure):
+    _fields_ = [("cache_keys", C.c_void_p), ("cache_key_len", C.c_size_t), ("cache_key_stride", C.c_size_t),
+                ("task_digests", C.c_void_p), ("task_digest_len", C.c_size_t), ("task_digest_stride", C.c_size_t)]
+
+
+FILTER_OFFERED, FILTER_CACHE_HIT, FILTER_JOINED = 0, 1, 2
+
+
 class yd_config(C.Structure):
     _fields_ = [
         ("abi_version", C.c_uint32),
@@ -204,6 +212,7 @@ PROTOTYPES = [
     ("yd_notify_servants_running_tasks", C.c_size_t,
      [_P, C.POINTER(yd_heartbeat_item), C.c_size_t, C.POINTER(C.c_uint64), C.POINTER(C.c_size_t)]),
     ("yd_rpc_expanded_requests", C.c_size_t, [_P, _P, C.c_size_t]),
+    ("yd_filter_and_wait_for_starting_new_tasks", C.c_size_t, [_P, C.c_int64, _P, C.c_size_t, _P, _P, _P, _P]),
     ("yd_bloom_reset", C.c_int, [_P, C.c_uint64, C.c_uint32]),
     ("yd_bloom_load", C.c_int, [_P, _P, C.c_size_t, C.c_uint32]),
     ("yd_bloom_add", None, [_P, _P, C.c_size_t, C.c_size_t, C.c_size_t]),

@@ -34,6 +34,7 @@
 #include "tasks.cuh"
 #include "tiny.cuh"
 #include "fused.cuh"
+#include "filter.cuh"
 
 namespace {
 
@@ -278,6 +279,9 @@ struct yd_sched {
   // in-flight task index (running_index.cuh)
   std::vector<RunningRec> rt_snapshot;
   DevBuf d_rt_bytes, d_rt_off, d_rt_len, d_rt_ids, d_rt_slots, d_rt_keys, d_rt_out;
+  DevBuf d_freqs, d_fverdict, d_ftile;  // pre-filtered solve (filter.cuh): the unfiltered queue, verdicts, tile counts
+  PinBuf h_fcount;
+  cudaEvent_t ev_f[2] = {};
   uint32_t rt_mask = 0;
   size_t rt_distinct = 0;
 
@@ -598,6 +602,7 @@ yd_sched* yd_create(const yd_config* cfg) {
   YD_CUDA_CHECK(cudaStreamCreateWithFlags(&s->st2, cudaStreamNonBlocking));
   YD_CUDA_CHECK(cudaStreamCreateWithFlags(&s->st_copy, cudaStreamNonBlocking));
   for (auto& e : s->ev) YD_CUDA_CHECK(cudaEventCreate(&e));
+  for (auto& e : s->ev_f) YD_CUDA_CHECK(cudaEventCreate(&e));
   YD_CUDA_CHECK(cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming));
   YD_CUDA_CHECK(cudaEventCreateWithFlags(&s->ev_join, cudaEventDisableTiming));
   YD_CUDA_CHECK(cudaEventCreateWithFlags(&s->ev_h2d, cudaEventDisableTiming));
@@ -643,6 +648,9 @@ void yd_destroy(yd_sched* s) {
   s->d_fsc.release();
   for (PinBuf* b : {&s->h_facts, &s->h_topo, &s->h_counters, &s->h_small, &s->h_dyn, &s->h_meta, &s->h_fsc}) b->release();
   for (auto& e : s->ev) cudaEventDestroy(e);
+  for (auto& e : s->ev_f) cudaEventDestroy(e);
+  for (DevBuf* b : {&s->d_freqs, &s->d_fverdict, &s->d_ftile}) b->release();
+  s->h_fcount.release();
   cudaEventDestroy(s->ev_fork); cudaEventDestroy(s->ev_join); cudaEventDestroy(s->ev_h2d); cudaEventDestroy(s->ev_fin);
   cudaStreamDestroy(s->st2); cudaStreamDestroy(s->st_copy);
   cudaStreamDestroy(s->st);
@@ -2168,6 +2176,90 @@ int yd_running_index_entry(yd_sched* s, uint32_t i, yd_running_task* out) {
   auto&& t = s->rt_snapshot[i];
   if (out) *out = yd_running_task{t.servant_task_id, t.task_grant_id, t.servant_location.c_str(), t.task_digest.c_str()};
   return 1;
+}
+
+// BASELINE configs[3] in one call: bloom probes, in-flight index probes, order-preserving compaction and the solve,
+// with the queue resident in HBM from the first stage to the last (filter.cuh).
+size_t yd_filter_and_wait_for_starting_new_tasks(yd_sched* s, int64_t now_ns, const yd_task_req* reqs, size_t n,
+                                                 const yd_prefilter* f, uint8_t* verdict_out, yd_running_hit* hits_out,
+                                                 yd_grant* grants_out) {
+  if (n == 0) return 0;
+  if (n > 0x40000000ull) { fprintf(stderr, "ydsched: batch too large\n"); abort(); }
+  YD_CUDA_CHECK(cudaSetDevice(s->device));
+  cudaStream_t st = s->st;
+  const uint32_t N = (uint32_t)n;
+  const uint32_t nt = (N + 1023) / 1024;
+  const bool bloom = f && f->cache_keys, dedupe = f && f->task_digests;
+  if (bloom) {
+    if (!s->bloom_bits) { fprintf(stderr, "ydsched: bloom filter used before yd_bloom_reset / yd_bloom_load\n"); abort(); }
+    if (f->cache_key_len > yd::kBloomMaxKey) { fprintf(stderr, "ydsched: bloom keys longer than %d bytes\n", yd::kBloomMaxKey); abort(); }
+  }
+  s->d_freqs.ensure(size_t(N) * sizeof(yd_task_req));
+  s->d_fverdict.ensure(N);
+  s->d_ftile.ensure(size_t(nt + 1) * 4);
+  s->d_reqs.ensure(size_t(NextPow2(N, 1024)) * sizeof(yd_task_req));
+  s->h_fcount.ensure(16);
+  s->staged_n = 0;
+  // uploads: the queue, the cache keys, the task digests (one stream: each stage starts when its input has landed)
+  YD_CUDA_CHECK(cudaMemcpyAsync(s->d_freqs.p, reqs, size_t(N) * sizeof(yd_task_req), cudaMemcpyHostToDevice, st));
+  if (bloom) {
+    const size_t span = (n - 1) * f->cache_key_stride + f->cache_key_len;
+    s->d_bloom_keys.ensure(span ? span : 1);
+    s->d_bloom_out.ensure(n);
+    YD_CUDA_CHECK(cudaMemcpyAsync(s->d_bloom_keys.p, f->cache_keys, span, cudaMemcpyHostToDevice, st));
+  }
+  if (dedupe) {
+    const size_t span = (n - 1) * f->task_digest_stride + f->task_digest_len;
+    s->d_rt_keys.ensure(span ? span : 1);
+    s->d_rt_out.ensure(n * sizeof(yd_running_hit));
+    YD_CUDA_CHECK(cudaMemcpyAsync(s->d_rt_keys.p, f->task_digests, span, cudaMemcpyHostToDevice, st));
+  }
+  YD_CUDA_CHECK(cudaEventRecord(s->ev_f[0], st));
+  if (bloom) {
+    yd::k_bloom<false><<<(N + 127) / 128, 128, 0, st>>>(s->d_bloom_keys.as<unsigned char>(), N, (uint32_t)f->cache_key_len,
+                                                        f->cache_key_stride, s->bloom_hashes, s->bloom_bits - 1,
+                                                        s->d_bloom.as<uint32_t>(), s->d_bloom_out.as<uint8_t>());
+  }
+  if (dedupe) {
+    yd::k_rt_find<<<(N + 255) / 256, 256, 0, st>>>(MakeRtIndex(s), s->d_rt_keys.as<unsigned char>(), N,
+                                                   (uint32_t)f->task_digest_len, f->task_digest_stride,
+                                                   s->d_rt_ids.as<unsigned long long>(), s->d_rt_out.as<uint4>());
+  }
+  yd::k_keep_count<<<nt, 1024, 0, st>>>(bloom ? s->d_bloom_out.as<uint8_t>() : nullptr, dedupe ? s->d_rt_out.as<uint4>() : nullptr, N,
+                                        s->d_fverdict.as<uint8_t>(), s->d_ftile.as<uint32_t>());
+  yd::k_scan_u32<<<1, 1024, 0, st>>>(s->d_ftile.as<uint32_t>(), nt + 1, nullptr, 0, nullptr, 0);
+  yd::k_keep_scatter<<<nt, 1024, 0, st>>>(s->d_freqs.as<yd_task_req>(), s->d_fverdict.as<uint8_t>(), s->d_ftile.as<uint32_t>(), N,
+                                          s->d_reqs.as<yd_task_req>());
+  YD_CUDA_CHECK(cudaGetLastError());
+  YD_CUDA_CHECK(cudaEventRecord(s->ev_f[1], st));
+  YD_CUDA_CHECK(cudaMemcpyAsync(s->h_fcount.p, s->d_ftile.as<uint32_t>() + nt, 4, cudaMemcpyDeviceToHost, st));
+  YD_CUDA_CHECK(cudaMemcpyAsync(verdict_out, s->d_fverdict.p, N, cudaMemcpyDeviceToHost, st));
+  if (hits_out) {
+    if (dedupe) YD_CUDA_CHECK(cudaMemcpyAsync(hits_out, s->d_rt_out.p, n * sizeof(yd_running_hit), cudaMemcpyDeviceToHost, st));
+    else for (size_t i = 0; i != n; ++i) hits_out[i] = yd_running_hit{0, YD_NO_SERVANT, 0};
+  }
+  YD_CUDA_CHECK(cudaStreamSynchronize(st));
+  const uint32_t kept = *s->h_fcount.as<uint32_t>();
+  float filter_ms = 0;
+  cudaEventElapsedTime(&filter_ms, s->ev_f[0], s->ev_f[1]);
+  if (kept) {
+    s->staged_n = kept;  // the compaction wrote the solver's queue
+    WaitImpl(s, now_ns, nullptr, nullptr, kept, grants_out, nullptr, nullptr);
+    yd_solve_stats st2;
+    yd_last_solve_stats(s, &st2);  // (turns the solve's events into milliseconds before they are reused)
+  } else {
+    s->stats = yd_solve_stats{};
+    s->stats_times_pending = 0;
+    s->have_stats = true;
+  }
+  // stats of the whole call: prep = the filter stages + compaction (device), solve / final = the solve's, decisions = n
+  s->stats.prep_ms += filter_ms;
+  s->stats.decisions = N;
+  s->stats.kernel_launches += 3 + (bloom ? 1 : 0) + (dedupe ? 1 : 0);
+  s->stats.h2d_bytes += size_t(N) * sizeof(yd_task_req) + (bloom ? (n - 1) * f->cache_key_stride + f->cache_key_len : 0) +
+                        (dedupe ? (n - 1) * f->task_digest_stride + f->task_digest_len : 0);
+  s->stats.d2h_bytes += N + 4 + (hits_out && dedupe ? n * sizeof(yd_running_hit) : 0);
+  return kept;
 }
 
 }  // extern "C"

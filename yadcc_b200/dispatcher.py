@@ -461,6 +461,32 @@ class TaskDispatcher:
                                             out.ctypes.data)
         return out
 
+    def filter_and_wait_for_starting_new_tasks(self, reqs: np.ndarray, cache_keys=None, task_digests=None, now: float = 0.0,
+                                               out: np.ndarray | None = None):
+        """BASELINE configs[3] in one call (yd_filter_and_wait_for_starting_new_tasks): bloom pre-filter on the
+        cache keys, in-flight dedupe on the task digests, then the solve over what is left.  Returns
+        (verdicts uint8[n], hits RUNNING_HIT[n], grants GRANT[n_offered])."""
+        assert reqs.dtype == REQ_DTYPE and reqs.flags.c_contiguous
+        n = reqs.shape[0]
+        f = _abi.yd_prefilter()
+        km = dm = None
+        if cache_keys is not None:
+            km = self._key_matrix(cache_keys)
+            assert km.shape[0] >= n
+            f.cache_keys, f.cache_key_len, f.cache_key_stride = km.ctypes.data, km.shape[1], km.strides[0]
+        if task_digests is not None:
+            dm = self._key_matrix(task_digests)
+            assert dm.shape[0] >= n
+            f.task_digests, f.task_digest_len, f.task_digest_stride = dm.ctypes.data, dm.shape[1], dm.strides[0]
+        verdict = np.zeros(n, dtype=np.uint8)
+        hits = np.zeros(n, dtype=_abi.RUNNING_HIT_DTYPE)
+        if out is None:
+            out = np.zeros(max(n, 1), dtype=GRANT_DTYPE)
+        assert out.dtype == GRANT_DTYPE and out.shape[0] >= n and out.flags.c_contiguous
+        k = self._lib.yd_filter_and_wait_for_starting_new_tasks(self._h, _ns(now), reqs.ctypes.data, n, C.byref(f),
+                                                                verdict.ctypes.data, hits.ctypes.data, out.ctypes.data)
+        return verdict, hits, out[: int(k)]
+
     def running_index_entry(self, snapshot_index: int) -> RunningTask | None:
         t = _abi.yd_running_task()
         import ctypes as C
