@@ -218,7 +218,10 @@ class Cfg4Stages:
     def one_call(self, reqs: np.ndarray, now: float, out: np.ndarray):
         """The three stages as ONE C-ABI call (yd_filter_and_wait_for_starting_new_tasks): (grants, offered)."""
         n = len(reqs)
-        _, _, g = self.d.filter_and_wait_for_starting_new_tasks(reqs, self.trace[:n], self.trace_digests[:n], now, out=out)
+        if getattr(self, "verdict", None) is None or len(self.verdict) < n:
+            self.verdict = self._pinned(self.d, np.zeros(n, dtype=np.uint8))
+        _, _, g = self.d.filter_and_wait_for_starting_new_tasks(reqs, self.trace[:n], self.trace_digests[:n], now, out=out,
+                                                                verdict_out=self.verdict, want_hits=False)
         return g, len(g)
 
 

@@ -1143,7 +1143,7 @@ uint32_t LaunchFused(yd_sched* s, uint32_t N, size_t slot_b, bool capturing, boo
   a.n_servants = (uint32_t)s->sv.size();
   a.prof = s->fused_prof ? s->d_fused_prof.as<unsigned long long>() : nullptr;
   YD_CUDA_CHECK(cudaStreamWaitEvent(st, s->ev_h2d, capturing ? cudaEventWaitExternal : 0));
-  const uint32_t grid = std::min(s->fused_grid, std::max(n_rtiles, n_tiles));
+  const uint32_t grid = s->fused_grid;  // one block per SM, whatever the batch: the phases hand out tiles of two kinds
   // solo: the scanned list offsets are searched once per request -- from shared memory when they fit
   const size_t cells = size_t(s->cls_bound) * n_tiles + 1;
   const size_t dyn = solo && cells <= kFusedLoffCacheWords ? cells * 4 : 0;

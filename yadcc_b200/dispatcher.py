@@ -462,7 +462,8 @@ class TaskDispatcher:
         return out
 
     def filter_and_wait_for_starting_new_tasks(self, reqs: np.ndarray, cache_keys=None, task_digests=None, now: float = 0.0,
-                                               out: np.ndarray | None = None):
+                                               out: np.ndarray | None = None, verdict_out: np.ndarray | None = None,
+                                               want_hits: bool = True):
         """BASELINE configs[3] in one call (yd_filter_and_wait_for_starting_new_tasks): bloom pre-filter on the
         cache keys, in-flight dedupe on the task digests, then the solve over what is left.  Returns
         (verdicts uint8[n], hits RUNNING_HIT[n], grants GRANT[n_offered])."""
@@ -478,13 +479,15 @@ class TaskDispatcher:
             dm = self._key_matrix(task_digests)
             assert dm.shape[0] >= n
             f.task_digests, f.task_digest_len, f.task_digest_stride = dm.ctypes.data, dm.shape[1], dm.strides[0]
-        verdict = np.zeros(n, dtype=np.uint8)
-        hits = np.zeros(n, dtype=_abi.RUNNING_HIT_DTYPE)
+        verdict = verdict_out[:n] if verdict_out is not None else np.zeros(n, dtype=np.uint8)
+        assert verdict.dtype == np.uint8 and verdict.shape[0] == n and verdict.flags.c_contiguous
+        hits = np.zeros(n, dtype=_abi.RUNNING_HIT_DTYPE) if want_hits else None
         if out is None:
             out = np.zeros(max(n, 1), dtype=GRANT_DTYPE)
         assert out.dtype == GRANT_DTYPE and out.shape[0] >= n and out.flags.c_contiguous
         k = self._lib.yd_filter_and_wait_for_starting_new_tasks(self._h, _ns(now), reqs.ctypes.data, n, C.byref(f),
-                                                                verdict.ctypes.data, hits.ctypes.data, out.ctypes.data)
+                                                                verdict.ctypes.data, hits.ctypes.data if want_hits else None,
+                                                                out.ctypes.data)
         return verdict, hits, out[: int(k)]
 
     def running_index_entry(self, snapshot_index: int) -> RunningTask | None:
