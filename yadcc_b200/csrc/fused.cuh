@@ -92,6 +92,7 @@ struct FusedArgs {
   Counters* counters;
   uint32_t n_servants;
   uint32_t loff_cache_words;  // dynamic shared memory of the launch, in words
+  uint32_t lite;              // solo: no leader scans -- every block derives the offsets it needs from the raw counts
   unsigned long long* prof;  // debug (YDSCHED_FUSED_PROF): block 0 stamps %globaltimer at every phase boundary, else null
 };
 
@@ -146,6 +147,16 @@ __device__ __forceinline__ void fused_release(uint32_t* bar, uint32_t epoch) {
 __device__ __forceinline__ void fused_wait(uint32_t* bar, uint32_t epoch) {
   if (threadIdx.x == 0) {
     while (fused_ld_acquire(&bar[1]) < epoch) {}
+  }
+  __syncthreads();
+}
+// A barrier without a leader section: arrive, then wait for everybody's arrival (one hop).
+__device__ __forceinline__ void fused_barrier(uint32_t* bar, uint32_t epoch) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    fused_atom_add_acq_rel(&bar[0], 1u);
+    const uint32_t want = epoch * gridDim.x;
+    while (fused_ld_acquire(&bar[0]) < want) {}
   }
   __syncthreads();
 }
@@ -233,6 +244,43 @@ __device__ __forceinline__ uint32_t fused_select(uint32_t q, const FusedArgs& a,
     if (row[mid] <= target) lo = mid; else hi = mid;
   }
   uint32_t j = target - row[lo];                      // the j-th member inside tile lo
+  const uint4* words = reinterpret_cast<const uint4*>(a.list_bal + (size_t(lo) * a.ct.cls_bound + c) * 32);
+  uint32_t w = 0, word = 0;
+  bool found = false;
+#pragma unroll 1
+  for (uint32_t v = 0; v < 8 && !found; ++v) {
+    const uint4 x = words[v];
+    const uint32_t xs[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (!found) {
+        const uint32_t p = __popc(xs[k]);
+        if (j < p) { found = true; w = v * 4 + k; word = xs[k]; }
+        else j -= p;
+      }
+    }
+  }
+  const uint32_t bit = __fns(word, 0, (int)j + 1);
+  return a.dec.rec[lo * kListTile + w * 32 + bit].x;
+}
+
+// The same with block-local tables built from the RAW counts (no scan by a leader): `rows` = per class the exclusive
+// offsets of its slot tiles + its total (n_ltiles + 1 words per class), `rpre[c]` = class-c requests in the request tiles
+// before this one.
+__device__ __forceinline__ uint32_t fused_select_lite(uint32_t q, const FusedArgs& a, const uint32_t* __restrict__ rows,
+                                                       const uint32_t* __restrict__ rpre) {
+  const uint32_t c = a.rcls[q];
+  if (c == kNone) return kResEnvNotFound;
+  if (a.ct.cls_nelig[c] == 0) return kResEnvNotFound;  // cc:105-108
+  const uint32_t target = rpre[c] + a.rrank[q];
+  const uint32_t* row = rows + c * (a.n_ltiles + 1);
+  if (target >= row[a.n_ltiles]) return kResTimeout;   // cc:116-118
+  uint32_t lo = 0, hi = a.n_ltiles;
+  while (hi - lo > 1) {
+    const uint32_t mid = (lo + hi) >> 1;
+    if (row[mid] <= target) lo = mid; else hi = mid;
+  }
+  uint32_t j = target - row[lo];
   const uint4* words = reinterpret_cast<const uint4*>(a.list_bal + (size_t(lo) * a.ct.cls_bound + c) * 32);
   uint32_t w = 0, word = 0;
   bool found = false;
@@ -369,7 +417,10 @@ __global__ void __launch_bounds__(1024, 1) k_fused_front(FusedArgs a) {
 
   fused_stamp(a, 3);
   // ---- E2: both count matrices -> offsets (class-major, tile-minor, + the end cell) -------------------------------
-  if (fused_arrive(a.bar, 2)) {
+  const bool lite = a.solo && a.lite && nlists * (a.n_ltiles + 1) <= a.loff_cache_words;  // (the same in every block)
+  if (lite) {
+    fused_barrier(a.bar, 2);  // the counts stay raw: each block derives what it needs below
+  } else if (fused_arrive(a.bar, 2)) {
     fused_scan_flat(a.rank_cnt, ncls * a.n_rtiles + 1);
     fused_scan_flat(a.list_cnt, nlists * a.n_ltiles + 1);
     fused_release(a.bar, 2);
@@ -397,8 +448,43 @@ __global__ void __launch_bounds__(1024, 1) k_fused_front(FusedArgs a) {
   TaskRing ring = a.ring;
   ring.next = s_dyn.ring_next;
   void* const out = s_zc_out ? reinterpret_cast<void*>(s_zc_out) : a.out;
-  if (a.solo) {
-    // every component with requests is data-parallel: no lists, the members are selected from the ballots
+  if (a.solo && lite) {
+    // every component with requests is data-parallel: no lists, the members are selected from the ballots; the tables
+    // the selection searches are built here, per block, from the raw (class, tile) counts
+    __shared__ uint32_t s_rpre[kMaxClasses];
+    const uint32_t lane = tid & 31, warp = tid >> 5, stride = a.n_ltiles + 1;
+    for (uint32_t c = warp; c < nlists; c += 32) {  // row-local exclusive offsets of class c's slot tiles + its total
+      uint32_t running = 0;
+      for (uint32_t t0 = 0; t0 < a.n_ltiles; t0 += 32) {
+        const uint32_t t = t0 + lane;
+        const uint32_t v = t < a.n_ltiles ? a.list_cnt[c * a.n_ltiles + t] : 0u;
+        uint32_t x = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const uint32_t y = __shfl_up_sync(0xffffffffu, x, d);
+          if (lane >= d) x += y;
+        }
+        if (t < a.n_ltiles) s_loff[c * stride + t] = running + x - v;
+        running += __shfl_sync(0xffffffffu, x, 31);
+      }
+      if (lane == 0) s_loff[c * stride + a.n_ltiles] = running;
+    }
+    for (uint32_t tile = blockIdx.x; tile < nb_live; tile += G) {
+      __syncthreads();  // (s_loff is complete; s_rpre of the previous tile has been consumed)
+      for (uint32_t c = warp; c < ncls; c += 32) {  // class-c requests in the tiles before this one
+        uint32_t sum = 0;
+        for (uint32_t t = lane; t < tile; t += 32) sum += a.rank_cnt[c * a.n_rtiles + t];
+        sum = __reduce_add_sync(0xffffffffu, sum);
+        if (lane == 0) s_rpre[c] = sum;
+      }
+      __syncthreads();
+      const uint32_t q = tile * 1024 + tid;
+      const uint32_t r = q < n ? fused_select_lite(q, a, s_loff, s_rpre) : kResEnvNotFound;
+      if (a.packed_out) final_tile<true, true, true>(tile, nb_live - 1, r, n, now_ns, rv, a.look, a.comp_sv, ring, out, a.counters, a.sv.run, a.sv.ever);
+      else final_tile<false, true, true>(tile, nb_live - 1, r, n, now_ns, rv, a.look, a.comp_sv, ring, out, a.counters, a.sv.run, a.sv.ever);
+    }
+  } else if (a.solo) {
+    // (tables too big for shared memory, or YDSCHED_FUSED_NOLITE: offsets scanned by the leader of E2)
     const uint32_t cells = nlists * a.n_ltiles + 1;
     const uint32_t* loff = a.list_cnt;
     if (cells <= a.loff_cache_words) {

@@ -140,7 +140,10 @@ __global__ void __launch_bounds__(1024) k_final_write(const uint32_t* __restrict
 // final_tile: tile `vb` of 1024 requests, r = the solver's verdict for request vb * 1024 + tid (kResEnvNotFound beyond
 // the queue's end).  Tiles below vb must be running or done.  kPacked: 8-byte grants {servant_index, status << 30 |
 // FIFO ordinal of the grant}, see yd_grant8 in ydsched.h.
-template <bool kPacked, bool kPos = false>  // kPos: r is already a registry position (else an index into comp_sv)
+// kPos: r is already a registry position (else an index into comp_sv).  kFlat: the tiles run side by side (fused kernel,
+// one tile per resident block): every predecessor's COUNT is fetched, 128 per round trip, instead of walking back to
+// the nearest published prefix -- the last tile finishes one L2 round trip after the slowest predecessor has counted.
+template <bool kPacked, bool kPos = false, bool kFlat = false>
 __device__ __forceinline__ void final_tile(uint32_t vb, uint32_t last_vb, uint32_t r, uint32_t n, long long now_ns,
                                            const ReqView& reqs, unsigned long long* __restrict__ look,
                                            const uint32_t* __restrict__ comp_sv, const TaskRing& ring,
@@ -160,7 +163,26 @@ __device__ __forceinline__ void final_tile(uint32_t vb, uint32_t last_vb, uint32
     volatile unsigned long long* vl = look;
     if (lane == 0) { __threadfence(); vl[vb] = (1ull << 62) | mine; }
     unsigned long long excl = 0;
-    int at = (int)vb - 1;
+    int at = kFlat ? -1 : (int)vb - 1;
+    if (kFlat) {
+      for (uint32_t base = 0; base < vb; base += 128) {
+        unsigned long long v[4];
+        bool missing;
+        do {
+          missing = false;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint32_t idx = base + k * 32 + lane;
+            v[k] = idx < vb ? vl[idx] : (1ull << 62);
+            missing |= (v[k] >> 62) == 0;
+          }
+        } while (__any_sync(0xffffffffu, missing));
+#pragma unroll
+        for (int k = 0; k < 4; ++k) excl += v[k] & ((1ull << 62) - 1);
+      }
+#pragma unroll
+      for (int d = 16; d; d >>= 1) excl += __shfl_xor_sync(0xffffffffu, excl, d);
+    }
     while (at >= 0) {
       const int idx = at - (int)lane;
       unsigned long long v;
@@ -184,8 +206,10 @@ __device__ __forceinline__ void final_tile(uint32_t vb, uint32_t last_vb, uint32
       at -= 32;
     }
     if (lane == 0) {
-      __threadfence();
-      vl[vb] = (2ull << 62) | (excl + mine);
+      if (!kFlat) {  // (flat: the word keeps this tile's COUNT, which is what the later tiles add up)
+        __threadfence();
+        vl[vb] = (2ull << 62) | (excl + mine);
+      }
       s_excl = excl;
       if (vb == last_vb) {  // the last block knows the batch's total
         counters->granted = excl + mine;

@@ -187,7 +187,8 @@ struct yd_sched {
   // merge solver (solve_merge.cuh): per-slot verdicts and the chunk boundary states
   DevBuf d_slot_pick, d_mst_in, d_mst_out, d_stream_scratch;
   size_t z_merge_off = 0, z_layout_off = 0, z_final_off = 0, z_scan_off = 0;
-  uint32_t merge_chunk = 512, merge_rounds = 8, merge_max_chunks = 0, merge_grid = 0, merge_grid_kcap = 0;
+  uint32_t merge_chunk = 512, merge_rounds = 16, merge_max_chunks = 0, merge_grid = 0, merge_grid_kcap = 0;
+  bool merge_chunk_auto = true;  // no YDSCHED_MERGE_CHUNK: 256 slots per chunk up to 262 144 requests, 512 above
   uint32_t stream_debug = 0;   // YDSCHED_STREAM_DEBUG, read once at yd_create
   uint32_t force_stream = 0;   // yd_config.reserved bit 1 / YDSCHED_FORCE_STREAM: no merge solver for self-requests
   bool dump_env = false, debug_env = false, tiny_ok = true;
@@ -210,6 +211,7 @@ struct yd_sched {
     bool operator==(const CleanSig& o) const { return gen == o.gen && z_cls_off == o.z_cls_off && z_bytes == o.z_bytes && res_words == o.res_words && zero == o.zero && res == o.res; } };
   CleanSig clean_sig;
   bool clean_valid = false;
+  bool fused_lite = true;      // YDSCHED_FUSED_NOLITE: the solo kernel's second barrier keeps its leader scans
   bool zero_copy = true;       // YDSCHED_NO_ZEROCOPY: page-locked caller arrays are copied like pageable ones
   bool fused_prof = false;     // YDSCHED_FUSED_PROF: phase stamps of the fused kernel, printed after every solve
   DevBuf d_fused_prof;
@@ -574,7 +576,7 @@ yd_sched* yd_create(const yd_config* cfg) {
   s->use_graphs = !(cfg->reserved & 1u) && !getenv("YDSCHED_NO_GRAPH");
   s->force_stream = ((cfg->reserved & 2u) || getenv("YDSCHED_FORCE_STREAM")) ? 1u : 0u;
   if (const char* e = getenv("YDSCHED_STREAM_DEBUG")) s->stream_debug = (uint32_t)atoi(e);
-  if (const char* e = getenv("YDSCHED_MERGE_CHUNK")) s->merge_chunk = std::max(32u, (uint32_t)atoi(e) & ~31u);
+  if (const char* e = getenv("YDSCHED_MERGE_CHUNK")) { s->merge_chunk = std::max(32u, (uint32_t)atoi(e) & ~31u); s->merge_chunk_auto = false; }
   if (const char* e = getenv("YDSCHED_MERGE_ROUNDS")) s->merge_rounds = std::max(2u, (uint32_t)atoi(e));
   s->tiny_ok = !(cfg->reserved & 4u) && !getenv("YDSCHED_NO_TINY");
   s->fused_cfg = !(cfg->reserved & 8u) && !getenv("YDSCHED_NO_FUSED");
@@ -583,6 +585,7 @@ yd_sched* yd_create(const yd_config* cfg) {
   memset(s->h_fio, 0, sizeof(yd::FusedHostIO));
   YD_CUDA_CHECK(cudaHostGetDevicePointer(reinterpret_cast<void**>(&s->d_fio), s->h_fio, 0));
   s->zero_copy = getenv("YDSCHED_NO_ZEROCOPY") == nullptr;
+  s->fused_lite = getenv("YDSCHED_FUSED_NOLITE") == nullptr;
   s->report_dev = getenv("YDSCHED_REPORT_DEV") != nullptr;
   s->host_prof = getenv("YDSCHED_HOST_PROF") != nullptr;
   s->d_report.ensure(sizeof(yd::FusedHostIO));
@@ -1145,9 +1148,10 @@ uint32_t LaunchFused(yd_sched* s, uint32_t N, size_t slot_b, bool capturing, boo
   YD_CUDA_CHECK(cudaStreamWaitEvent(st, s->ev_h2d, capturing ? cudaEventWaitExternal : 0));
   const uint32_t grid = s->fused_grid;  // one block per SM, whatever the batch: the phases hand out tiles of two kinds
   // solo: the scanned list offsets are searched once per request -- from shared memory when they fit
-  const size_t cells = size_t(s->cls_bound) * n_tiles + 1;
+  const size_t cells = size_t(s->cls_bound) * (n_tiles + 1) + 1;
   const size_t dyn = solo && cells <= kFusedLoffCacheWords ? cells * 4 : 0;
   a.loff_cache_words = (uint32_t)(dyn / 4);
+  a.lite = s->fused_lite ? 1u : 0u;
   yd::k_fused_front<<<grid, 1024, dyn, st>>>(a);
   s->last_fused = a;
   s->last_fused_grid = grid;
@@ -1413,6 +1417,9 @@ void WaitImpl(yd_sched* s, int64_t now_ns, const yd_task_req* reqs, const yd_tas
   const uint32_t Nb = (uint32_t)NextPow2(N, 1024);
   // The slot table: kept across solves (all running_tasks values of every servant) while it is small enough,
   // else rebuilt per solve and clamped to the batch size.
+  // Merge-solver chunk: more, shorter chunks pay while the request-side passes are short (measured on a B200: cfg2-random
+  // 306 vs 349 us, cfg-self 181 vs 199 us at 256 vs 512 slots; at 1 M requests 551 vs 515 us)
+  if (s->merge_chunk_auto && !s->shard) s->merge_chunk = Nb <= 262144 ? 256u : 512u;
   const size_t static_bound = S ? s->static_bound_cache : 0;  // (= StaticSlotBound(s), kept by SyncFacts)
   const bool want_static = s->solver_pref != 1 && static_bound <= kStaticSlotLimit;
   size_t slot_bound = static_bound;
