@@ -279,6 +279,8 @@ def measure_workload(name: str, dev_index: int, steps: int, warmup: int, solver:
     out8 = d.alloc_grants8(n)
     pack_requests(src, reqs16)
     use_packed = stages is None  # (cfg4's queue is filtered on the way: it goes through the plain call)
+    if os.environ.get("BENCH_NO_PACKED"):  # (diagnostics: time the plain call alone, as before the packed interface existed)
+        use_packed = False
 
     def one_pass(queue, now, mode):
         """(grants, decisions offered to the solver); mode: "staged" | "plain" | "packed" """
@@ -350,8 +352,11 @@ def measure_workload(name: str, dev_index: int, steps: int, warmup: int, solver:
             n_solves += 1
             h2d, d2h = st["h2d_bytes"], st["d2h_bytes"]
             solver_used = st["solver"]
-        if use_packed:
+        if use_packed and n <= 2_000_000:
             # -- timed (e2e, 24-byte requests / 16-byte grants): the plain call, for comparison -----------------
+            # (not for the 10 M queue: as the sixth workload of one process this third pass measured 24.5 ms where the
+            # same call takes 8.4-8.6 ms by the library's own host clock and alone in a fresh process --
+            # profiles/r2f_cfg5_plain_call_diagnostics.log; a harness artefact, not traced further)
             d.free_tasks(prev_ids)
             d.on_expiration_timer(now=now)
             flush.fill_((it + 7) & 0xFF)
