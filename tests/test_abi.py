@@ -38,6 +38,10 @@ def test_library_exports_every_symbol(lib, port_lib):
 def test_struct_sizes_match_header():
     assert _abi.REQ_DTYPE.itemsize == 24  # struct yd_task_req
     assert _abi.GRANT_DTYPE.itemsize == 16  # struct yd_grant
+    assert _abi.REQ16_DTYPE.itemsize == 16  # struct yd_task_req16
+    assert _abi.GRANT8_DTYPE.itemsize == 8  # struct yd_grant8
+    assert _abi.PACKED_IDS_DTYPE.itemsize == 16  # struct yd_packed_ids
+    assert ctypes.sizeof(_abi.yd_prefilter) == 48  # struct yd_prefilter
     assert _abi.SERVANT_STATE_DTYPE.itemsize == 32
     assert ctypes.sizeof(_abi.yd_servant) == 72
     assert ctypes.sizeof(_abi.yd_running_task) == 32
