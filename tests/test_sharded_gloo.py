@@ -196,3 +196,26 @@ def test_range_sharded_queue_on_two_gloo_ranks_equals_one_scheduler(tmp_path, po
     st = one.servant_state()
     for r in range(world):
         assert (np.asarray(ranks[r][2]["running_tasks"]) == st["running_tasks"]).all()
+
+
+def test_component_digest_owner_keeps_components_together():
+    """ADVICE (round 1): with the plain crc32 map a servant advertising two compilers usually has its digests on
+    different ranks; the component-aware map derives ownership from the connected components."""
+    from yadcc_b200 import Servant
+    from yadcc_b200.sharded import ShardedDispatcher, component_digest_owner, default_digest_owner
+
+    digs = [f"{i:02x}" * 32 for i in range(12)]
+    servants = [Servant(f"10.0.0.{i}:1", None, [digs[i % 12], digs[(i * 5 + 1) % 12]] if i % 3 else [digs[i % 12]], 1, 8, 0, 0, 0, 8)
+                for i in range(40)]
+    servants.append(Servant("10.0.1.1:1", None, [], 1, 8, 0, 0, 0, 8))
+    world = 4
+    owner = component_digest_owner(servants, world)
+    for sv in servants:
+        assert len({owner(d, world) for d in sv.environments}) <= 1
+    assert owner("ff" * 32, world) == default_digest_owner("ff" * 32, world)  # a digest nobody holds
+    # the plain map does split at least one of these servants (that is what the helper is for)
+    assert any(len({default_digest_owner(d, world) for d in sv.environments}) > 1 for sv in servants)
+    sd = ShardedDispatcher.__new__(ShardedDispatcher)
+    sd.world, sd.digest_owner = world, owner
+    for sv in servants:
+        sd.owner_of_servant(sv)  # does not raise

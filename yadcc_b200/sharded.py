@@ -43,6 +43,43 @@ def default_digest_owner(digest: str, world: int) -> int:
     return zlib.crc32(digest.encode()) % world
 
 
+def component_digest_owner(servants: Sequence[Servant], world: int) -> Callable[[str, int], int]:
+    """A digest -> rank map that keeps every component (digests joined through servants that hold several of them,
+    the union-find of SyncTopology) on ONE rank: the owner is the default map applied to the component's smallest
+    digest.  Digests no listed servant holds fall back to the default map.  Build it from the servant set the ranks
+    agree on (all of them see every heartbeat) and pass it as `digest_owner`; with the plain default map a servant
+    that advertises two compilers usually has digests on different ranks and `keep_servant_alive` refuses it."""
+    parent: dict[str, str] = {}
+
+    def find(x: str) -> str:
+        parent.setdefault(x, x)
+        while parent[x] != x:
+            parent[x] = parent[parent[x]]
+            x = parent[x]
+        return x
+
+    for sv in servants:
+        envs = list(sv.environments)
+        for e in envs[1:]:
+            a, b = find(envs[0]), find(e)
+            if a != b:
+                parent[max(a, b)] = min(a, b)
+        if envs:
+            find(envs[0])
+    smallest: dict[str, str] = {}
+    for d in list(parent):
+        r = find(d)
+        smallest[r] = min(smallest.get(r, d), d)
+
+    def owner(digest: str, w: int) -> int:
+        if digest in parent:
+            return default_digest_owner(smallest[find(digest)], w)
+        return default_digest_owner(digest, w)
+
+    del world
+    return owner
+
+
 class ShardedDispatcher:
     def __init__(self, local: TaskDispatcher, rank: int, world: int, *, group=None, device=None,
                  digest_owner: Callable[[str, int], int] = default_digest_owner, id_mode: str = "strided"):
@@ -88,6 +125,10 @@ class ShardedDispatcher:
 
     def on_expiration_timer(self, *, now: float) -> None:
         self.local.on_expiration_timer(now=now)
+        # "fifo" ids: leases that expired, were orphaned or swept never come back through free_tasks; once the library
+        # holds no lease at all the whole id map is garbage
+        if self._chunks and self.local.num_tasks() == 0:
+            self._chunks = []
 
     # -- the hot path ------------------------------------------------------------
     def wait_for_starting_new_tasks(self, digests: Sequence[str], owners: np.ndarray, local_reqs: np.ndarray,
