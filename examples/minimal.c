@@ -89,6 +89,30 @@ int main(void) {
   printf("after free: %s, %llu live leases\n", grants[0].status == YD_STATUS_GRANTED ? "granted" : "not granted",
          (unsigned long long)yd_num_tasks(s));
   if (grants[0].status != YD_STATUS_GRANTED || yd_num_tasks(s) != 4) return 1;
+  /* the packed form of the same call: 16-byte requests (lease in milliseconds), 8-byte grants, ids by ordinal */
+  {
+    yd_task_req16 r16[2];
+    yd_grant8 g8[2];
+    yd_packed_ids ids;
+    uint64_t gone = grants[0].task_id;
+    yd_grant g;
+    int i;
+    for (i = 0; i < 2; ++i) {
+      r16[i].env_id = reqs[0].env_id;
+      r16[i].min_version = 8;
+      r16[i].requestor_ip = reqs[0].requestor_ip;
+      r16[i].lease = 15000u | (i == 1 ? YD_LEASE_PREFETCH : 0u);
+    }
+    yd_wait_for_starting_new_tasks_packed(s, 4 * NS, r16, 2, g8, &ids); /* every slot is taken */
+    if (yd_unpack_grant(g8[0], ids).status != YD_STATUS_TIMEOUT || yd_unpack_grant(g8[1], ids).status != YD_STATUS_TIMEOUT) return 1;
+    yd_free_tasks(s, &gone, 1);
+    yd_wait_for_starting_new_tasks_packed(s, 5 * NS, r16, 2, g8, &ids); /* one slot came back */
+    g = yd_unpack_grant(g8[0], ids);
+    printf("packed: task %llu on %s, then %s\n", (unsigned long long)g.task_id, yd_servant_location(s, g.servant_index),
+           yd_unpack_grant(g8[1], ids).status == YD_STATUS_TIMEOUT ? "timeout" : "?");
+    if (g.status != YD_STATUS_GRANTED || g.task_id != ids.first_task_id || yd_unpack_grant(g8[1], ids).status != YD_STATUS_TIMEOUT ||
+        yd_next_task_id(s) != g.task_id + 1 || yd_num_tasks(s) != 4) return 1;
+  }
   yd_destroy(s);
   puts("ok");
   return 0;
