@@ -216,8 +216,8 @@ void yd_wait_for_starting_new_tasks(yd_sched* s, int64_t now_ns, const yd_task_r
 /* The same decisions over a narrower host<->device interface: 16 bytes up and 8 bytes down per
  * decision instead of 24 + 16 (PCIe is what an end-to-end batch of 100 k decisions spends most of
  * its time on).  Nothing is lost: the lease length is a count of milliseconds on the RPC surface
- * (scheduler.proto WaitForStartingTaskRequest.next_keep_alive_in_ms; SchedulerServiceImpl multiplies
- * by 1ms, scheduler_service_impl.cc:228-231), and task ids are dense (next_task_id++ per grant,
+ * (scheduler.proto:197 WaitForStartingTaskRequest.next_keep_alive_in_ms; SchedulerServiceImpl multiplies
+ * by 1ms, scheduler_service_impl.cc:221-222), and task ids are dense (next_task_id++ per grant,
  * task_dispatcher.cc:127), so the k-th grant of a batch has id first_task_id + k * stride. */
 typedef struct yd_task_req16 {
   uint32_t env_id;       /* as yd_task_req */
